@@ -1,0 +1,217 @@
+/*
+ * laplace_b200.h -- C ABI of the B200-native graph-propagation library (liblaplace_b200.so).
+ *
+ * The reference (dream-faster/laplace-gnn-recommendation) is pure Python and has no FFI of its own;
+ * its hot path bottoms out in torch_sparse / torch_scatter / ATen kernels.  Every entry point below
+ * replaces one such call site (cited as reference file:line) and is what a ctypes binding in the
+ * reference would bind.  Conventions:
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory (outputs and workspaces are caller-allocated; *_ws_bytes tells how much);
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work and never synchronise
+ *     unless documented;
+ *   - indices handed in by the reference are int64; the library's own CSR arrays are int32
+ *     (n_rows, nnz < 2^31 is checked);
+ *   - dense operands are row-major fp32 with row stride == d;
+ *   - return value 0 = success, otherwise an LGB_E* code; lgb_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback anywhere: without a CUDA device every compute call
+ *     returns LGB_ECUDA.
+ */
+#ifndef LAPLACE_B200_H
+#define LAPLACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGB_ABI_VERSION 1
+
+enum {
+  LGB_OK = 0,
+  LGB_EINVAL = 1,   /* bad argument (null pointer, negative size, d == 0, ...) */
+  LGB_ERANGE = 2,   /* size does not fit the int32 index space */
+  LGB_EWS = 3,      /* workspace too small */
+  LGB_ECUDA = 4     /* CUDA runtime error (message has the cudaError string) */
+};
+
+int lgb_abi_version(void);
+const char* lgb_last_error(void);
+/* number of SMs of the current device (host-side query). */
+int lgb_sm_count(int* out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * CSR / CSC construction -- replaces torch_sparse.SparseTensor(row=, col=, sparse_sizes=) as called
+ * at data/lightgcn_loader.py:65-79: entries ordered by key row*n_cols+col, duplicates
+ * kept, rowptr[i] = #{e: row[e] < i}.  perm (optional) receives the stable sorting permutation.
+ * Also used per mini-batch for the hetero edge types (row = destination, col = source).
+ * ------------------------------------------------------------------------------------------- */
+int lgb_csr_build_ws_bytes(int64_t nnz, int64_t n_rows, size_t* bytes_host);
+int lgb_csr_build(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n_rows, int64_t n_cols,
+                  int32_t* rowptr, int32_t* colidx, int64_t* perm, void* ws, size_t ws_bytes, void* stream);
+
+/* CSR -> CSC: colptr[n_cols+1], rowidx[nnz], csr2csc[nnz] = argsort(col*n_rows+row) (stable).  The
+ * transposed operand of the SpMM backward (torch_sparse SPMMSum::backward; model/lightgcn.py:85-87). */
+int lgb_csr_transpose_ws_bytes(int64_t nnz, int64_t n_cols, size_t* bytes_host);
+int lgb_csr_transpose(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, int64_t n_cols,
+                      int64_t nnz, int32_t* colptr, int32_t* rowidx, int32_t* csr2csc, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* dst[i] = src[perm[i]]  (values of the transposed matrix: valT = val[csr2csc]). */
+int lgb_gather_f32(const float* src, const int32_t* perm, int64_t n, float* dst, void* stream);
+
+/* gcn_norm(adj, add_self_loops=False) -- model/lightgcn.py:56 (PyG):
+ * deg = row counts, dinv = deg^-1/2 (0 where deg == 0), val[e] = (1*dinv[row])*dinv[col]. Square matrix. */
+int lgb_gcn_norm(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz, float* dinv,
+                 float* val, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SpMM plan: rows longer than `chunk` non-zeros are split into fixed-size tasks whose partial sums
+ * are reduced in a fixed order by a second stage (deterministic, no atomics).
+ *   lgb_spmm_plan_count : counts_host[0] = #long rows, counts_host[1] = #tasks  (SYNCHRONISES the stream)
+ *   lgb_spmm_plan_fill  : long_rows[n_long] ascending, long_ptr[n_long+1] (task range per long row),
+ *                         task_row[n_tasks], task_start[n_tasks]
+ * ------------------------------------------------------------------------------------------- */
+int lgb_spmm_plan_count(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int64_t* counts_host,
+                        void* ws, size_t ws_bytes, void* stream);
+int lgb_spmm_plan_ws_bytes(int64_t n_rows, size_t* bytes_host);
+int lgb_spmm_plan_fill(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int64_t n_long,
+                       int64_t n_tasks, int32_t* long_rows, int32_t* long_ptr, int32_t* task_row,
+                       int32_t* task_start, void* ws, size_t ws_bytes, void* stream);
+
+/* Optional degree-bucketed row order: rows sorted by descending ceil(log2(deg)) bucket, stable. */
+int lgb_degree_order_ws_bytes(int64_t n_rows, size_t* bytes_host);
+int lgb_degree_order(const int32_t* rowptr, int64_t n_rows, int32_t* row_order, void* ws, size_t ws_bytes,
+                     void* stream);
+
+typedef struct lgb_csr {
+  int64_t n_rows;
+  int64_t n_cols;
+  int64_t nnz;
+  const int32_t* rowptr;     /* [n_rows+1] */
+  const int32_t* colidx;     /* [nnz] */
+  const float* val;          /* [nnz] or NULL (all ones) */
+  const int32_t* row_order;  /* [n_rows] or NULL (natural order) */
+  int32_t chunk;             /* split threshold used to build the plan (0 = no plan: every row by one warp) */
+  int32_t _pad;
+  int64_t n_long;
+  int64_t n_tasks;
+  const int32_t* long_rows;
+  const int32_t* long_ptr;
+  const int32_t* task_row;
+  const int32_t* task_start;
+} lgb_csr;
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused SpMM -- replaces torch_sparse.matmul(adj_t, x) (model/lightgcn.py:85-87), its autograd
+ * backward (same kernel on the CSC arrays), the stack/mean read-out (model/lightgcn.py:67-68) and,
+ * with val == NULL, the per-edge-type gather + scatter-{add,mean} of PyG SAGEConv
+ * (model/layers.py:9-24 -> MessagePassing.propagate -> torch_scatter).
+ *
+ *   t[r,:]  = sum_{e in row r} val[e] * X[colidx[e],:]            (val == NULL: 1)
+ *   if (flags & LGB_SPMM_MEAN)  t[r,:] /= max(deg(r), 1)
+ *   y       = t (+ resid[r,:] if resid)
+ *   if (Y)        Y[r,:]       = y
+ *   if (acc_out)  acc_out[r,:] = ((acc_in ? acc_in[r,:] : 0) + y) / acc_div
+ *
+ * X/Y/resid/acc_* are [n, d] row-major.  partial_ws must hold n_tasks*d floats when g->n_tasks > 0.
+ * ------------------------------------------------------------------------------------------- */
+#define LGB_SPMM_MEAN 1
+int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid,
+             const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws,
+             void* stream);
+
+/* scatter-max per destination (PyG aggr="max"): Y[r,:] = max_e X[colidx[e],:] (0 for empty rows),
+ * argmax[r,:] = the winning source row (or -1), used by the backward. */
+int lgb_segment_max(const lgb_csr* g, const float* X, int32_t d, float* Y, int32_t* argmax, void* stream);
+int lgb_segment_max_bwd(const float* gY, const int32_t* argmax, int64_t n_rows, int32_t d, float* gX_zeroed,
+                        void* stream);
+
+/* X[r,:] /= max(deg(r),1)  into out (mean-aggregation backward pre-scale). */
+int lgb_row_div_by_degree(const float* X, const int32_t* rowptr, int64_t n_rows, int32_t d, float* out,
+                          void* stream);
+
+/* cudaMemsetAsync(p, 0, bytes) on `stream` (gradient buffers that the atomic scatters accumulate into). */
+int lgb_zero(void* p, size_t bytes, void* stream);
+
+/* out = cat(a[na,d], b[nb,d]) * scale   (one pass; cat/split/mean backward of model/lightgcn.py:58,67-72). */
+int lgb_scale_concat(const float* a, int64_t na, const float* b, int64_t nb, int32_t d, float scale,
+                     float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused BPR -- replaces the six row gathers (run_pipeline_lightgcn.py:133-144) + bpr_loss
+ * (utils/metrics_lightgcn.py:9-45) + their autograd backward (index_put accumulate).
+ *
+ * Operand k in {u_f,u_0,p_f,p_0,n_f,n_0}: row b lives at base_k + (idx ? idx[b] : b)*d, where idx is
+ * iu for the two user operands, ip for the positives and in for the negatives.
+ *   x_b   = <u_f,p_f> - <u_f,n_f>
+ *   loss  = -(1/B) sum_b softplus(x_b) + lambda * sum_b (|u_0|^2 + |p_0|^2 + |n_0|^2)
+ * Backward (when any grad pointer is non-NULL), with g = *gout (device scalar; NULL = 1):
+ *   d u_f += -g*sigma(x_b)/B*(p_f-n_f) * gscale;  d p_f += -g*sigma/B*u_f * gscale;  d n_f += +g*sigma/B*u_f * gscale
+ *   d k_0 += 2*lambda*g*k_0
+ * With index arrays the gradient rows are accumulated with red.global.add.v4.f32 into caller-ZEROED
+ * [N,d] buffers (duplicates add up); without indices they are plain stores into [B,d] buffers.
+ * ws: 2*lgb_bpr_blocks(B) floats.  loss: device float[1].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lgb_bpr_args {
+  const float* uf; const float* u0; const float* pf; const float* p0; const float* nf; const float* n0;
+  const int64_t* iu; const int64_t* ip; const int64_t* in;   /* all three NULL, or all three set */
+  int64_t B;
+  int32_t d;
+  float lambda;
+  float gscale;            /* extra factor folded into the *_f gradients, e.g. 1/(K+1) */
+  const float* gout;       /* device scalar upstream gradient or NULL */
+  float* duf; float* du0; float* dpf; float* dp0; float* dnf; float* dn0;   /* each may be NULL */
+  float* loss;             /* device float[1], may be NULL when only gradients are wanted */
+  float* ws;
+} lgb_bpr_args;
+int64_t lgb_bpr_blocks(int64_t B);
+int lgb_bpr(const lgb_bpr_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edge decoder -- model/encoder_decoder.py:55-72.
+ *   concat: out[e, :] = [zu[row[e], :du] , zi[col[e], :di]]   (the reference's gather + cat; MLP stays cuBLAS)
+ *   dot   : out[e]    = <zu[row[e]], zi[col[e]]>              (the decoder BASELINE.json's north_star names)
+ * Backward accumulates into caller-zeroed dzu/dzi with vector atomics.
+ * ------------------------------------------------------------------------------------------- */
+int lgb_edge_concat_fwd(const float* zu, const float* zi, const int64_t* row, const int64_t* col, int64_t L,
+                        int32_t du, int32_t di, float* out, void* stream);
+int lgb_edge_concat_bwd(const float* gout, const int64_t* row, const int64_t* col, int64_t L, int32_t du,
+                        int32_t di, float* dzu_zeroed, float* dzi_zeroed, void* stream);
+int lgb_edge_dot_fwd(const float* zu, const float* zi, const int64_t* row, const int64_t* col, int64_t L,
+                     int32_t d, float* out, void* stream);
+int lgb_edge_dot_bwd(const float* zu, const float* zi, const int64_t* row, const int64_t* col,
+                     const float* gout, int64_t L, int32_t d, float* dzu_zeroed, float* dzi_zeroed,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Candidate generation -- make_predictions_for_user (utils/metrics_lightgcn.py:125-142) for a block of
+ * users: scores = Wu[u] . Wi^T (fp32 FMA, ascending-d order), seen items masked, top-k by (score desc,
+ * id asc).  seen CSR (seen_ptr[n_users_total+1], seen_idx) is indexed by user id (NULL = nothing seen).
+ * k <= 1024, d <= 512.  score_ws: n_users*n_items floats.  out_ids[u*k + j] = -1 past the last unseen item.
+ * ------------------------------------------------------------------------------------------- */
+int lgb_topk_exclude(const float* Wu, const float* Wi, const int64_t* users, int64_t n_users, int64_t n_items,
+                     int32_t d, const int32_t* seen_ptr, const int32_t* seen_idx, int32_t k, int64_t* out_ids,
+                     float* out_scores, float* score_ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Negative-sample rejection test -- the np.isin step of PyG structured_negative_sampling
+ * (data/lightgcn_loader.py:105-107): mask[j] = 1 iff key(row[j], cand[j]) is in the
+ * positive key set {row*num_nodes + col} (plus self-loop keys i*(num_nodes+1), i < num_nodes, when
+ * with_self_loops != 0).  pos_keys_sorted is the ascending int64 key array.  The random draws
+ * themselves stay on torch's CPU generator so the indices are bit-identical to the reference.
+ * ------------------------------------------------------------------------------------------- */
+int lgb_neg_reject_mask(const int64_t* row, const int64_t* cand, int64_t n, int64_t num_nodes,
+                        const int64_t* pos_keys_sorted, int64_t n_pos, int32_t with_self_loops,
+                        uint8_t* mask, void* stream);
+int lgb_sort_keys_ws_bytes(int64_t n, size_t* bytes_host);
+/* keys_out = sort(row*num_nodes + col) ascending. */
+int lgb_edge_keys_sorted(const int64_t* row, const int64_t* col, int64_t n, int64_t num_nodes,
+                         int64_t* keys_out, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAPLACE_B200_H */

@@ -1,0 +1,22 @@
+"""laplace_gnn_recommendation_b200 -- B200-native (sm_100a) graph-propagation hot path behind the
+call surface of dream-faster/laplace-gnn-recommendation's ``model/lightgcn.py`` and
+``model/encoder_decoder.py``.
+
+Only the hot path lives here: the CUDA kernels + C ABI (``csrc/``, ``include/laplace_b200.h``) and the
+host-side mirror of the reference interface (``LightGCN``, ``bpr_loss``, ``SparseTensor``, ``matmul``,
+``gcn_norm``, ``sample_mini_batch``, ``SAGEConv``, ``to_hetero``, ``Encoder_Decoder_Model`` ...).
+There is no CPU fallback: the kernels fail loudly when the shared library or a CUDA device is missing.
+"""
+from . import _lib  # noqa: F401
+from .bpr import bpr_indexed, bpr_loss  # noqa: F401
+from .csr import DeviceCSR  # noqa: F401
+from .lightgcn import LightGCN  # noqa: F401
+from .loader import sample_mini_batch, structured_negative_sampling  # noqa: F401
+from .sparse import SparseTensor, gcn_norm, matmul  # noqa: F401
+from .topk import SeenItems, make_predictions_for_user, recommend_topk, topk_dict  # noqa: F401
+
+__all__ = [
+    "LightGCN", "bpr_loss", "bpr_indexed", "SparseTensor", "matmul", "gcn_norm", "DeviceCSR",
+    "sample_mini_batch", "structured_negative_sampling", "recommend_topk", "make_predictions_for_user",
+    "SeenItems", "topk_dict",
+]

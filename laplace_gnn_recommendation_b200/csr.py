@@ -1,0 +1,204 @@
+"""Device-resident CSR graph + the fused SpMM call (host side of lgb_csr_build / lgb_spmm).
+
+HBM layout per graph (int32 indices, fp32 values):
+    rowptr[n_rows+1] | colidx[nnz] | val[nnz] (optional) | split plan (long_rows, long_ptr, task_row,
+    task_start) | optional degree-bucketed row_order[n_rows] | per-d partial-sum scratch [n_tasks, d]
+The transposed graph (CSC arrays, used by every backward) is a second DeviceCSR built lazily and cached.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import LgbCsr, check, ptr, stream
+
+DEFAULT_CHUNK = 1024  # rows with more non-zeros are split into chunk-sized tasks (see csrc/spmm.cu)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class DeviceCSR:
+    """An [n_rows, n_cols] sparse matrix in CSR form living in HBM."""
+
+    def __init__(self, n_rows: int, n_cols: int, rowptr: torch.Tensor, colidx: torch.Tensor,
+                 val: Optional[torch.Tensor] = None, chunk: int = DEFAULT_CHUNK):
+        _lib.require_cuda(rowptr, colidx, val)
+        assert rowptr.dtype == torch.int32 and colidx.dtype == torch.int32
+        self.n_rows, self.n_cols, self.nnz = int(n_rows), int(n_cols), int(colidx.numel())
+        self.rowptr, self.colidx, self.val = rowptr, colidx, val
+        self.device = rowptr.device
+        self.chunk = int(chunk)
+        self.row_order: Optional[torch.Tensor] = None
+        self.n_long = 0
+        self.n_tasks = 0
+        self.long_rows = self.long_ptr = self.task_row = self.task_start = None
+        self.perm: Optional[torch.Tensor] = None      # COO -> CSR permutation (int64) when built from COO
+        self.csr2csc: Optional[torch.Tensor] = None   # set on the TRANSPOSED graph: its entry i is CSR entry csr2csc[i]
+        self._t: Optional["DeviceCSR"] = None
+        self._partials: Dict[int, torch.Tensor] = {}
+        self._struct: Optional[LgbCsr] = None
+        if self.chunk > 0:
+            self._build_plan()
+
+    # ---- construction -------------------------------------------------------------------
+    @classmethod
+    def from_coo(cls, row: torch.Tensor, col: torch.Tensor, n_rows: int, n_cols: int,
+                 chunk: int = DEFAULT_CHUNK, want_perm: bool = False) -> "DeviceCSR":
+        """SparseTensor(row, col, sparse_sizes) semantics (reference data/lightgcn_loader.py:65-79)."""
+        _lib.require_cuda(row, col)
+        lib = _lib.load()
+        row, col = _lib.i64c(row), _lib.i64c(col)
+        nnz = row.numel()
+        dev = row.device
+        need = C.c_size_t(0)
+        check(lib.lgb_csr_build_ws_bytes(nnz, n_rows, C.byref(need)), "csr_build_ws_bytes")
+        ws = _ws(need.value, dev)
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        perm = torch.empty(nnz, dtype=torch.int64, device=dev) if want_perm else None
+        with torch.cuda.device(dev):
+            check(lib.lgb_csr_build(ptr(row), ptr(col), nnz, n_rows, n_cols, ptr(rowptr), ptr(colidx), ptr(perm),
+                                    ptr(ws), ws.numel(), stream()), "csr_build")
+        _lib.count_launch(3)
+        g = cls(n_rows, n_cols, rowptr, colidx, None, chunk)
+        g.perm = perm
+        return g
+
+    def _build_plan(self) -> None:
+        lib = _lib.load()
+        need = C.c_size_t(0)
+        check(lib.lgb_spmm_plan_ws_bytes(self.n_rows, C.byref(need)), "spmm_plan_ws_bytes")
+        ws = _ws(need.value, self.device)
+        counts = (C.c_int64 * 2)()
+        with torch.cuda.device(self.device):
+            check(lib.lgb_spmm_plan_count(ptr(self.rowptr), self.n_rows, self.chunk, counts, ptr(ws), ws.numel(),
+                                          stream()), "spmm_plan_count")
+            self.n_long, self.n_tasks = int(counts[0]), int(counts[1])
+            if self.n_long:
+                i32 = dict(dtype=torch.int32, device=self.device)
+                self.long_rows = torch.empty(self.n_long, **i32)
+                self.long_ptr = torch.empty(self.n_long + 1, **i32)
+                self.task_row = torch.empty(self.n_tasks, **i32)
+                self.task_start = torch.empty(self.n_tasks, **i32)
+                check(lib.lgb_spmm_plan_fill(ptr(self.rowptr), self.n_rows, self.chunk, self.n_long, self.n_tasks,
+                                             ptr(self.long_rows), ptr(self.long_ptr), ptr(self.task_row),
+                                             ptr(self.task_start), ptr(ws), ws.numel(), stream()), "spmm_plan_fill")
+        self._struct = None
+
+    def use_degree_order(self, on: bool = True) -> "DeviceCSR":
+        """Process ordinary rows in descending degree-bucket order (better intra-CTA balance on skewed graphs)."""
+        if not on:
+            self.row_order = None
+        elif self.row_order is None and self.n_rows:
+            lib = _lib.load()
+            need = C.c_size_t(0)
+            check(lib.lgb_degree_order_ws_bytes(self.n_rows, C.byref(need)), "degree_order_ws_bytes")
+            ws = _ws(need.value, self.device)
+            self.row_order = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib.lgb_degree_order(ptr(self.rowptr), self.n_rows, ptr(self.row_order), ptr(ws), ws.numel(),
+                                           stream()), "degree_order")
+        self._struct = None
+        return self
+
+    def with_values(self, val: Optional[torch.Tensor]) -> "DeviceCSR":
+        """Same structure (arrays and plan shared), different values."""
+        g = DeviceCSR.__new__(DeviceCSR)
+        g.__dict__.update(self.__dict__)
+        g.val = val
+        g._t = None
+        g._struct = None
+        g._partials = self._partials
+        return g
+
+    def transpose(self) -> "DeviceCSR":
+        """CSC arrays as the CSR of A^T (cached); values follow through csr2csc."""
+        if self._t is not None:
+            return self._t
+        lib = _lib.load()
+        need = C.c_size_t(0)
+        check(lib.lgb_csr_transpose_ws_bytes(self.nnz, self.n_cols, C.byref(need)), "csr_transpose_ws_bytes")
+        ws = _ws(need.value, self.device)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        colptr = torch.empty(self.n_cols + 1, **i32)
+        rowidx = torch.empty(self.nnz, **i32)
+        csr2csc = torch.empty(self.nnz, **i32)
+        with torch.cuda.device(self.device):
+            check(lib.lgb_csr_transpose(ptr(self.rowptr), ptr(self.colidx), self.n_rows, self.n_cols, self.nnz,
+                                        ptr(colptr), ptr(rowidx), ptr(csr2csc), ptr(ws), ws.numel(), stream()),
+                  "csr_transpose")
+            val_t = None
+            if self.val is not None:
+                val_t = torch.empty_like(self.val)
+                check(lib.lgb_gather_f32(ptr(self.val), ptr(csr2csc), self.nnz, ptr(val_t), stream()), "gather_f32")
+        _lib.count_launch(4)
+        t = DeviceCSR(self.n_cols, self.n_rows, colptr, rowidx, val_t, self.chunk)
+        t.csr2csc = csr2csc
+        if self.row_order is not None:
+            t.use_degree_order()
+        t._t = self
+        self._t = t
+        return t
+
+    def gcn_norm(self):
+        """(dinv, val) of gcn_norm(add_self_loops=False) -- reference model/lightgcn.py:56."""
+        if self.n_rows != self.n_cols:
+            raise RuntimeError("gcn_norm needs a square adjacency")
+        lib = _lib.load()
+        dinv = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+        val = torch.empty(self.nnz, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.lgb_gcn_norm(ptr(self.rowptr), ptr(self.colidx), self.n_rows, self.nnz, ptr(dinv), ptr(val),
+                                   stream()), "gcn_norm")
+        _lib.count_launch(2)
+        return dinv, val
+
+    # ---- C struct -----------------------------------------------------------------------
+    @property
+    def struct(self) -> LgbCsr:
+        if self._struct is None:
+            s = LgbCsr()
+            s.n_rows, s.n_cols, s.nnz = self.n_rows, self.n_cols, self.nnz
+            s.rowptr, s.colidx, s.val, s.row_order = ptr(self.rowptr), ptr(self.colidx), ptr(self.val), ptr(self.row_order)
+            s.chunk = self.chunk
+            s.n_long, s.n_tasks = self.n_long, self.n_tasks
+            s.long_rows, s.long_ptr = ptr(self.long_rows), ptr(self.long_ptr)
+            s.task_row, s.task_start = ptr(self.task_row), ptr(self.task_start)
+            self._struct = s
+        return self._struct
+
+    def _partial_ws(self, d: int) -> Optional[torch.Tensor]:
+        if self.n_tasks == 0:
+            return None
+        buf = self._partials.get(d)
+        if buf is None or buf.numel() < self.n_tasks * d:
+            buf = torch.empty(self.n_tasks * d, dtype=torch.float32, device=self.device)
+            self._partials[d] = buf
+        return buf
+
+    # ---- the hot call -------------------------------------------------------------------
+    def spmm(self, X: torch.Tensor, Y: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+             acc_in: Optional[torch.Tensor] = None, acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0,
+             mean: bool = False, want_y: bool = True) -> Optional[torch.Tensor]:
+        """Y = A @ X with the fused epilogue of lgb_spmm.  Allocates Y when want_y and Y is None."""
+        _lib.require_cuda(X)
+        if X.dim() != 2 or X.shape[0] != self.n_cols:
+            raise RuntimeError(f"spmm: X has shape {tuple(X.shape)}, expected [{self.n_cols}, d]")
+        X = _lib.f32c(X)
+        d = X.shape[1]
+        if Y is None and want_y:
+            Y = torch.empty(self.n_rows, d, dtype=torch.float32, device=self.device)
+        for name, t in (("Y", Y), ("resid", resid), ("acc_in", acc_in), ("acc_out", acc_out)):
+            if t is not None and (tuple(t.shape) != (self.n_rows, d) or not t.is_contiguous() or t.dtype != torch.float32):
+                raise RuntimeError(f"spmm: {name} must be contiguous float32 [{self.n_rows}, {d}]")
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            check(lib.lgb_spmm(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
+                               float(acc_div), 1 if mean else 0, ptr(self._partial_ws(d)), stream()), "spmm")
+        _lib.count_launch(2 if self.n_long else 1)
+        return Y

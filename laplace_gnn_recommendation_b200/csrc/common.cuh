@@ -1,0 +1,91 @@
+// Shared helpers for liblaplace_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/laplace_b200.h"
+
+namespace lgb {
+
+void set_error(const char* fmt, ...);
+
+#define LGB_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::lgb::set_error(__VA_ARGS__);   \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+#define LGB_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::lgb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                       __LINE__);                                                       \
+      return LGB_ECUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+#define LGB_LAUNCH_CHECK() LGB_CUDA(cudaGetLastError())
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ---- memory-access primitives -------------------------------------------------------------
+// Streamed, read-once data (CSR arrays): read-only path, do not allocate in L1.
+__device__ __forceinline__ int ld_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+// Gathered embedding rows: 128-bit read-only loads (rows are re-used across the grid -> keep default L2 policy).
+__device__ __forceinline__ float4 ld_gather_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+// Streaming 128-bit store (written once, read by a later kernel).
+__device__ __forceinline__ void st_f4(float4* p, const float4& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// Vector reduction into global memory (sm_90+): one 16-byte atomic instead of four scalar ones.
+__device__ __forceinline__ void red_add_f4(float4* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4& a, float w, const float4& v) {
+  a.x = fmaf(w, v.x, a.x);
+  a.y = fmaf(w, v.y, a.y);
+  a.z = fmaf(w, v.z, a.z);
+  a.w = fmaf(w, v.w, a.w);
+}
+__device__ __forceinline__ float4 f4_add(const float4& a, const float4& b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_shfl_xor(const float4& v, int off) {
+  return make_float4(__shfl_xor_sync(FULL_MASK, v.x, off), __shfl_xor_sync(FULL_MASK, v.y, off),
+                     __shfl_xor_sync(FULL_MASK, v.z, off), __shfl_xor_sync(FULL_MASK, v.w, off));
+}
+
+}  // namespace lgb

@@ -1,0 +1,386 @@
+// Fused CSR SpMM for sm_100a: Y = A @ X with the LightGCN layer-accumulate / mean / residual epilogues.
+//
+// Replaces torch_sparse.matmul (reference model/lightgcn.py:85-87), its backward (the same kernel on the
+// CSC arrays), the [N,K+1,d] stack + mean read-out (model/lightgcn.py:67-68) and, with val == NULL, PyG
+// SAGEConv's gather + scatter-{add,mean} (model/layers.py:9-24).
+//
+// Design (HBM/L2-bound gather, no tensor cores):
+//   * one warp per row (or per <=chunk-sized slice of a long row); the warp is cut into 32/G groups of G
+//     lanes, G*VPL float4 = one embedding row, so every gathered row is fetched with 128-bit
+//     ld.global.nc loads that cover whole 32-byte sectors;
+//   * the 32 (col,val) pairs of a batch are loaded coalesced (one per lane, streaming / no L1 allocate)
+//     and broadcast with __shfl_sync; UNROLL independent row gathers per lane are issued before the
+//     first FMA to keep enough bytes in flight for HBM latency;
+//   * rows longer than `chunk` were split at plan time into fixed slices; slices write partial sums
+//     that a second kernel reduces in a fixed order -> deterministic summation, no atomics;
+//   * epilogue fuses the mean division, the residual add, the layer accumulate (acc_out = (acc_in + y)/div)
+//     and lets the last layer skip writing Y altogether.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace lgb {
+
+constexpr int SPMM_WARPS = 4;  // 128-thread CTAs: fine-grained dynamic balancing across skewed degrees
+
+struct SpmmParams {
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const float* val;
+  const int32_t* row_order;
+  const int32_t* task_row;
+  const int32_t* task_start;
+  const int32_t* long_rows;
+  const int32_t* long_ptr;
+  int64_t n_rows;
+  int64_t n_tasks;
+  int64_t n_long;
+  int32_t chunk;
+  int32_t d4;  // d / 4
+  const float* X;
+  float* Y;
+  const float* resid;
+  const float* acc_in;
+  float* acc_out;
+  float acc_div;
+  int32_t mean;
+  float* partial;
+};
+
+template <int G, int VPL, int UNROLL>
+__device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int e, int lane, float4 (&acc)[VPL]) {
+  constexpr int NG = 32 / G;
+  const int grp = lane / G;
+  const int lig = lane % G;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  const int d4 = p.d4;
+  for (int base = s; base < e; base += 32) {
+    const int idx = base + lane;
+    int c = 0;
+    float w = 0.f;
+    if (idx < e) {
+      c = ld_stream_i32(p.colidx + idx);
+      w = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+    }
+    const int cnt = min(32, e - base);
+    for (int j = 0; j < cnt; j += NG * UNROLL) {
+      float4 v[UNROLL][VPL];
+      float ww[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int k = j + u * NG + grp;
+        const int cc = __shfl_sync(FULL_MASK, c, k & 31);
+        const float wk = __shfl_sync(FULL_MASK, w, k & 31);
+        const bool ok = k < cnt;
+        ww[u] = ok ? wk : 0.f;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int f = lig + q * G;
+          v[u][q] = (ok && f < d4) ? ld_gather_f4(X4 + (size_t)cc * d4 + f) : f4_zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) f4_fma(acc[q], ww[u], v[u][q]);
+    }
+  }
+  // combine the groups (fixed butterfly order)
+#pragma unroll
+  for (int off = G; off < 32; off <<= 1)
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = f4_add(acc[q], f4_shfl_xor(acc[q], off));
+}
+
+template <int G, int VPL>
+__device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg, int lig, float4 (&acc)[VPL]) {
+  const size_t rowoff = (size_t)r * p.d4;
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const int f = lig + q * G;
+    if (f >= p.d4) continue;
+    float4 y = acc[q];
+    if (p.mean) {
+      const float c = (float)max(deg, 1);
+      y.x = __fdiv_rn(y.x, c); y.y = __fdiv_rn(y.y, c); y.z = __fdiv_rn(y.z, c); y.w = __fdiv_rn(y.w, c);
+    }
+    if (p.resid) y = f4_add(y, ld_stream_f4(reinterpret_cast<const float4*>(p.resid) + rowoff + f));
+    if (p.Y) st_f4(reinterpret_cast<float4*>(p.Y) + rowoff + f, y);
+    if (p.acc_out) {
+      float4 a = y;
+      if (p.acc_in) a = f4_add(ld_stream_f4(reinterpret_cast<const float4*>(p.acc_in) + rowoff + f), y);
+      if (p.acc_div != 1.0f) {
+        a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
+        a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
+      }
+      st_f4(reinterpret_cast<float4*>(p.acc_out) + rowoff + f, a);
+    }
+  }
+}
+
+// Stage 1: slices of long rows first (heaviest work is scheduled first), then one warp per ordinary row.
+template <int G, int VPL, int UNROLL>
+__global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_rows_kernel(const SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  float4 acc[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
+
+  if (w < p.n_tasks) {
+    const int r = p.task_row[w];
+    const int s = p.task_start[w];
+    const int e = min(s + p.chunk, p.rowptr[r + 1]);
+    accumulate_slice<G, VPL, UNROLL>(p, s, e, lane, acc);
+    if (lane < G) {
+      float4* out = reinterpret_cast<float4*>(p.partial) + (size_t)w * p.d4;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int f = lane + q * G;
+        if (f < p.d4) st_f4(out + f, acc[q]);
+      }
+    }
+    return;
+  }
+  int64_t ri = w - p.n_tasks;
+  if (ri >= p.n_rows) return;
+  const int r = p.row_order ? p.row_order[ri] : (int)ri;
+  const int s = p.rowptr[r];
+  const int e = p.rowptr[r + 1];
+  if (p.chunk > 0 && e - s > p.chunk) return;  // long row: handled by its slices + stage 2
+  accumulate_slice<G, VPL, UNROLL>(p, s, e, lane, acc);
+  if (lane < G) epilogue_row<G, VPL>(p, r, e - s, lane, acc);
+}
+
+// Stage 2: one CTA per long row sums that row's partials in a fixed order, then runs the epilogue.
+template <int G, int VPL>
+__global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams p) {
+  constexpr int NGRP = 256 / G;
+  __shared__ float4 sm[NGRP][G * VPL];
+  const int L = blockIdx.x;
+  const int grp = threadIdx.x / G;
+  const int lig = threadIdx.x % G;
+  const int t0 = p.long_ptr[L], t1 = p.long_ptr[L + 1];
+  const float4* part = reinterpret_cast<const float4*>(p.partial);
+  float4 acc[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
+  for (int t = t0 + grp; t < t1; t += NGRP) {
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int f = lig + q * G;
+      if (f < p.d4) acc[q] = f4_add(acc[q], part[(size_t)t * p.d4 + f]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) sm[grp][lig + q * G] = acc[q];
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      float4 t = sm[0][lig + q * G];
+      for (int g2 = 1; g2 < NGRP; ++g2) t = f4_add(t, sm[g2][lig + q * G]);
+      acc[q] = t;
+    }
+    const int r = p.long_rows[L];
+    epilogue_row<G, VPL>(p, r, p.rowptr[r + 1] - p.rowptr[r], lig, acc);
+  }
+}
+
+// Scalar path for d % 4 != 0 (tiny test shapes): one warp per row, lane strides over the columns.
+__global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_scalar_kernel(const SpmmParams p, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  if (w >= p.n_rows) return;
+  const int r = (int)w;
+  const int s = p.rowptr[r], e = p.rowptr[r + 1];
+  for (int f = lane; f < d; f += 32) {
+    float acc = 0.f;
+    for (int i = s; i < e; ++i) acc = fmaf(p.val ? p.val[i] : 1.f, p.X[(size_t)p.colidx[i] * d + f], acc);
+    float y = acc;
+    if (p.mean) y = __fdiv_rn(y, (float)max(e - s, 1));
+    const size_t o = (size_t)r * d + f;
+    if (p.resid) y += p.resid[o];
+    if (p.Y) p.Y[o] = y;
+    if (p.acc_out) {
+      float a = p.acc_in ? p.acc_in[o] + y : y;
+      if (p.acc_div != 1.0f) a = __fdiv_rn(a, p.acc_div);
+      p.acc_out[o] = a;
+    }
+  }
+}
+
+template <int G, int VPL, int UNROLL>
+static int launch_vec(const SpmmParams& p, cudaStream_t stream) {
+  const int64_t warps = p.n_tasks + p.n_rows;
+  if (warps > 0) {
+    const int64_t blocks = (warps + SPMM_WARPS - 1) / SPMM_WARPS;
+    LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
+    spmm_rows_kernel<G, VPL, UNROLL><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  if (p.n_long > 0) {
+    spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  return LGB_OK;
+}
+
+// ---- segment max (PyG aggr="max") ----------------------------------------------------------
+__global__ void segment_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                   const float* __restrict__ X, int64_t n_rows, int d, float* __restrict__ Y,
+                                   int32_t* __restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int s = rowptr[r], e = rowptr[r + 1];
+  for (int f = lane; f < d; f += 32) {
+    float best = 0.f;
+    int arg = -1;
+    for (int i = s; i < e; ++i) {
+      const int c = colidx[i];
+      const float v = X[(size_t)c * d + f];
+      if (arg < 0 || v > best) { best = v; arg = c; }
+    }
+    Y[(size_t)r * d + f] = best;
+    if (argmax) argmax[(size_t)r * d + f] = arg;
+  }
+}
+__global__ void segment_max_bwd_kernel(const float* __restrict__ gY, const int32_t* __restrict__ argmax, int64_t total,
+                                       int d, float* __restrict__ gX) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int a = argmax[i];
+  if (a >= 0) atomicAdd(gX + (size_t)a * d + (i % d), gY[i]);
+}
+
+__global__ void row_div_kernel(const float* __restrict__ X, const int32_t* __restrict__ rowptr, int64_t n_rows, int d,
+                               float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * d) return;
+  const int64_t r = i / d;
+  out[i] = __fdiv_rn(X[i], (float)max(rowptr[r + 1] - rowptr[r], 1));
+}
+
+__global__ void scale_concat_kernel(const float4* __restrict__ a, int64_t na4, const float4* __restrict__ b, int64_t nb4,
+                                    float scale, float4* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < na4 + nb4; i += stride) {
+    float4 v = i < na4 ? (a ? ld_stream_f4(a + i) : f4_zero()) : (b ? ld_stream_f4(b + (i - na4)) : f4_zero());
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    st_f4(out + i, v);
+  }
+}
+__global__ void scale_concat_scalar_kernel(const float* __restrict__ a, int64_t na, const float* __restrict__ b,
+                                           int64_t nb, float scale, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < na + nb; i += stride) {
+    float v = i < na ? (a ? a[i] : 0.f) : (b ? b[i - na] : 0.f);
+    out[i] = v * scale;
+  }
+}
+
+}  // namespace lgb
+
+using namespace lgb;
+
+extern "C" {
+
+int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
+             float* acc_out, float acc_div, int32_t flags, float* partial_ws, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LGB_REQUIRE(g && g->rowptr && X && d > 0, LGB_EINVAL, "lgb_spmm: null graph/X or d <= 0");
+  LGB_REQUIRE(g->nnz == 0 || g->colidx, LGB_EINVAL, "lgb_spmm: null colidx");
+  LGB_REQUIRE(Y || acc_out, LGB_EINVAL, "lgb_spmm: no output requested");
+  LGB_REQUIRE(acc_div != 0.f, LGB_EINVAL, "lgb_spmm: acc_div == 0");
+  LGB_REQUIRE(g->n_rows < (1ll << 31) - 1 && g->n_cols < (1ll << 31) - 1 && g->nnz < (1ll << 31), LGB_ERANGE,
+              "lgb_spmm: size exceeds int32");
+  LGB_REQUIRE(Y != X && acc_out != X, LGB_EINVAL, "lgb_spmm: output aliases the gathered operand");
+  if (g->n_rows == 0) return LGB_OK;
+  SpmmParams p;
+  p.rowptr = g->rowptr; p.colidx = g->colidx; p.val = g->val; p.row_order = g->row_order;
+  p.task_row = g->task_row; p.task_start = g->task_start; p.long_rows = g->long_rows; p.long_ptr = g->long_ptr;
+  p.n_rows = g->n_rows; p.n_tasks = g->chunk > 0 ? g->n_tasks : 0; p.n_long = g->chunk > 0 ? g->n_long : 0;
+  p.chunk = g->chunk; p.d4 = d / 4;
+  p.X = X; p.Y = Y; p.resid = resid; p.acc_in = acc_in; p.acc_out = acc_out; p.acc_div = acc_div;
+  p.mean = (flags & LGB_SPMM_MEAN) ? 1 : 0; p.partial = partial_ws;
+  if (p.n_tasks > 0) {
+    LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->long_rows && g->long_ptr, LGB_EINVAL,
+                "lgb_spmm: plan has %lld tasks but plan arrays / partial workspace missing", (long long)p.n_tasks);
+  }
+  if (d % 4 != 0) {
+    // scalar path ignores the plan (tiny shapes only)
+    const int64_t blocks = (p.n_rows + SPMM_WARPS - 1) / SPMM_WARPS;
+    spmm_scalar_kernel<<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p, d);
+    LGB_LAUNCH_CHECK();
+    return LGB_OK;
+  }
+  const int d4 = d / 4;
+  if (d4 <= 8) return launch_vec<8, 1, 4>(p, stream);
+  if (d4 <= 16) return launch_vec<16, 1, 8>(p, stream);
+  if (d4 <= 32) return launch_vec<32, 1, 8>(p, stream);
+  if (d4 <= 64) return launch_vec<32, 2, 4>(p, stream);
+  if (d4 <= 128) return launch_vec<32, 4, 2>(p, stream);
+  set_error("lgb_spmm: d=%d > 512 not supported", d);
+  return LGB_EINVAL;
+}
+
+int lgb_segment_max(const lgb_csr* g, const float* X, int32_t d, float* Y, int32_t* argmax, void* stream) {
+  LGB_REQUIRE(g && g->rowptr && X && Y && d > 0, LGB_EINVAL, "lgb_segment_max: bad argument");
+  if (g->n_rows == 0) return LGB_OK;
+  const int warps = 4;
+  const int64_t blocks = (g->n_rows + warps - 1) / warps;
+  segment_max_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(g->rowptr, g->colidx, X, g->n_rows, d, Y,
+                                                                                argmax);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_segment_max_bwd(const float* gY, const int32_t* argmax, int64_t n_rows, int32_t d, float* gX, void* stream) {
+  LGB_REQUIRE(n_rows >= 0 && d > 0 && (n_rows == 0 || (gY && argmax && gX)), LGB_EINVAL, "lgb_segment_max_bwd: bad argument");
+  const int64_t total = n_rows * d;
+  if (total == 0) return LGB_OK;
+  segment_max_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gY, argmax, total, d, gX);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_row_div_by_degree(const float* X, const int32_t* rowptr, int64_t n_rows, int32_t d, float* out, void* stream) {
+  LGB_REQUIRE(n_rows >= 0 && d > 0 && (n_rows == 0 || (X && rowptr && out)), LGB_EINVAL,
+              "lgb_row_div_by_degree: bad argument");
+  const int64_t total = n_rows * d;
+  if (total == 0) return LGB_OK;
+  row_div_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, rowptr, n_rows, d, out);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_zero(void* p, size_t bytes, void* stream) {
+  LGB_REQUIRE(p || bytes == 0, LGB_EINVAL, "lgb_zero: null pointer");
+  if (bytes) LGB_CUDA(cudaMemsetAsync(p, 0, bytes, (cudaStream_t)stream));
+  return LGB_OK;
+}
+
+int lgb_scale_concat(const float* a, int64_t na, const float* b, int64_t nb, int32_t d, float scale, float* out,
+                     void* stream) {
+  LGB_REQUIRE(na >= 0 && nb >= 0 && d > 0 && out, LGB_EINVAL, "lgb_scale_concat: bad argument");
+  const int64_t ea = na * d, eb = nb * d;
+  if (ea + eb == 0) return LGB_OK;
+  int sms = 148;
+  const bool vec = (ea % 4 == 0) && (eb % 4 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0);
+  if (vec) {
+    const int64_t n4 = (ea + eb) / 4;
+    const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sms * 16);
+    scale_concat_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)a, ea / 4, (const float4*)b, eb / 4,
+                                                                  scale, (float4*)out);
+  } else {
+    const unsigned blocks = (unsigned)std::min<int64_t>((ea + eb + 255) / 256, (int64_t)sms * 16);
+    scale_concat_scalar_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, ea, b, eb, scale, out);
+  }
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""LightGCN with the reference's constructor / forward / attributes (model/lightgcn.py:11-87) on the
+sm_100a kernels of liblaplace_b200.
+
+HBM layout: the two embedding tables live back to back in ONE [U+I, d] fp32 buffer; ``users_emb.weight``
+and ``items_emb.weight`` are Parameters whose storage are the two row ranges of it, so E^0 = cat(Wu, Wi)
+(model/lightgcn.py:58) costs nothing and the backward hands the two gradient row-ranges of one buffer
+straight to the optimizer.  Forward keeps two ping-pong layer buffers and one accumulator:
+
+    layer 1:   Y1 = A E0        acc  = E0 + Y1            (one fused kernel)
+    layer k:   Yk = A Y(k-1)    acc += Yk
+    layer K:                    E_f  = (acc + A Y(K-1)) / (K+1)      (Y_K is never written)
+
+which replaces K SpMMs + stack + mean (+ the [N, K+1, d] tensor) of the reference.  Backward is the Horner
+form g <- A^T g + r with r = dE_f/(K+1), K launches of the same kernel on the CSC arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import check, ptr, stream
+from .bpr import bpr_indexed
+from .csr import DeviceCSR
+from .sparse import SparseTensor, gcn_norm, matmul
+
+
+def _scale_concat(a: Optional[torch.Tensor], b: Optional[torch.Tensor], na: int, nb: int, d: int, scale: float,
+                  out: torch.Tensor) -> torch.Tensor:
+    with torch.cuda.device(out.device):
+        check(_lib.load().lgb_scale_concat(ptr(a), na, ptr(b), nb, d, float(scale), ptr(out), stream()), "scale_concat")
+    _lib.count_launch()
+    return out
+
+
+def propagate_forward(g: DeviceCSR, E0: torch.Tensor, K: int) -> torch.Tensor:
+    """E_f = mean_k (A^k E0), k = 0..K, with the fused accumulate epilogue (no stack, no Y_K)."""
+    if K == 0:
+        return E0.clone()
+    N, d = E0.shape
+    E_f = torch.empty_like(E0)
+    if K == 1:
+        g.spmm(E0, want_y=False, acc_in=E0, acc_out=E_f, acc_div=2.0)
+        return E_f
+    ya = torch.empty_like(E0)
+    yb = torch.empty_like(E0) if K > 2 else None
+    g.spmm(E0, Y=ya, acc_in=E0, acc_out=E_f)
+    x, y = ya, yb
+    for _ in range(K - 2):
+        g.spmm(x, Y=y, acc_in=E_f, acc_out=E_f)
+        x, y = y, x
+    g.spmm(x, want_y=False, acc_in=E_f, acc_out=E_f, acc_div=float(K + 1))
+    return E_f
+
+
+def propagate_backward(gt: DeviceCSR, r: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dE0 = sum_{k=0..K} (A^T)^k r  via Horner: g <- A^T g + r, K times (r already holds dE_f/(K+1))."""
+    if K == 0:
+        return r
+    g = r
+    bufs = [None, None]
+    for k in range(K):
+        last = k == K - 1
+        dst = out if (last and out is not None) else bufs[k % 2]
+        if dst is None:
+            dst = torch.empty_like(r)
+            if not last:
+                bufs[k % 2] = dst
+        gt.spmm(g, Y=dst, resid=r)
+        g = dst
+    return g
+
+
+class _Propagate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Wu, Wi, model: "LightGCN", g: DeviceCSR, K: int):
+        E0 = model._table_for(Wu, Wi)
+        ctx.g, ctx.K, ctx.U = g, K, Wu.shape[0]
+        return propagate_forward(g, E0, K)
+
+    @staticmethod
+    def backward(ctx, gE):
+        K, U = ctx.K, ctx.U
+        gE = _lib.f32c(gE)
+        N, d = gE.shape
+        r = _scale_concat(gE, None, N, 0, d, 1.0 / (K + 1), torch.empty_like(gE))
+        G = propagate_backward(ctx.g.transpose(), r, K)
+        return G[:U], G[U:], None, None, None
+
+
+class LightGCN(nn.Module):
+    """Drop-in for the reference ``model.lightgcn.LightGCN`` (same ctor, forward, attributes, state_dict keys)."""
+
+    def __init__(self, num_users, num_items, embedding_dim: int, num_iterations: int, add_self_loops=False):
+        super().__init__()
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        self.embedding_dim, self.num_iterations = int(embedding_dim), int(num_iterations)
+        self.add_self_loops = add_self_loops
+        # same construction + init order as the reference (model/lightgcn.py:36-44) so seeded runs draw the same values
+        self.users_emb = nn.Embedding(num_embeddings=self.num_users, embedding_dim=self.embedding_dim)
+        self.items_emb = nn.Embedding(num_embeddings=self.num_items, embedding_dim=self.embedding_dim)
+        nn.init.normal_(self.users_emb.weight, std=0.1)
+        nn.init.normal_(self.items_emb.weight, std=0.1)
+        self._table: Optional[torch.Tensor] = None
+        self._fuse_tables()
+
+    # ---- one [U+I, d] buffer behind both Parameters ------------------------------------------
+    def _fuse_tables(self) -> None:
+        Wu, Wi = self.users_emb.weight, self.items_emb.weight
+        table = torch.empty(self.num_users + self.num_items, self.embedding_dim, dtype=Wu.dtype, device=Wu.device)
+        table[: self.num_users].copy_(Wu.data)
+        table[self.num_users:].copy_(Wi.data)
+        Wu.data = table[: self.num_users]
+        Wi.data = table[self.num_users:]
+        self._table = table
+
+    def _is_fused(self, Wu: torch.Tensor, Wi: torch.Tensor) -> bool:
+        t = self._table
+        return (t is not None and t.device == Wu.device and Wu.data_ptr() == t.data_ptr()
+                and Wi.data_ptr() == t.data_ptr() + self.num_users * self.embedding_dim * t.element_size()
+                and Wu.is_contiguous() and Wi.is_contiguous())
+
+    def _table_for(self, Wu: torch.Tensor, Wi: torch.Tensor) -> torch.Tensor:
+        """E^0 = cat(Wu, Wi) (model/lightgcn.py:58): zero-copy when the tables are fused, else one copy kernel."""
+        if self._is_fused(Wu, Wi):
+            return self._table
+        d = self.embedding_dim
+        out = torch.empty(self.num_users + self.num_items, d, dtype=torch.float32, device=Wu.device)
+        return _scale_concat(_lib.f32c(Wu.detach()), _lib.f32c(Wi.detach()), self.num_users, self.num_items, d, 1.0, out)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if not self._is_fused(self.users_emb.weight, self.items_emb.weight):
+            self._fuse_tables()
+        return out
+
+    # ---- reference API ------------------------------------------------------------------------
+    def forward(self, edge_index: SparseTensor):
+        """-> (e_u^K, e_u^0, e_i^K, e_i^0); elements 1 and 3 are the Parameters themselves, like the reference."""
+        Wu, Wi = self.users_emb.weight, self.items_emb.weight
+        _lib.require_cuda(Wu, Wi)
+        adj = gcn_norm(edge_index, add_self_loops=self.add_self_loops)   # cached per graph
+        g = adj.csr()
+        if g.n_rows != self.num_users + self.num_items or g.n_cols != g.n_rows:
+            raise RuntimeError(f"adjacency is {g.n_rows}x{g.n_cols}, expected a square matrix of "
+                               f"{self.num_users + self.num_items} nodes")
+        emb_final = _Propagate.apply(Wu, Wi, self, g, self.num_iterations)
+        users_emb_final, items_emb_final = torch.split(emb_final, [self.num_users, self.num_items])
+        return users_emb_final, Wu, items_emb_final, Wi
+
+    def propagate(self, edge_index: SparseTensor, x: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self.message_and_aggregate(edge_index, x)
+
+    def message(self, x_j: torch.Tensor) -> torch.Tensor:
+        return x_j
+
+    def message_and_aggregate(self, adj_t: SparseTensor, x: torch.Tensor) -> torch.Tensor:
+        return matmul(adj_t, x)
+
+    # ---- fused training step (no autograd graph, no gathered copies) ------------------------------
+    @torch.no_grad()
+    def fused_step(self, edge_index: SparseTensor, user_indices: torch.Tensor, pos_item_indices: torch.Tensor,
+                   neg_item_indices: torch.Tensor, lambda_val: float) -> torch.Tensor:
+        """One iteration of run_pipeline_lightgcn.py:120-158 (forward, six gathers, bpr_loss, backward) as
+        2K + 3 kernels: returns the loss (0-dim device tensor) and leaves the gradients in
+        ``users_emb.weight.grad`` / ``items_emb.weight.grad`` (overwritten, i.e. zero_grad + backward)."""
+        Wu, Wi = self.users_emb.weight, self.items_emb.weight
+        _lib.require_cuda(Wu, Wi)
+        K, U = self.num_iterations, self.num_users
+        g = gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr()
+        E0 = self._table_for(Wu, Wi)
+        N, d = E0.shape
+        E_f = propagate_forward(g, E0, K)
+        loss = torch.empty((), dtype=torch.float32, device=E0.device)
+        r = torch.empty_like(E0)
+        with torch.cuda.device(E0.device):
+            check(_lib.load().lgb_zero(ptr(r), r.numel() * 4, stream()), "zero")
+        # loss + d/dE_f (already divided by K+1), scattered with vector atomics
+        bpr_indexed(E_f, E0, U, user_indices, pos_item_indices, neg_item_indices, lambda_val, loss=loss, dE_f=r,
+                    gscale=1.0 / (K + 1))
+        if K == 0:
+            G = r
+        else:
+            G = propagate_backward(g.transpose(), r, K)
+        # + 2*lambda*E0[rows] on the layer-0 rows of the batch
+        bpr_indexed(E_f, E0, U, user_indices, pos_item_indices, neg_item_indices, lambda_val, dE_0=G)
+        Wu.grad, Wi.grad = G[:U], G[U:]
+        self.last_final = E_f
+        return loss

@@ -1,0 +1,326 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
+golden fixtures of the real reference.  Integers (CSR arrays, negative samples, top-k ids) bit-exact;
+fp32 within rtol 1e-5 (north_star)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import laplace_gnn_recommendation_b200 as lg
+from laplace_gnn_recommendation_b200.csr import DeviceCSR
+from oracle import lightgcn_oracle as lo
+from oracle import sampler_oracle as so
+from oracle import topk_oracle as to
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def close(a, b, rtol=RTOL, atol=1e-7):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), rtol=rtol, atol=atol)
+
+
+def random_graph(seed, n_rows, n_cols, nnz, skew=False):
+    g = torch.Generator().manual_seed(seed)
+    if skew:  # a few very heavy rows/cols -> exercises the split plan
+        row = (torch.rand(nnz, generator=g) ** 4 * n_rows).long().clamp(max=n_rows - 1)
+        col = (torch.rand(nnz, generator=g) ** 3 * n_cols).long().clamp(max=n_cols - 1)
+    else:
+        row = torch.randint(0, n_rows, (nnz,), generator=g)
+        col = torch.randint(0, n_cols, (nnz,), generator=g)
+    return row, col
+
+
+# ------------------------------------------------------------------ CSR / CSC / gcn_norm: bit-exact
+@pytest.mark.parametrize("shape", [(9, 9, 7), (50, 70, 400), (1000, 1000, 20000), (5, 5, 0), (3, 4, 1)])
+def test_csr_build_bit_exact(cuda_dev, shape):
+    n_rows, n_cols, nnz = shape
+    row, col = random_graph(1, n_rows, n_cols, nnz)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n_rows, n_cols, want_perm=True)
+    rowptr, c, perm = lo.csr_from_coo(row, col, n_rows, n_cols)
+    assert torch.equal(g.rowptr.cpu().long(), rowptr)
+    assert torch.equal(g.colidx.cpu().long(), c)
+    if nnz:
+        keys = row * n_cols + col
+        assert torch.equal(keys[g.perm.cpu()], lo.rows_from_rowptr(rowptr) * n_cols + c)
+    t = g.transpose()
+    colptr, r, csr2csc = lo.csc_from_csr(rowptr, c, n_cols)
+    assert torch.equal(t.rowptr.cpu().long(), colptr)
+    assert torch.equal(t.colidx.cpu().long(), r)
+    assert torch.equal(t.csr2csc.cpu().long(), csr2csc)
+
+
+def test_csr_reference_fixture_and_gcn_norm_bit_exact(cuda_dev):
+    # tests/data_generator.py:144 fixture under wiring (R)
+    row, col = torch.tensor([0, 0, 0, 1, 1, 2, 2]), torch.tensor([0, 2, 4, 1, 5, 3, 0])
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), 9, 9)
+    assert g.rowptr.tolist() == [0, 3, 5, 7, 7, 7, 7, 7, 7, 7]
+    assert g.colidx.tolist() == [0, 2, 4, 1, 5, 0, 3]
+    dinv, val = g.gcn_norm()
+    o_dinv, o_val = lo.gcn_norm_values(g.rowptr.cpu().long(), g.colidx.cpu().long())
+    assert torch.equal(dinv.cpu(), o_dinv) and torch.equal(val.cpu(), o_val)
+    row, col = random_graph(2, 3000, 3000, 50000, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), 3000, 3000)
+    dinv, val = g.gcn_norm()
+    o_dinv, o_val = lo.gcn_norm_values(g.rowptr.cpu().long(), g.colidx.cpu().long())
+    assert torch.equal(dinv.cpu(), o_dinv) and torch.equal(val.cpu(), o_val)  # IEEE sqrt/div/mul: identical bits
+
+
+# ------------------------------------------------------------------ SpMM
+@pytest.mark.parametrize("d", [4, 8, 32, 64, 84, 128, 256, 6])
+@pytest.mark.parametrize("chunk", [1024, 8, 0])
+def test_spmm_vs_oracle(cuda_dev, d, chunk):
+    n, nnz = 700, 30000
+    row, col = random_graph(d, n, n, nnz, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=chunk)
+    if chunk == 8:
+        assert g.n_long > 0 and g.n_tasks > g.n_long
+    _, val = g.gcn_norm()
+    g = g.with_values(val)
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+    rowptr, c = g.rowptr.cpu().long(), g.colidx.cpu().long()
+    want = lo.spmm(rowptr, c, val.cpu(), X)
+    close(g.spmm(X.to(cuda_dev)), want, atol=1e-6)
+    # unweighted sum and mean (hetero aggregation) on the same structure
+    g1 = g.with_values(None)
+    want1 = lo.spmm(rowptr, c, None, X)
+    close(g1.spmm(X.to(cuda_dev)), want1, rtol=1e-5, atol=1e-6 * float(want1.abs().max()))
+    deg = (rowptr[1:] - rowptr[:-1]).clamp(min=1).float().unsqueeze(1)
+    close(g1.spmm(X.to(cuda_dev), mean=True), lo.spmm(rowptr, c, None, X) / deg, rtol=1e-5, atol=1e-6)
+    # transposed operator (the backward)
+    gt = g.transpose()
+    colptr, r, csr2csc = lo.csc_from_csr(rowptr, c, n)
+    close(gt.spmm(X.to(cuda_dev)), lo.spmm(colptr, r, val.cpu()[csr2csc], X), atol=1e-6)
+
+
+def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
+    n, nnz, d = 500, 20000, 64
+    row, col = random_graph(5, n, n, nnz, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
+    _, val = g.gcn_norm()
+    g = g.with_values(val)
+    gen = torch.Generator().manual_seed(1)
+    X, R, A = (torch.randn(n, d, generator=gen) for _ in range(3))
+    base = lo.spmm(g.rowptr.cpu().long(), g.colidx.cpu().long(), val.cpu(), X)
+    for order in (False, True):
+        g.use_degree_order(order)
+        Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
+        g.spmm(X.to(cuda_dev), Y=Y, resid=R.to(cuda_dev), acc_in=A.to(cuda_dev), acc_out=acc, acc_div=4.0)
+        close(Y, base + R, atol=1e-6)
+        close(acc, (A + (base + R)) / 4.0, atol=1e-6)
+        acc2 = A.to(cuda_dev).clone()
+        g.spmm(X.to(cuda_dev), want_y=False, acc_in=acc2, acc_out=acc2)       # in-place accumulate, no Y
+        close(acc2, A + base, atol=1e-6)
+    # determinism: two launches give identical bits (no atomics in the SpMM)
+    y1, y2 = g.spmm(X.to(cuda_dev)), g.spmm(X.to(cuda_dev))
+    assert torch.equal(y1, y2)
+
+
+def test_spmm_empty_and_ragged(cuda_dev):
+    d = 64
+    g = DeviceCSR.from_coo(torch.empty(0, dtype=torch.long, device=cuda_dev), torch.empty(0, dtype=torch.long, device=cuda_dev), 10, 10)
+    assert torch.count_nonzero(g.spmm(torch.randn(10, d, device=cuda_dev))) == 0
+    # one row holds every entry, all others are empty
+    n, nnz = 40, 5000
+    row = torch.full((nnz,), 7); col = torch.randint(0, n, (nnz,), generator=torch.Generator().manual_seed(3))
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=128)
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(4))
+    want = lo.spmm(g.rowptr.cpu().long(), g.colidx.cpu().long(), None, X)
+    close(g.spmm(X.to(cuda_dev)), want, rtol=1e-5, atol=1e-4)
+    with pytest.raises(RuntimeError):
+        g.spmm(torch.randn(n + 1, d, device=cuda_dev))
+    with pytest.raises(RuntimeError):
+        g.spmm(torch.randn(n, d))  # CPU tensor: no fallback
+
+
+def test_spmm_large_properties(cuda_dev):
+    """ML-1M-shaped symmetric graph: adjointness <A x, y> == <x, A^T y>, linearity, and a float64 check
+    of sampled rows (size-independent properties; the oracle's message buffer would not fit at full scale)."""
+    U, I, E, d = 6040, 3706, 1_000_209, 64
+    gen = torch.Generator().manual_seed(1234)
+    users, items = torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)
+    row, col, n = lo.wiring_symmetric(users, items, U, I)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n)
+    assert g.nnz == 2 * E
+    dinv, val = g.gcn_norm()
+    g = g.with_values(val)
+    x = torch.randn(n, d, device=cuda_dev); y = torch.randn(n, d, device=cuda_dev)
+    Ax, Aty = g.spmm(x), g.transpose().spmm(y)
+    lhs, rhs = (Ax.double() * y.double()).sum(), (x.double() * Aty.double()).sum()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)
+    close(g.spmm(2.0 * x + y), 2.0 * Ax + g.spmm(y), rtol=1e-4, atol=1e-5)
+    close(Ax, g.transpose().spmm(x), rtol=1e-4, atol=1e-6)  # symmetric-normalised => A == A^T
+    rows = torch.randint(0, n, (64,), generator=gen)
+    rp, ci, v = g.rowptr.cpu().long(), g.colidx.cpu().long(), val.cpu().double()
+    xc = x.cpu().double()
+    for r in rows.tolist():
+        s, e = rp[r], rp[r + 1]
+        want = (v[s:e, None] * xc[ci[s:e]]).sum(0)
+        torch.testing.assert_close(Ax[r].cpu().double(), want, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ LightGCN forward/backward + BPR
+def run_case(c, dev, fused):
+    U, I, d, K = c["U"], c["I"], c["d"], c["K"]
+    model = lg.LightGCN(U, I, d, K)
+    with torch.no_grad():
+        model.users_emb.weight.copy_(c["Wu"]); model.items_emb.weight.copy_(c["Wi"])
+    model = model.to(dev)
+    adj = lg.SparseTensor(row=c["row"], col=c["col"], sparse_sizes=(U + I, U + I)).to(dev)
+    u, p, n = c["u"].to(dev), c["p"].to(dev), c["n"].to(dev)
+    if fused:
+        loss = model.fused_step(adj, u, p, n, c["lam"])
+        Ef = model.last_final
+        u_f, i_f = Ef[:U], Ef[U:]
+    else:
+        u_f, u_0, i_f, i_0 = model(adj)
+        assert u_0 is model.users_emb.weight and i_0 is model.items_emb.weight
+        loss = lg.bpr_loss(u_f[u], u_0[u], i_f[p], i_0[p], i_f[n], i_0[n], c["lam"])
+        loss.backward()
+    return loss, u_f, i_f, model.users_emb.weight.grad, model.items_emb.weight.grad
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_lightgcn_against_reference_golden(cuda_dev, golden, fused):
+    for c in golden["lightgcn"]:
+        loss, u_f, i_f, gu, gi = run_case(c, cuda_dev, fused)
+        close(u_f, c["u_final"]); close(i_f, c["i_final"])
+        close(loss, c["loss"])
+        close(gu, c["dWu"], atol=1e-9); close(gi, c["dWi"], atol=1e-9)
+
+
+@pytest.mark.parametrize("wiring", ["R", "S"])
+@pytest.mark.parametrize("K,d", [(3, 64), (1, 32), (2, 128), (0, 64), (4, 32)])
+def test_lightgcn_against_oracle(cuda_dev, wiring, K, d):
+    U, I, E, B, lam = 400, 250, 6000, 512, 1e-4
+    gen = torch.Generator().manual_seed(K * 100 + d)
+    users, items = torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)
+    row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(users, items, U, I)
+    Wu, Wi = torch.randn(U, d, generator=gen) * 0.1, torch.randn(I, d, generator=gen) * 0.1
+    pick = torch.randint(0, E, (B,), generator=gen)
+    c = dict(U=U, I=I, d=d, K=K, row=row, col=col, Wu=Wu, Wi=Wi, lam=lam,
+             u=users[pick], p=items[pick], n=torch.randint(0, I, (B,), generator=gen))
+    rowptr, cc, _ = lo.csr_from_coo(row, col, n, n)
+    o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(Wu, Wi, rowptr, cc, K, c["u"], c["p"], c["n"], lam)
+    for fused in (False, True):
+        loss, u_f, i_f, gu, gi = run_case(c, cuda_dev, fused)
+        close(u_f, o_uf); close(i_f, o_if); close(loss, o_loss)
+        close(gu, o_gu, atol=1e-9); close(gi, o_gi, atol=1e-9)
+
+
+def test_bpr_against_reference_golden(cuda_dev, golden):
+    for c in golden["bpr"]:
+        xs = [x.to(cuda_dev).requires_grad_(True) for x in c["inputs"]]
+        loss = lg.bpr_loss(*xs, c["lam"])
+        (loss * 1.0).backward()
+        close(loss, c["loss"])
+        for x, g in zip(xs, c["grads"]):
+            close(x.grad, g, atol=1e-9)
+    # upstream gradient is honoured
+    xs = [x.to(cuda_dev).requires_grad_(True) for x in golden["bpr"][0]["inputs"]]
+    (lg.bpr_loss(*xs, 1e-6) * 3.0).backward()
+    close(xs[0].grad, 3.0 * golden["bpr"][0]["grads"][0], atol=1e-9)
+
+
+def test_bpr_full_split_size(cuda_dev):
+    """evaluation() runs bpr_loss over every edge of a split (B = E_split): many CTAs + the finalize pass."""
+    gen = torch.Generator().manual_seed(9)
+    B, d = 200_003, 64
+    xs = [torch.randn(B, d, generator=gen) * 0.3 for _ in range(6)]
+    want = lo.bpr_loss(*xs, 1e-6)
+    got = lg.bpr_loss(*[x.to(cuda_dev) for x in xs], 1e-6)
+    close(got, want, rtol=1e-5)
+
+
+def test_module_contract(cuda_dev):
+    """Attributes / state_dict / optimizer behaviour the reference driver relies on."""
+    m = lg.LightGCN(7, 5, 16, 2).to(cuda_dev)
+    assert [k for k in m.state_dict()] == ["users_emb.weight", "items_emb.weight"]
+    assert len(list(m.parameters())) == 2
+    assert m.users_emb.weight.shape == (7, 16) and m.items_emb.weight.shape == (5, 16)
+    assert m._is_fused(m.users_emb.weight, m.items_emb.weight)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    adj = lg.SparseTensor(row=torch.tensor([0, 1, 7, 8]), col=torch.tensor([7, 8, 0, 1]), sparse_sizes=(12, 12)).to(cuda_dev)
+    before = m.items_emb.weight.detach().clone()
+    for _ in range(2):
+        u_f, u_0, i_f, i_0 = m(adj)
+        idx = torch.tensor([0, 1], device=cuda_dev)
+        loss = lg.bpr_loss(u_f[idx], u_0[idx], i_f[idx], i_0[idx], i_f[idx + 1], i_0[idx + 1], 1e-3)
+        opt.zero_grad(); loss.backward(); opt.step()
+    assert not torch.equal(before, m.items_emb.weight.detach())
+    assert m._is_fused(m.users_emb.weight, m.items_emb.weight)  # in-place optimizer updates keep the fused table
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m2 = lg.LightGCN(7, 5, 16, 2).to(cuda_dev)
+    m2.load_state_dict(sd)
+    close(m2(adj)[0], m(adj)[0])
+
+
+# ------------------------------------------------------------------ sampler: bit-exact indices
+def test_sample_mini_batch_bit_exact_vs_reference_golden(cuda_dev, golden):
+    g = golden["loader"]
+    torch.manual_seed(g["seed"]); random.seed(g["seed"]); np.random.seed(g["seed"])
+    tr = g["train"].to(cuda_dev)
+    for want in g["batches"]:
+        got = torch.stack(lg.sample_mini_batch(g["batch_size"], tr))
+        assert got.device.type == "cpu" and got.dtype == torch.int64
+        assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("loops", [True, False])
+def test_structured_negative_sampling_bit_exact(cuda_dev, loops):
+    gen = torch.Generator().manual_seed(77)
+    U, I, E = 300, 40, 6000   # dense enough that many draws are rejected and redrawn
+    ei = torch.stack([torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)])
+    num_nodes = torch.max(ei[1])
+    torch.manual_seed(5)
+    want = so.structured_negative_sampling(ei, num_nodes=num_nodes, contains_neg_self_loops=loops)
+    torch.manual_seed(5)
+    got = lg.structured_negative_sampling(ei.to(cuda_dev), num_nodes=num_nodes, contains_neg_self_loops=loops)
+    for a, b in zip(got, want):
+        assert torch.equal(a.cpu(), b)
+    torch.manual_seed(5)
+    got_cpu_in = lg.structured_negative_sampling(ei, num_nodes=num_nodes, contains_neg_self_loops=loops)
+    assert got_cpu_in[2].device.type == "cpu" and torch.equal(got_cpu_in[2], want[2])
+
+
+# ------------------------------------------------------------------ top-k ids: bit-exact
+def test_topk_against_reference_golden(cuda_dev, golden):
+    g = golden["topk"]
+    U, I = g["Wu"].shape[0], g["Wi"].shape[0]
+    seen = lg.SeenItems(g["exclude"].to(cuda_dev), U, I)
+    ids = lg.recommend_topk(g["Wu"].to(cuda_dev), g["Wi"].to(cuda_dev), torch.arange(U, device=cuda_dev), g["k"], seen)
+    assert torch.equal(ids.cpu(), g["preds"])
+    d = to.create_adj_dict(g["exclude"])
+    for u in (0, 5, 39):
+        one = lg.make_predictions_for_user(g["Wu"].to(cuda_dev), g["Wi"].to(cuda_dev), u, d, g["k"])
+        assert torch.equal(one, g["preds"][u])
+
+
+@pytest.mark.parametrize("k,I,d", [(12, 3706, 64), (256, 3706, 64), (12, 500, 32), (1000, 1200, 16), (5, 3, 8)])
+def test_topk_against_oracle(cuda_dev, k, I, d):
+    gen = torch.Generator().manual_seed(k + I)
+    U = 64
+    Wu, Wi = torch.randn(U, d, generator=gen), torch.randn(I, d, generator=gen)
+    excl = torch.stack([torch.randint(0, U, (U * 20,), generator=gen), torch.randint(0, I, (U * 20,), generator=gen)])
+    seen = lg.SeenItems(excl.to(cuda_dev), U, I)
+    users = torch.arange(U, device=cuda_dev)
+    ids, scores = lg.recommend_topk(Wu.to(cuda_dev), Wi.to(cuda_dev), users, k, seen, return_scores=True)
+    ids = ids.cpu()
+    seen_d = to.create_adj_dict(excl)
+    full = Wu @ Wi.T
+    for u in range(U):
+        mask = torch.zeros(I, dtype=torch.bool)
+        if u in seen_d:
+            mask[seen_d[u]] = True
+        n_avail = int((~mask).sum())
+        got = ids[u][ids[u] >= 0]
+        assert len(got) == min(k, n_avail)
+        if k + len(seen_d.get(u, [])) <= I:
+            want = to.predictions_for_user(Wu, Wi, u, seen_d, k)
+            if not torch.equal(got, want):  # only legal difference: scores closer than fp32 summation-order noise
+                diff = (got != want).nonzero().flatten()
+                assert (full[u][got[diff]] - full[u][want[diff]]).abs().max() < 1e-5
+        assert not mask[got].any()
+        s = full[u][got]
+        assert (s[:-1] >= s[1:] - 1e-5).all()
