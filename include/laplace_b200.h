@@ -66,6 +66,10 @@ int lgb_gather_f32(const float* src, const int32_t* perm, int64_t n, float* dst,
  * deg = row counts, dinv = deg^-1/2 (0 where deg == 0), val[e] = (1*dinv[row])*dinv[col]. Square matrix. */
 int lgb_gcn_norm(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz, float* dinv,
                  float* val, void* stream);
+/* Same weights from a caller-supplied dinv[n] (multi-GPU: a rank's local block needs the GLOBAL degrees):
+ * val[e] = (1*dinv[row[e]])*dinv[colidx[e]]. */
+int lgb_gcn_values(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz, const float* dinv,
+                   float* val, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SpMM plan: rows longer than `chunk` non-zeros are split into fixed-size tasks whose partial sums
@@ -136,6 +140,11 @@ int lgb_row_div_by_degree(const float* X, const int32_t* rowptr, int64_t n_rows,
 /* cudaMemsetAsync(p, 0, bytes) on `stream` (gradient buffers that the atomic scatters accumulate into). */
 int lgb_zero(void* p, size_t bytes, void* stream);
 
+/* out[i] = ((acc ? acc[i] : 0) + y[i] + (resid ? resid[i] : 0)) / div over n floats -- the SpMM epilogue as a
+ * stand-alone pass, for rows whose sum arrives from a collective (multi-GPU item rows). out may alias acc or y. */
+int lgb_accumulate(const float* y, const float* acc, const float* resid, int64_t n, float div, float* out,
+                   void* stream);
+
 /* out = cat(a[na,d], b[nb,d]) * scale   (one pass; cat/split/mean backward of model/lightgcn.py:58,67-72). */
 int lgb_scale_concat(const float* a, int64_t na, const float* b, int64_t nb, int32_t d, float scale,
                      float* out, void* stream);
@@ -159,9 +168,11 @@ typedef struct lgb_bpr_args {
   const float* uf; const float* u0; const float* pf; const float* p0; const float* nf; const float* n0;
   const int64_t* iu; const int64_t* ip; const int64_t* in;   /* all three NULL, or all three set */
   int64_t B;
+  int64_t B_norm;          /* the 1/B of the mean; 0 = use B.  A rank that holds a shard of a global batch passes the global size */
   int32_t d;
   float lambda;
   float gscale;            /* extra factor folded into the *_f gradients, e.g. 1/(K+1) */
+  int32_t _pad;
   const float* gout;       /* device scalar upstream gradient or NULL */
   float* duf; float* du0; float* dpf; float* dp0; float* dnf; float* dn0;   /* each may be NULL */
   float* loss;             /* device float[1], may be NULL when only gradients are wanted */

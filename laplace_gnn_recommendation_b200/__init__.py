@@ -10,6 +10,8 @@ There is no CPU fallback: the kernels fail loudly when the shared library or a C
 from . import _lib  # noqa: F401
 from .bpr import bpr_indexed, bpr_loss  # noqa: F401
 from .csr import DeviceCSR  # noqa: F401
+from .hetero import (EdgeDecoder, Encoder_Decoder_Model, GNNEncoder, HeteroEncoder, SAGEConv, aggregate,  # noqa: F401
+                     build_edge_csr, edge_concat, edge_dot, get_linear_layers, get_SAGEConv_layers, to_hetero)
 from .lightgcn import LightGCN  # noqa: F401
 from .loader import sample_mini_batch, structured_negative_sampling  # noqa: F401
 from .sparse import SparseTensor, gcn_norm, matmul  # noqa: F401
@@ -18,5 +20,7 @@ from .topk import SeenItems, make_predictions_for_user, recommend_topk, topk_dic
 __all__ = [
     "LightGCN", "bpr_loss", "bpr_indexed", "SparseTensor", "matmul", "gcn_norm", "DeviceCSR",
     "sample_mini_batch", "structured_negative_sampling", "recommend_topk", "make_predictions_for_user",
-    "SeenItems", "topk_dict",
+    "SeenItems", "topk_dict", "SAGEConv", "to_hetero", "GNNEncoder", "HeteroEncoder", "EdgeDecoder",
+    "Encoder_Decoder_Model", "get_SAGEConv_layers", "get_linear_layers", "aggregate", "build_edge_csr",
+    "edge_concat", "edge_dot",
 ]

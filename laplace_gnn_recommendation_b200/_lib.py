@@ -34,7 +34,7 @@ class LgbBprArgs(C.Structure):
     _fields_ = [
         ("uf", c_vp), ("u0", c_vp), ("pf", c_vp), ("p0", c_vp), ("nf", c_vp), ("n0", c_vp),
         ("iu", c_vp), ("ip", c_vp), ("in_", c_vp),
-        ("B", c_i64), ("d", c_i32), ("lambda_", c_f32), ("gscale", c_f32),
+        ("B", c_i64), ("B_norm", c_i64), ("d", c_i32), ("lambda_", c_f32), ("gscale", c_f32), ("_pad", c_i32),
         ("gout", c_vp),
         ("duf", c_vp), ("du0", c_vp), ("dpf", c_vp), ("dp0", c_vp), ("dnf", c_vp), ("dn0", c_vp),
         ("loss", c_vp), ("ws", c_vp),
@@ -62,6 +62,8 @@ PROTOTYPES = {
     "lgb_segment_max": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_i32, c_vp, c_vp, c_vp]),
     "lgb_segment_max_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_row_div_by_degree": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    "lgb_gcn_values": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "lgb_accumulate": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp]),
     "lgb_zero": (C.c_int, [c_vp, c_sz, c_vp]),
     "lgb_scale_concat": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp]),
     "lgb_bpr_blocks": (c_i64, [c_i64]),

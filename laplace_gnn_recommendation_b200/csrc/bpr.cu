@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
   const bool want_0 = a.du0 || a.dp0 || a.dn0;
   if (active && (want_f || want_0)) {
     const float g = a.gout ? *a.gout : 1.f;
-    const float cf = -g * sig / (float)a.B * a.gscale;  // d loss / d x, folded with the caller's scale
+    const float cf = -g * sig / (float)(a.B_norm > 0 ? a.B_norm : a.B) * a.gscale;  // d loss / d x, folded with the caller's scale
     const float c0 = 2.f * a.lambda * g;
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_scalar_kernel(const BprParams
   const float sig = x > 20.f ? 1.f : z / (z + 1.f);
   if (active && (a.duf || a.dpf || a.dnf || a.du0 || a.dp0 || a.dn0)) {
     const float g = a.gout ? *a.gout : 1.f;
-    const float cf = -g * sig / (float)a.B * a.gscale;
+    const float cf = -g * sig / (float)(a.B_norm > 0 ? a.B_norm : a.B) * a.gscale;
     const float c0 = 2.f * a.lambda * g;
     for (int f = lane; f < d; f += 32) {
       const float u = a.uf[ru * d + f], pp = a.pf[rp * d + f], nn = a.nf[rn * d + f];
@@ -260,7 +260,7 @@ int lgb_bpr(const lgb_bpr_args* a, void* stream_) {
   int rc = n_idx ? launch_bpr<true>(p, stream) : launch_bpr<false>(p, stream);
   if (rc) return rc;
   if (a->loss) {
-    bpr_finalize_kernel<<<1, 1024, 0, stream>>>(a->ws, p.nblocks, a->B, a->lambda, a->loss);
+    bpr_finalize_kernel<<<1, 1024, 0, stream>>>(a->ws, p.nblocks, a->B_norm > 0 ? a->B_norm : a->B, a->lambda, a->loss);
     LGB_LAUNCH_CHECK();
   }
   return LGB_OK;

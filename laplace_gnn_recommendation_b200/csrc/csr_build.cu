@@ -325,6 +325,18 @@ int lgb_gcn_norm(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_
   return LGB_OK;
 }
 
+int lgb_gcn_values(const int32_t* rowptr, const int32_t* colidx, int64_t n, int64_t nnz, const float* dinv, float* val,
+                   void* stream) {
+  LGB_REQUIRE(rowptr && dinv && n >= 0 && nnz >= 0 && (nnz == 0 || (colidx && val)), LGB_EINVAL,
+              "lgb_gcn_values: bad argument");
+  LGB_REQUIRE(n < (1ll << 31) - 1 && nnz < (1ll << 31), LGB_ERANGE, "lgb_gcn_values: size exceeds int32");
+  if (nnz > 0) {
+    gcn_val_kernel<<<blocks_for(nnz, 256), 256, 0, (cudaStream_t)stream>>>(rowptr, colidx, dinv, (int32_t)n, nnz, val);
+    LGB_LAUNCH_CHECK();
+  }
+  return LGB_OK;
+}
+
 // ---- plan ---------------------------------------------------------------------------------
 int lgb_spmm_plan_ws_bytes(int64_t n_rows, size_t* bytes) {
   LGB_REQUIRE(bytes && n_rows >= 0, LGB_EINVAL, "lgb_spmm_plan_ws_bytes: bad argument");

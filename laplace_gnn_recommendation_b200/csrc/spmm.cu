@@ -262,6 +262,19 @@ __global__ void row_div_kernel(const float* __restrict__ X, const int32_t* __res
   out[i] = __fdiv_rn(X[i], (float)max(rowptr[r + 1] - rowptr[r], 1));
 }
 
+__global__ void accumulate_kernel(const float* __restrict__ y, const float* acc, const float* __restrict__ resid, int64_t n,
+                                  float div, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = y[i];
+    if (resid) v += resid[i];
+    if (acc) v = acc[i] + v;
+    if (div != 1.0f) v = __fdiv_rn(v, div);
+    out[i] = v;
+  }
+}
+
 __global__ void scale_concat_kernel(const float4* __restrict__ a, int64_t na4, const float4* __restrict__ b, int64_t nb4,
                                     float scale, float4* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,6 +366,15 @@ int lgb_row_div_by_degree(const float* X, const int32_t* rowptr, int64_t n_rows,
   const int64_t total = n_rows * d;
   if (total == 0) return LGB_OK;
   row_div_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(X, rowptr, n_rows, d, out);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_accumulate(const float* y, const float* acc, const float* resid, int64_t n, float div, float* out, void* stream) {
+  LGB_REQUIRE(n >= 0 && div != 0.f && (n == 0 || (y && out)), LGB_EINVAL, "lgb_accumulate: bad argument");
+  if (n == 0) return LGB_OK;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  accumulate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, acc, resid, n, div, out);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
 }

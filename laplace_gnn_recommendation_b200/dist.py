@@ -1,0 +1,297 @@
+"""Multi-GPU LightGCN: users range-sharded, items replicated, one all-reduce of the [I, d] item block per
+propagation layer (SURVEY.md 8e "bipartite-aware 1.5-D row sharding").  One process per GPU, NCCL through
+``torch.distributed`` (the reference has no distributed code at all: this layer is new).
+
+Per rank g (owning users [u_g, u_{g+1}), split at nnz-balanced points):
+    local table   [U_g + I, d]   rows 0..U_g-1 = owned user embeddings, rows U_g.. = ALL item embeddings (replicated)
+    local graph   the symmetric block [[0, R_g], [R_g^T, 0]] with the GLOBAL symmetric normalisation
+                  (user degrees are local, item degrees are all-reduced once at build time)
+    two row views of that CSR (free: rowptr slices)
+        G_users : rows 0..U_g-1      users <- items   complete locally (items are replicated)
+        G_items : rows U_g..U_g+I-1  items <- users   PARTIAL sums over the owned users only
+A layer is   Y_items(partial) = G_items X   ->  all-reduce(Y_items) on the comm stream
+          || Y_users = G_users X with the fused accumulate epilogue on the compute stream   (overlap)
+          -> item rows: acc += all-reduced Y_items (small [I, d] pass).
+User embeddings never move.  The backward is the same pattern on the (symmetric) block with the
+residual r = dE_f/(K+1); BPR triples are handled by the rank that owns the user, item-row gradient
+contributions are partial sums folded into the all-reduces.
+
+The collective / kernel calls go through a small ``ops`` object so that the partition + exchange logic
+can be exercised on the CPU with gloo and an oracle-backed ops object in tests/ (the product ops object
+is CUDA-only and fails loudly otherwise).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, ptr, stream
+from .bpr import LgbBprArgs, _launch as _bpr_launch, _ws as _bpr_ws
+from .csr import DEFAULT_CHUNK, DeviceCSR
+
+
+# --------------------------------------------------------------------------------------------
+# partitioning (pure index arithmetic; shared by the CUDA path and the CPU tests)
+# --------------------------------------------------------------------------------------------
+def balanced_user_bounds(user_degree: torch.Tensor, world: int) -> List[int]:
+    """Split points u_0=0 <= u_1 <= ... <= u_G=U so every range carries ~nnz/G interactions."""
+    U = user_degree.numel()
+    csum = torch.cumsum(user_degree.to(torch.int64), 0)
+    total = int(csum[-1]) if U else 0
+    bounds = [0]
+    for g in range(1, world):
+        target = (total * g) // world
+        b = int(torch.searchsorted(csum, torch.tensor(target, device=csum.device), right=False)) + 1 if U else 0
+        bounds.append(min(max(b, bounds[-1]), U))
+    bounds.append(U)
+    return bounds
+
+
+def local_block(users: torch.Tensor, items: torch.Tensor, lo: int, hi: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """COO of the local symmetric block in local numbering (users 0..U_g-1, items U_g..U_g+I-1)."""
+    m = (users >= lo) & (users < hi)
+    lu = users[m] - lo
+    li = items[m] + (hi - lo)
+    return torch.cat([lu, li]), torch.cat([li, lu]), lu, items[m]
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA ops object
+# --------------------------------------------------------------------------------------------
+class CudaOps:
+    """liblaplace_b200 kernels + NCCL collectives.  ``comm`` stream carries the all-reduces."""
+
+    def __init__(self, device: torch.device, group=None):
+        if device.type != "cuda":
+            raise RuntimeError("ShardedLightGCN needs CUDA devices (no CPU fallback); tests inject their own ops object")
+        self.device, self.group = device, group
+        self.comm = torch.cuda.Stream(device=device)
+
+    # graph ----------------------------------------------------------------------------------
+    def build_graph(self, row, col, n, dinv):
+        g = DeviceCSR.from_coo(row, col, n, n, chunk=0)
+        val = torch.empty(g.nnz, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_gcn_values(ptr(g.rowptr), ptr(g.colidx), n, g.nnz, ptr(dinv), ptr(val), stream()), "gcn_values")
+        _lib.count_launch()
+        g.val = val
+        return g
+
+    def row_view(self, g: DeviceCSR, lo: int, hi: int) -> DeviceCSR:
+        """Rows [lo, hi) of g as a CSR of its own (rowptr slice; colidx/val shared, offsets stay absolute)."""
+        v = DeviceCSR(hi - lo, g.n_cols, g.rowptr[lo:hi + 1], g.colidx, g.val, chunk=DEFAULT_CHUNK)
+        v.nnz = int(g.rowptr[hi]) - int(g.rowptr[lo])   # entries of the view (the arrays themselves are shared)
+        v._struct = None
+        return v
+
+    def spmm(self, g, X, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
+        g.spmm(X, Y=Y, resid=resid, acc_in=acc_in, acc_out=acc_out, acc_div=acc_div, want_y=Y is not None)
+
+    def accumulate(self, y, acc, resid, div, out):
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_accumulate(ptr(y), ptr(acc), ptr(resid), y.numel(), float(div), ptr(out), stream()), "accumulate")
+        _lib.count_launch()
+
+    def zero(self, t):
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_zero(ptr(t), t.numel() * t.element_size(), stream()), "zero")
+
+    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
+        d = Ef.shape[1]
+        off = Ug * d * 4
+        a = LgbBprArgs()
+        a.uf, a.pf, a.nf = Ef.data_ptr(), Ef.data_ptr() + off, Ef.data_ptr() + off
+        a.u0, a.p0, a.n0 = E0.data_ptr(), E0.data_ptr() + off, E0.data_ptr() + off
+        a.iu, a.ip, a.in_ = ptr(u), ptr(p), ptr(n)
+        a.B, a.B_norm, a.d, a.lambda_, a.gscale = u.numel(), int(B_norm), d, float(lam), float(gscale)
+        if dEf is not None:
+            a.duf, a.dpf, a.dnf = dEf.data_ptr(), dEf.data_ptr() + off, dEf.data_ptr() + off
+        if dE0_users is not None:
+            a.du0 = dE0_users.data_ptr()
+        if dE0_items is not None:
+            a.dp0 = a.dn0 = dE0_items.data_ptr()
+        if loss is not None:
+            ws = _bpr_ws(max(u.numel(), 1), Ef.device)
+            a.loss, a.ws = loss.data_ptr(), ptr(ws)
+            self._keep = ws
+        if u.numel() == 0:
+            if loss is not None:
+                self.zero(loss)
+            return
+        _bpr_launch(a, Ef.device)
+
+    # collectives -------------------------------------------------------------------------------
+    def all_reduce_async(self, t: torch.Tensor):
+        """Sum-all-reduce of ``t`` on the comm stream, ordered after the work already queued on the
+        compute stream; returns a handle whose wait() makes the compute stream wait for the result."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return _Done()
+        cur = torch.cuda.current_stream(self.device)
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        t.record_stream(self.comm)
+        return _StreamWait(self.comm, cur)
+
+    def all_reduce(self, t: torch.Tensor):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class _Done:
+    def wait(self):
+        pass
+
+
+class _StreamWait:
+    def __init__(self, comm, cur):
+        self.comm, self.cur = comm, cur
+
+    def wait(self):
+        self.cur.wait_stream(self.comm)
+
+
+# --------------------------------------------------------------------------------------------
+# the sharded engine
+# --------------------------------------------------------------------------------------------
+class ShardedLightGCN:
+    """LightGCN fwd + BPR + bwd over a user-sharded graph.  Every rank passes the same (users, items) COO
+    (or any superset of its own users' edges plus all item-degree information via ``item_degree``)."""
+
+    def __init__(self, num_users: int, num_items: int, embedding_dim: int, num_iterations: int,
+                 users: torch.Tensor, items: torch.Tensor, device, group=None, ops=None,
+                 rank: Optional[int] = None, world: Optional[int] = None, init_tables=None):
+        self.U, self.I, self.d, self.K = int(num_users), int(num_items), int(embedding_dim), int(num_iterations)
+        self.device = torch.device(device)
+        inited = dist.is_available() and dist.is_initialized()
+        self.rank = rank if rank is not None else (dist.get_rank(group) if inited else 0)
+        self.world = world if world is not None else (dist.get_world_size(group) if inited else 1)
+        self.ops = ops if ops is not None else CudaOps(self.device, group)
+        users, items = users.to(self.device), items.to(self.device)
+
+        udeg = torch.bincount(users, minlength=self.U)
+        self.bounds = balanced_user_bounds(udeg, self.world)
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.Ug = self.hi - self.lo
+        row, col, lu, li = local_block(users, items, self.lo, self.hi)
+        self.local_edges = int(lu.numel())
+        # global degrees: users are wholly local; item degrees are summed over ranks
+        ideg = torch.bincount(li, minlength=self.I).to(torch.float32)
+        self.ops.all_reduce(ideg)
+        deg = torch.cat([udeg[self.lo:self.hi].to(torch.float32), ideg])
+        dinv = torch.where(deg > 0, 1.0 / torch.sqrt(deg), torch.zeros_like(deg))
+        n = self.Ug + self.I
+        self.n = n
+        g = self.ops.build_graph(row, col, n, dinv)
+        self.g_users = self.ops.row_view(g, 0, self.Ug)
+        self.g_items = self.ops.row_view(g, self.Ug, n)
+        self.g_full = g
+
+        # parameters: one local table; the item block is identical on every rank
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.table = torch.empty(n, self.d, **f32)
+        if init_tables is not None:
+            Wu, Wi = init_tables
+            self.table[: self.Ug].copy_(Wu[self.lo:self.hi])
+            self.table[self.Ug:].copy_(Wi)
+        else:
+            gen = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
+            self.table[: self.Ug].normal_(0, 0.1, generator=gen)
+            gen_i = torch.Generator(device=self.device).manual_seed(999)
+            self.table[self.Ug:].normal_(0, 0.1, generator=gen_i)
+        self.grad = torch.empty(n, self.d, **f32)
+        self.E_f = torch.empty(n, self.d, **f32)
+        self._ya = torch.empty(n, self.d, **f32)
+        self._yb = torch.empty(n, self.d, **f32)
+        self._r = torch.empty(n, self.d, **f32)
+        self.loss = torch.zeros((), **f32)
+
+    def graphs(self):
+        return [self.g_users, self.g_items]
+
+    @property
+    def users_weight(self):
+        return self.table[: self.Ug]
+
+    @property
+    def items_weight(self):
+        return self.table[self.Ug:]
+
+    # ---- one propagation layer:  Y = A X (+resid) with the item rows all-reduced ------------------
+    def _layer(self, X, Y, resid=None, acc_in=None, acc_out=None, acc_div=1.0, write_y=True):
+        """Y[:Ug] = G_users X (+resid) ; Y[Ug:] = allreduce(G_items X) (+resid);
+        acc_out (optional) = (acc_in + that) / acc_div on both row blocks."""
+        Ug, ops = self.Ug, self.ops
+        yi = Y[Ug:]
+        ops.spmm(self.g_items, X, Y=yi)                                     # partial item rows
+        h = ops.all_reduce_async(yi)                                          # ... summed over ranks (comm stream)
+        ops.spmm(self.g_users, X, Y=Y[:Ug] if write_y else None,              # overlaps with the all-reduce
+                 resid=None if resid is None else resid[:Ug],
+                 acc_in=None if acc_in is None else acc_in[:Ug],
+                 acc_out=None if acc_out is None else acc_out[:Ug], acc_div=acc_div)
+        h.wait()
+        if acc_out is not None:
+            ops.accumulate(yi, None if acc_in is None else acc_in[Ug:], None if resid is None else resid[Ug:], acc_div,
+                           acc_out[Ug:])
+        elif resid is not None:
+            ops.accumulate(yi, None, resid[Ug:], 1.0, yi)
+
+    def forward(self) -> torch.Tensor:
+        """E_f = mean_k A^k E0 on the local rows (item rows replicated)."""
+        K, E0, Ef = self.K, self.table, self.E_f
+        if K == 0:
+            Ef.copy_(E0)
+            return Ef
+        x, y = E0, self._ya
+        for k in range(K):
+            last = k == K - 1
+            self._layer(x, y, acc_in=E0 if k == 0 else Ef, acc_out=Ef, acc_div=float(K + 1) if last else 1.0,
+                        write_y=not last)
+            x, y = y, (self._yb if y is self._ya else self._ya)
+        return Ef
+
+    def backward(self, r: torch.Tensor, reg=None) -> torch.Tensor:
+        """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (item rows already summed over ranks)."""
+        K = self.K
+        if K == 0:
+            self.grad.copy_(r)
+            return self.grad
+        g = r
+        bufs = [self._ya, self._yb]
+        for k in range(K):
+            last = k == K - 1
+            dst = self.grad if last else bufs[k % 2]
+            self._layer(g, dst, resid=r)
+            g = dst
+        return self.grad
+
+    @torch.no_grad()
+    def fused_step(self, user_indices: torch.Tensor, pos_item_indices: torch.Tensor, neg_item_indices: torch.Tensor,
+                   lambda_val: float) -> torch.Tensor:
+        """Global batch in, global loss out (0-dim tensor, identical on every rank); gradients in ``self.grad``
+        (rows [:Ug] for the owned users, rows [Ug:] for the replicated items, identical on every rank)."""
+        ops, Ug, K = self.ops, self.Ug, self.K
+        u, p, n = (t.to(self.device) for t in (user_indices, pos_item_indices, neg_item_indices))
+        B = u.numel()
+        mine = (u >= self.lo) & (u < self.hi)
+        lu, lp, ln = (u[mine] - self.lo).contiguous(), p[mine].contiguous(), n[mine].contiguous()
+        Ef = self.forward()
+        r = self._r
+        ops.zero(r)
+        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, loss=self.loss, dEf=r, gscale=1.0 / (K + 1))
+        # item-row gradient contributions of the local triples are partial sums: reduce them (and the loss)
+        h = ops.all_reduce_async(r[Ug:])
+        ops.all_reduce(self.loss)
+        h.wait()
+        G = self.backward(r)
+        # + 2*lambda*E0 on the batch rows: users locally; items are partial over ranks -> reduce a small buffer
+        reg_items = self._ya[Ug:]
+        ops.zero(reg_items)
+        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, dE0_users=G, dE0_items=reg_items)
+        h = ops.all_reduce_async(reg_items)
+        h.wait()
+        ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
+        return self.loss

@@ -1,0 +1,394 @@
+"""Ranking encoder-decoder with the reference's call surface (model/encoder_decoder.py:17-164,
+model/layers.py:6-56) on the sm_100a kernels.
+
+What runs where
+  * per edge type neighbour aggregation (PyG SAGEConv -> propagate -> gather + torch_scatter): one per-batch
+    CSR build (lgb_csr_build, dst-major, stable => deterministic) + the fused segment-reduce kernel
+    lgb_spmm (sum / mean) or lgb_segment_max; backward = the same kernel on the transposed arrays;
+  * edge decoder: gather+concat kernel (reference-faithful concat -> MLP) or the fused dot-product
+    decoder north_star names, both with hand-written backward;
+  * the dense pieces (SAGE lin_l / lin_r, decoder Linear layers, BatchNorm1d, feature Embedding) stay
+    torch / cuBLAS library calls -- they are not gather/scatter work.
+
+Reference quirks kept on purpose: the feature-embedding ModuleLists live in a plain dict
+(not in state_dict(), not in parameters()) -- they only follow the module across devices here so that the
+model can run on the GPU at all; encoder dropout is applied with training=True even in eval mode (what FX
+tracing bakes in) unless ``bake_dropout_training=False``.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+from collections import defaultdict, deque
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn import BatchNorm1d, Embedding, Linear, ModuleList
+
+from . import _lib
+from ._lib import check, ptr, stream
+from .csr import DeviceCSR
+
+NODE_USER, NODE_ITEM = "customer", "article"                       # utils/constants.py:4-5
+EDGE_KEY = (NODE_USER, "buys", NODE_ITEM)                          # utils/constants.py:14
+REV_EDGE_KEY = (NODE_ITEM, "rev_buys", NODE_USER)                  # utils/constants.py:15
+
+
+def key2str(key) -> str:
+    return "__".join(key) if isinstance(key, tuple) else key
+
+
+# --------------------------------------------------------------------------------------------
+# neighbour aggregation
+# --------------------------------------------------------------------------------------------
+def build_edge_csr(edge_index: torch.Tensor, n_src: int, n_dst: int) -> DeviceCSR:
+    """dst-major CSR of one edge type: row = edge_index[1] (target), col = edge_index[0] (source)."""
+    _lib.require_cuda(edge_index)
+    return DeviceCSR.from_coo(edge_index[1], edge_index[0], n_dst, n_src)
+
+
+class _Aggregate(torch.autograd.Function):
+    """agg[t] = (+|mean|max)_{e: dst[e]=t} x_src[src[e]]  (SURVEY.md A8)."""
+
+    @staticmethod
+    def forward(ctx, x_src, g: DeviceCSR, aggr: str):
+        x_src = _lib.f32c(x_src)
+        ctx.g, ctx.aggr = g, aggr
+        if aggr in ("add", "sum"):
+            return g.spmm(x_src)
+        if aggr == "mean":
+            return g.spmm(x_src, mean=True)
+        if aggr == "max":
+            d = x_src.shape[1]
+            out = torch.empty(g.n_rows, d, dtype=torch.float32, device=x_src.device)
+            arg = torch.empty(g.n_rows, d, dtype=torch.int32, device=x_src.device)
+            with torch.cuda.device(x_src.device):
+                check(_lib.load().lgb_segment_max(C.byref(g.struct), ptr(x_src), d, ptr(out), ptr(arg), stream()), "segment_max")
+            _lib.count_launch()
+            ctx.arg = arg
+            return out
+        raise RuntimeError(f"SAGEConv aggr={aggr!r} is not supported (add, mean, max)")
+
+    @staticmethod
+    def backward(ctx, gout):
+        g: DeviceCSR = ctx.g
+        gout = _lib.f32c(gout)
+        lib = _lib.load()
+        d = gout.shape[1]
+        if ctx.aggr == "max":
+            gx = torch.empty(g.n_cols, d, dtype=torch.float32, device=gout.device)
+            with torch.cuda.device(gout.device):
+                check(lib.lgb_zero(ptr(gx), gx.numel() * 4, stream()), "zero")
+                check(lib.lgb_segment_max_bwd(ptr(gout), ptr(ctx.arg), g.n_rows, d, ptr(gx), stream()), "segment_max_bwd")
+            _lib.count_launch()
+            return gx, None, None
+        if ctx.aggr == "mean":
+            scaled = torch.empty_like(gout)
+            with torch.cuda.device(gout.device):
+                check(lib.lgb_row_div_by_degree(ptr(gout), ptr(g.rowptr), g.n_rows, d, ptr(scaled), stream()),
+                      "row_div_by_degree")
+            _lib.count_launch()
+            gout = scaled
+        return g.transpose().spmm(gout), None, None
+
+
+def aggregate(x_src: torch.Tensor, g: DeviceCSR, aggr: str) -> torch.Tensor:
+    return _Aggregate.apply(x_src, g, aggr)
+
+
+class SAGEConv(nn.Module):
+    """PyG ``SAGEConv(in_channels, out_channels, aggr, normalize=False, bias=True)`` as the reference builds it
+    (model/layers.py:9-24): out = lin_l(aggr_j x_j) + lin_r(x_i); lazy input widths (``-1``)."""
+
+    def __init__(self, in_channels, out_channels: int, aggr: str = "mean", normalize: bool = False,
+                 root_weight: bool = True, bias: bool = True):
+        super().__init__()
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.aggr, self.normalize, self.root_weight = aggr, normalize, root_weight
+        self.lin_l = nn.LazyLinear(out_channels, bias=bias) if in_channels[0] <= 0 else Linear(in_channels[0], out_channels, bias=bias)
+        if root_weight:
+            self.lin_r = nn.LazyLinear(out_channels, bias=False) if in_channels[1] <= 0 else Linear(in_channels[1], out_channels, bias=False)
+
+    def forward(self, x, edge_index, size=None, graph: Optional[DeviceCSR] = None) -> torch.Tensor:
+        x_src, x_dst = (x, x) if isinstance(x, torch.Tensor) else x
+        if graph is None:
+            graph = build_edge_csr(edge_index, x_src.shape[0], x_dst.shape[0])
+        out = self.lin_l(aggregate(x_src, graph, self.aggr))
+        if self.root_weight and x_dst is not None:
+            out = out + self.lin_r(x_dst)
+        if self.normalize:
+            out = F.normalize(out, p=2.0, dim=-1)
+        return out
+
+
+def get_SAGEConv_layers(num_layers: int, hidden_channels: int, out_channels: int, agg_type: str) -> nn.ModuleList:
+    """model/layers.py:6-32."""
+    single = SAGEConv((-1, -1, -1), hidden_channels, aggr=agg_type, normalize=False, bias=True)
+    last = SAGEConv((-1, -1, -1), out_channels, aggr=agg_type, normalize=False, bias=True)
+    if num_layers == 1:
+        return nn.ModuleList([last])
+    return nn.ModuleList([copy.deepcopy(single) for _ in range(num_layers - 1)] + [last])
+
+
+def get_linear_layers(num_layers: int, in_channels: int, hidden_channels: int, out_channels: int) -> nn.ModuleList:
+    """model/layers.py:35-56."""
+    if num_layers == 1:
+        return nn.ModuleList([Linear(in_channels, out_channels)])
+    if num_layers == 2:
+        return nn.ModuleList([Linear(in_channels, hidden_channels), Linear(hidden_channels, out_channels)])
+    middle = Linear(hidden_channels, hidden_channels)
+    return nn.ModuleList([Linear(in_channels, hidden_channels)]
+                         + [copy.deepcopy(middle) for _ in range(num_layers - 2)]
+                         + [Linear(hidden_channels, out_channels)])
+
+
+# --------------------------------------------------------------------------------------------
+# encoder (GNNEncoder lifted over node / edge types)
+# --------------------------------------------------------------------------------------------
+class GNNEncoder(nn.Module):
+    """model/encoder_decoder.py:17-46 (homogeneous form; ``to_hetero`` lifts it)."""
+
+    def __init__(self, layers: ModuleList, p_dropout_edges: Optional[float], p_dropout_features: Optional[float]):
+        super().__init__()
+        self.layers = layers
+        self.p_dropout_edges = p_dropout_edges
+        self.p_dropout_features = p_dropout_features
+
+    def forward(self, x, edge_index):
+        for index, layer in enumerate(self.layers):
+            if index == len(self.layers) - 1:
+                x = layer(x, edge_index)
+            else:
+                if self.p_dropout_features is not None:
+                    x = F.dropout(x, p=self.p_dropout_features, training=self.training)
+                x = layer(x, edge_index).relu()
+        return x
+
+
+_FAN_IN = {"sum": torch.add, "mean": torch.add, "max": torch.max, "min": torch.min, "mul": torch.mul}
+
+
+def _fan_in(outs: List[torch.Tensor], aggr: str) -> torch.Tensor:
+    """Per-destination pairwise reduction of temporary_hetero.py:201-228 (pop two, combine, push back)."""
+    n = len(outs)
+    queue = deque(outs)
+    while len(queue) >= 2:
+        a, b = queue.popleft(), queue.popleft()
+        queue.append(_FAN_IN[aggr](a, b))
+    out = queue.popleft()
+    return torch.div(out, n) if (aggr == "mean" and n > 1) else out
+
+
+class HeteroEncoder(nn.Module):
+    """``to_hetero(GNNEncoder(...), metadata, aggr)``: one copy of every conv layer per edge type
+    (sub-module names ``layers.<i>.<src>__<rel>__<dst>`` as PyG generates them), fan-in per destination."""
+
+    def __init__(self, module: GNNEncoder, metadata, aggr: str = "sum", bake_dropout_training: bool = True):
+        super().__init__()
+        if aggr not in _FAN_IN:
+            raise RuntimeError(f"to_hetero aggr={aggr!r} not supported")
+        self.node_types, self.edge_types = list(metadata[0]), [tuple(e) for e in metadata[1]]
+        self.aggr = aggr
+        self.p_dropout_features = module.p_dropout_features
+        self.bake_dropout_training = bake_dropout_training
+        self.layers = nn.ModuleList([
+            nn.ModuleDict({key2str(et): copy.deepcopy(layer) for et in self.edge_types}) for layer in module.layers])
+
+    def forward(self, x_dict: Dict[str, torch.Tensor], edge_index_dict) -> Dict[str, torch.Tensor]:
+        x = dict(x_dict)
+        # one CSR (+ lazily its transpose) per edge type per batch, shared by all layers and the backward
+        graphs = {et: build_edge_csr(edge_index_dict[et], x[et[0]].shape[0], x[et[2]].shape[0]) for et in self.edge_types}
+        for li, convs in enumerate(self.layers):
+            last = li == len(self.layers) - 1
+            if not last and self.p_dropout_features is not None:
+                training = True if self.bake_dropout_training else self.training
+                x = {k: F.dropout(v, p=self.p_dropout_features, training=training) for k, v in x.items()}
+            per_dst: Dict[str, List[torch.Tensor]] = defaultdict(list)
+            for et in self.edge_types:
+                s, _, t = et
+                per_dst[t].append(convs[key2str(et)]((x[s], x[t]), edge_index_dict[et], graph=graphs[et]))
+            x = {t: _fan_in(v, self.aggr) for t, v in per_dst.items()}
+            if not last:
+                x = {k: v.relu() for k, v in x.items()}
+        return x
+
+
+def to_hetero(module: nn.Module, metadata, aggr: str = "sum", **kwargs) -> HeteroEncoder:
+    """The one use the reference makes of PyG ``to_hetero`` (model/encoder_decoder.py:93-95)."""
+    if not hasattr(module, "layers") or not hasattr(module, "p_dropout_features"):
+        raise RuntimeError("to_hetero here lifts GNNEncoder-shaped modules (a ModuleList `layers` of SAGEConv) only")
+    return HeteroEncoder(module, metadata, aggr, **kwargs)
+
+
+# --------------------------------------------------------------------------------------------
+# edge decoder
+# --------------------------------------------------------------------------------------------
+class _EdgeConcat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, zu, zi, row, col):
+        zu, zi, row, col = _lib.f32c(zu), _lib.f32c(zi), _lib.i64c(row), _lib.i64c(col)
+        _lib.require_cuda(zu, zi, row, col)
+        L, du, di = row.numel(), zu.shape[1], zi.shape[1]
+        out = torch.empty(L, du + di, dtype=torch.float32, device=zu.device)
+        with torch.cuda.device(zu.device):
+            check(_lib.load().lgb_edge_concat_fwd(ptr(zu), ptr(zi), ptr(row), ptr(col), L, du, di, ptr(out), stream()),
+                  "edge_concat_fwd")
+        _lib.count_launch()
+        ctx.save_for_backward(row, col)
+        ctx.shapes = (zu.shape, zi.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        row, col = ctx.saved_tensors
+        (nu, du), (ni, di) = ctx.shapes
+        gout = _lib.f32c(gout)
+        dzu = torch.empty(nu, du, dtype=torch.float32, device=gout.device) if ctx.needs_input_grad[0] else None
+        dzi = torch.empty(ni, di, dtype=torch.float32, device=gout.device) if ctx.needs_input_grad[1] else None
+        lib = _lib.load()
+        with torch.cuda.device(gout.device):
+            for t in (dzu, dzi):
+                if t is not None:
+                    check(lib.lgb_zero(ptr(t), t.numel() * 4, stream()), "zero")
+            check(lib.lgb_edge_concat_bwd(ptr(gout), ptr(row), ptr(col), row.numel(), du, di, ptr(dzu), ptr(dzi), stream()),
+                  "edge_concat_bwd")
+        _lib.count_launch()
+        return dzu, dzi, None, None
+
+
+class _EdgeDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, zu, zi, row, col):
+        zu, zi, row, col = _lib.f32c(zu), _lib.f32c(zi), _lib.i64c(row), _lib.i64c(col)
+        _lib.require_cuda(zu, zi, row, col)
+        if zu.shape[1] != zi.shape[1]:
+            raise RuntimeError("dot decoder needs equal embedding widths")
+        L, d = row.numel(), zu.shape[1]
+        out = torch.empty(L, dtype=torch.float32, device=zu.device)
+        with torch.cuda.device(zu.device):
+            check(_lib.load().lgb_edge_dot_fwd(ptr(zu), ptr(zi), ptr(row), ptr(col), L, d, ptr(out), stream()), "edge_dot_fwd")
+        _lib.count_launch()
+        ctx.save_for_backward(zu, zi, row, col)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        zu, zi, row, col = ctx.saved_tensors
+        gout = _lib.f32c(gout)
+        dzu = torch.empty_like(zu) if ctx.needs_input_grad[0] else None
+        dzi = torch.empty_like(zi) if ctx.needs_input_grad[1] else None
+        lib = _lib.load()
+        with torch.cuda.device(gout.device):
+            for t in (dzu, dzi):
+                if t is not None:
+                    check(lib.lgb_zero(ptr(t), t.numel() * 4, stream()), "zero")
+            check(lib.lgb_edge_dot_bwd(ptr(zu), ptr(zi), ptr(row), ptr(col), ptr(gout), row.numel(), zu.shape[1],
+                                       ptr(dzu), ptr(dzi), stream()), "edge_dot_bwd")
+        _lib.count_launch()
+        return dzu, dzi, None, None
+
+
+def edge_concat(zu, zi, row, col):
+    return _EdgeConcat.apply(zu, zi, row, col)
+
+
+def edge_dot(zu, zi, row, col):
+    return _EdgeDot.apply(zu, zi, row, col)
+
+
+class EdgeDecoder(nn.Module):
+    """model/encoder_decoder.py:49-72.  ``mode="mlp"`` is the reference (concat -> [dropout -> Linear -> relu]* ->
+    Linear -> view(-1)); ``mode="dot"`` is the dot-product decoder of north_star (layers unused)."""
+
+    def __init__(self, layers: ModuleList, p_dropout_features: Optional[float], mode: str = "mlp"):
+        super().__init__()
+        self.layers = layers
+        self.p_dropout_features = p_dropout_features
+        self.mode = mode
+
+    def forward(self, z_dict: dict, edge_label_index) -> torch.Tensor:
+        customer_index, article_index = edge_label_index
+        zu, zi = z_dict[NODE_USER], z_dict[NODE_ITEM]
+        if self.mode == "dot":
+            return edge_dot(zu, zi, customer_index, article_index)
+        z = edge_concat(zu, zi, customer_index, article_index)
+        for index, layer in enumerate(self.layers):
+            if index == len(self.layers) - 1:
+                z = layer(z)
+            else:
+                if self.p_dropout_features is not None:
+                    z = F.dropout(z, p=self.p_dropout_features, training=self.training)
+                z = layer(z).relu()
+        return z.view(-1)
+
+
+# --------------------------------------------------------------------------------------------
+# the model
+# --------------------------------------------------------------------------------------------
+def padded_stack(tensors: List[torch.Tensor], value=0) -> torch.Tensor:
+    """utils/tensor.py:24-61 (right padding, constant)."""
+    full = max(x.size(-1) for x in tensors)
+    return torch.stack([F.pad(x, (0, full - x.size(-1)), value=value) if full > x.size(-1) else x for x in tensors], dim=0)
+
+
+class Encoder_Decoder_Model(nn.Module):
+    """Drop-in for model/encoder_decoder.py:75-164 (same ctor kwargs, forward / infer /
+    initialize_encoder_input_size, same state_dict keys)."""
+
+    def __init__(self, encoder_layers: ModuleList, decoder_layers: ModuleList, feature_info: dict, metadata,
+                 embedding: bool, heterogeneous_prop_agg_type: str, batch_normalize: bool,
+                 p_dropout_edges: Optional[float], p_dropout_features: Optional[float],
+                 decoder_mode: str = "mlp", bake_dropout_training: bool = True):
+        super().__init__()
+        self.embedding = embedding
+        self.batch_normalize = batch_normalize
+        self.encoder = to_hetero(GNNEncoder(encoder_layers, p_dropout_edges, p_dropout_features), metadata,
+                                 aggr=heterogeneous_prop_agg_type, bake_dropout_training=bake_dropout_training)
+        self.decoder = EdgeDecoder(decoder_layers, p_dropout_features, mode=decoder_mode)
+        self.encoder_layer_norm_customer = BatchNorm1d(encoder_layers[-1].out_channels)
+        self.encoder_layer_norm_article = BatchNorm1d(encoder_layers[-1].out_channels)
+        # reference quirk: a plain dict -> not registered, not trained, not in state_dict (model/encoder_decoder.py:101-114)
+        self.embedding_layers = dict()
+        if self.embedding:
+            for key, item in feature_info.items():
+                self.embedding_layers[key] = ModuleList([
+                    Embedding(num_embeddings=int(item.num_cat[i] + 1), embedding_dim=int(item.embedding_size[i]), max_norm=1)
+                    for i in range(item.num_feat)])
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        for ml in self.embedding_layers.values():   # follow the module across devices (still unregistered)
+            ml._apply(fn)
+        return out
+
+    def _embed(self, x_dict: dict) -> dict:
+        for key, item in self.embedding_layers.items():
+            features = x_dict[key]
+            x_dict[key] = torch.cat([layer(features[:, i]) for i, layer in enumerate(item)], dim=1)
+        return x_dict
+
+    def initialize_encoder_input_size(self, data) -> None:
+        x_dict, edge_index_dict = data.x_dict, data.edge_index_dict
+        if self.embedding:
+            x_dict = self._embed(x_dict)
+        self.encoder(x_dict, edge_index_dict)
+
+    def forward(self, x_dict, edge_index_dict: dict, edge_label_index: torch.Tensor) -> torch.Tensor:
+        if self.embedding:
+            x_dict = self._embed(x_dict)
+        z_dict = self.encoder(x_dict, edge_index_dict)
+        if self.batch_normalize:
+            z_dict[NODE_USER] = self.encoder_layer_norm_customer(z_dict[NODE_USER])
+            z_dict[NODE_ITEM] = self.encoder_layer_norm_article(z_dict[NODE_ITEM])
+        return self.decoder(z_dict, edge_label_index)
+
+    def infer(self, x_dict, edge_index_dict: dict, edge_label_index: torch.Tensor) -> torch.Tensor:
+        self.eval()
+        out = self.forward(x_dict, edge_index_dict, edge_label_index).detach()
+        users = edge_label_index[0].unique(sorted=True)
+        out_per_user = [out[edge_label_index[0] == user] for user in users]
+        return padded_stack(out_per_user, value=-(1 << 50))

