@@ -76,14 +76,14 @@ int lgb_gcn_values(const int32_t* rowptr, const int32_t* colidx, int64_t n, int6
  * are reduced in a fixed order by a second stage (deterministic, no atomics).
  *   lgb_spmm_plan_count : counts_host[0] = #long rows, counts_host[1] = #tasks  (SYNCHRONISES the stream)
  *   lgb_spmm_plan_fill  : long_rows[n_long] ascending, long_ptr[n_long+1] (task range per long row),
- *                         task_row[n_tasks], task_start[n_tasks]
+ *                         task_row[n_tasks], task_start[n_tasks], task_end[n_tasks]
  * ------------------------------------------------------------------------------------------- */
 int lgb_spmm_plan_count(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int64_t* counts_host,
                         void* ws, size_t ws_bytes, void* stream);
 int lgb_spmm_plan_ws_bytes(int64_t n_rows, size_t* bytes_host);
 int lgb_spmm_plan_fill(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int64_t n_long,
                        int64_t n_tasks, int32_t* long_rows, int32_t* long_ptr, int32_t* task_row,
-                       int32_t* task_start, void* ws, size_t ws_bytes, void* stream);
+                       int32_t* task_start, int32_t* task_end, void* ws, size_t ws_bytes, void* stream);
 
 /* Optional degree-bucketed row order: rows sorted by descending ceil(log2(deg)) bucket, stable. */
 int lgb_degree_order_ws_bytes(int64_t n_rows, size_t* bytes_host);
@@ -106,6 +106,7 @@ typedef struct lgb_csr {
   const int32_t* long_ptr;
   const int32_t* task_row;
   const int32_t* task_start;
+  const int32_t* task_end;   /* [n_tasks] exclusive end offset of each slice */
 } lgb_csr;
 
 /* ---------------------------------------------------------------------------------------------
@@ -123,6 +124,10 @@ typedef struct lgb_csr {
  * X/Y/resid/acc_* are [n, d] row-major.  partial_ws must hold n_tasks*d floats when g->n_tasks > 0.
  * ------------------------------------------------------------------------------------------- */
 #define LGB_SPMM_MEAN 1
+/* bits 4..7 of flags pick a kernel variant for A/B measurements (d in 33..64 only): 0 = tuned default
+ * (one warp per row / slice, 64 resident warps per SM), 1 = first version (unroll 8), 2/3 = software-pipelined
+ * persistent warps, 4..6 = other unroll / occupancy points.  Variants 0,1,4,5,6 are bit-identical. */
+#define LGB_SPMM_VARIANT_SHIFT 4
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid,
              const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws,
              void* stream);

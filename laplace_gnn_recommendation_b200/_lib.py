@@ -25,7 +25,7 @@ class LgbCsr(C.Structure):
         ("rowptr", c_vp), ("colidx", c_vp), ("val", c_vp), ("row_order", c_vp),
         ("chunk", c_i32), ("_pad", c_i32),
         ("n_long", c_i64), ("n_tasks", c_i64),
-        ("long_rows", c_vp), ("long_ptr", c_vp), ("task_row", c_vp), ("task_start", c_vp),
+        ("long_rows", c_vp), ("long_ptr", c_vp), ("task_row", c_vp), ("task_start", c_vp), ("task_end", c_vp),
     ]
 
 
@@ -55,7 +55,7 @@ PROTOTYPES = {
     "lgb_gcn_norm": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "lgb_spmm_plan_count": (C.c_int, [c_vp, c_i64, c_i32, C.POINTER(c_i64), c_vp, c_sz, c_vp]),
     "lgb_spmm_plan_ws_bytes": (C.c_int, [c_i64, C.POINTER(c_sz)]),
-    "lgb_spmm_plan_fill": (C.c_int, [c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lgb_spmm_plan_fill": (C.c_int, [c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgb_degree_order_ws_bytes": (C.c_int, [c_i64, C.POINTER(c_sz)]),
     "lgb_degree_order": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "lgb_spmm": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp]),

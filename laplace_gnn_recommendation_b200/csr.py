@@ -15,7 +15,11 @@ import torch
 from . import _lib
 from ._lib import LgbCsr, check, ptr, stream
 
-DEFAULT_CHUNK = 1024  # rows with more non-zeros are split into chunk-sized tasks (see csrc/spmm.cu)
+import os as _os
+
+SPMM_VARIANT = int(_os.environ.get("LGB_SPMM_VARIANT", "0"))  # 0 = tuned default; see LGB_SPMM_VARIANT_SHIFT in the header
+DEFAULT_CHUNK = int(_os.environ.get("LGB_SPMM_CHUNK", "1024"))   # rows with more non-zeros are split into chunk-sized tasks (csrc/spmm.cu): bounds the length of
+                      # any sequential fp32 accumulation chain (accuracy) and the work of one warp (load balance)
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -36,7 +40,7 @@ class DeviceCSR:
         self.row_order: Optional[torch.Tensor] = None
         self.n_long = 0
         self.n_tasks = 0
-        self.long_rows = self.long_ptr = self.task_row = self.task_start = None
+        self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
         self.perm: Optional[torch.Tensor] = None      # COO -> CSR permutation (int64) when built from COO
         self.csr2csc: Optional[torch.Tensor] = None   # set on the TRANSPOSED graph: its entry i is CSR entry csr2csc[i]
         self._t: Optional["DeviceCSR"] = None
@@ -85,9 +89,11 @@ class DeviceCSR:
                 self.long_ptr = torch.empty(self.n_long + 1, **i32)
                 self.task_row = torch.empty(self.n_tasks, **i32)
                 self.task_start = torch.empty(self.n_tasks, **i32)
+                self.task_end = torch.empty(self.n_tasks, **i32)
                 check(lib.lgb_spmm_plan_fill(ptr(self.rowptr), self.n_rows, self.chunk, self.n_long, self.n_tasks,
                                              ptr(self.long_rows), ptr(self.long_ptr), ptr(self.task_row),
-                                             ptr(self.task_start), ptr(ws), ws.numel(), stream()), "spmm_plan_fill")
+                                             ptr(self.task_start), ptr(self.task_end), ptr(ws), ws.numel(), stream()),
+                      "spmm_plan_fill")
         self._struct = None
 
     def use_degree_order(self, on: bool = True) -> "DeviceCSR":
@@ -168,7 +174,7 @@ class DeviceCSR:
             s.chunk = self.chunk
             s.n_long, s.n_tasks = self.n_long, self.n_tasks
             s.long_rows, s.long_ptr = ptr(self.long_rows), ptr(self.long_ptr)
-            s.task_row, s.task_start = ptr(self.task_row), ptr(self.task_start)
+            s.task_row, s.task_start, s.task_end = ptr(self.task_row), ptr(self.task_start), ptr(self.task_end)
             self._struct = s
         return self._struct
 
@@ -184,7 +190,7 @@ class DeviceCSR:
     # ---- the hot call -------------------------------------------------------------------
     def spmm(self, X: torch.Tensor, Y: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
              acc_in: Optional[torch.Tensor] = None, acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0,
-             mean: bool = False, want_y: bool = True) -> Optional[torch.Tensor]:
+             mean: bool = False, want_y: bool = True, variant: Optional[int] = None) -> Optional[torch.Tensor]:
         """Y = A @ X with the fused epilogue of lgb_spmm.  Allocates Y when want_y and Y is None."""
         _lib.require_cuda(X)
         if X.dim() != 2 or X.shape[0] != self.n_cols:
@@ -199,6 +205,7 @@ class DeviceCSR:
         lib = _lib.load()
         with torch.cuda.device(self.device):
             check(lib.lgb_spmm(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
-                               float(acc_div), 1 if mean else 0, ptr(self._partial_ws(d)), stream()), "spmm")
+                               float(acc_div), (1 if mean else 0) | ((SPMM_VARIANT if variant is None else variant) << 4),
+                               ptr(self._partial_ws(d)), stream()), "spmm")
         _lib.count_launch(2 if self.n_long else 1)
         return Y

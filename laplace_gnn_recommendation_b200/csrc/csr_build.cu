@@ -168,17 +168,19 @@ __global__ void plan_ntasks_kernel(const int32_t* __restrict__ rowptr, const int
 
 __global__ void plan_tasks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ long_rows,
                                   const int32_t* __restrict__ long_ptr, int64_t n_long, int32_t chunk,
-                                  int32_t* __restrict__ task_row, int32_t* __restrict__ task_start) {
+                                  int32_t* __restrict__ task_row, int32_t* __restrict__ task_start,
+                                  int32_t* __restrict__ task_end) {
   // one warp per long row
   int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= n_long) return;
   int32_t r = long_rows[w];
-  int32_t s = rowptr[r];
+  int32_t s = rowptr[r], e = rowptr[r + 1];
   int32_t t0 = long_ptr[w], t1 = long_ptr[w + 1];
   for (int32_t t = t0 + lane; t < t1; t += 32) {
     task_row[t] = r;
     task_start[t] = s + (t - t0) * chunk;
+    task_end[t] = min(s + (t - t0 + 1) * chunk, e);
   }
 }
 
@@ -370,13 +372,13 @@ int lgb_spmm_plan_count(const int32_t* rowptr, int64_t n_rows, int32_t chunk, in
 }
 
 int lgb_spmm_plan_fill(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int64_t n_long, int64_t n_tasks,
-                       int32_t* long_rows, int32_t* long_ptr, int32_t* task_row, int32_t* task_start, void* ws,
-                       size_t ws_bytes, void* stream_) {
+                       int32_t* long_rows, int32_t* long_ptr, int32_t* task_row, int32_t* task_start, int32_t* task_end,
+                       void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LGB_REQUIRE(rowptr && n_rows >= 0 && chunk > 0 && n_long >= 0 && n_tasks >= 0, LGB_EINVAL,
               "lgb_spmm_plan_fill: bad argument");
   if (n_long == 0) return LGB_OK;
-  LGB_REQUIRE(long_rows && long_ptr && task_row && task_start, LGB_EINVAL, "lgb_spmm_plan_fill: null output");
+  LGB_REQUIRE(long_rows && long_ptr && task_row && task_start && task_end, LGB_EINVAL, "lgb_spmm_plan_fill: null output");
   size_t need = 0;
   int rc = lgb_spmm_plan_ws_bytes(n_rows, &need);
   if (rc) return rc;
@@ -390,7 +392,7 @@ int lgb_spmm_plan_fill(const int32_t* rowptr, int64_t n_rows, int32_t chunk, int
   LGB_LAUNCH_CHECK();
   LGB_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, long_ptr, long_ptr, (int)n_long + 1, stream));
   plan_tasks_kernel<<<blocks_for(n_long * 32, 256), 256, 0, stream>>>(rowptr, long_rows, long_ptr, n_long, chunk,
-                                                                       task_row, task_start);
+                                                                       task_row, task_start, task_end);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
 }

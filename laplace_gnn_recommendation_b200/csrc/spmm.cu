@@ -30,6 +30,7 @@ struct SpmmParams {
   const int32_t* row_order;
   const int32_t* task_row;
   const int32_t* task_start;
+  const int32_t* task_end;
   const int32_t* long_rows;
   const int32_t* long_ptr;
   int64_t n_rows;
@@ -119,8 +120,8 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
 }
 
 // Stage 1: slices of long rows first (heaviest work is scheduled first), then one warp per ordinary row.
-template <int G, int VPL, int UNROLL>
-__global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_rows_kernel(const SpmmParams p) {
+template <int G, int VPL, int UNROLL, int MINB>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const SpmmParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
   float4 acc[VPL];
@@ -150,6 +151,168 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_rows_kernel(const SpmmPa
   if (p.chunk > 0 && e - s > p.chunk) return;  // long row: handled by its slices + stage 2
   accumulate_slice<G, VPL, UNROLL>(p, s, e, lane, acc);
   if (lane < G) epilogue_row<G, VPL>(p, r, e - s, lane, acc);
+}
+
+
+// ---- software-pipelined persistent variant ---------------------------------------------------------
+// ncu on the first version (profiles/r1a_*) showed the kernel latency-bound, not HBM-bound: a short row costs four
+// DEPENDENT memory round trips (rowptr -> col/val -> gathered rows -> acc/resid) and the SM only holds ~28 such
+// chains.  Here every warp is persistent and walks work items w, w+W, w+2W, ... (W = warps in the grid) with a
+// 3-deep software pipeline: while the gathers of item i are in flight, the (col,val) batch of item i+1, the row
+// pointers of item i+2 and the epilogue operands (acc_in / resid rows) of item i are already loading, so an
+// item costs ~one round trip instead of four.  Long-row slices carry their end offset in the plan (task_end), so
+// no stage has a dependent load.  Summation order is identical to spmm_rows_kernel (bit-identical results).
+enum { ITEM_SKIP = 0, ITEM_ROW = 1, ITEM_TASK = 2 };
+
+__device__ __forceinline__ void load_item(const SpmmParams& p, int64_t w, int64_t total, int& r, int& s, int& e, int& kind) {
+  r = 0; s = 0; e = 0; kind = ITEM_SKIP;
+  if (w >= total) return;
+  if (w < p.n_tasks) {
+    r = ld_stream_i32(p.task_row + w);
+    s = ld_stream_i32(p.task_start + w);
+    e = ld_stream_i32(p.task_end + w);
+    kind = ITEM_TASK;
+    return;
+  }
+  const int64_t ri = w - p.n_tasks;
+  r = p.row_order ? p.row_order[ri] : (int)ri;
+  s = p.rowptr[r];
+  e = p.rowptr[r + 1];
+  kind = ITEM_ROW;
+}
+
+__device__ __forceinline__ void load_first_batch(const SpmmParams& p, int s, int e, int lane, int& c, float& w) {
+  c = 0; w = 0.f;
+  const int idx = s + lane;
+  if (idx < e) {
+    c = ld_stream_i32(p.colidx + idx);
+    w = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+  }
+}
+
+template <int G, int VPL, int UNROLL>
+__device__ __forceinline__ void accumulate_slice_pf(const SpmmParams& p, int s, int e, int lane, int c, float w,
+                                                    float4 (&acc)[VPL]) {
+  constexpr int NG = 32 / G;
+  const int grp = lane / G;
+  const int lig = lane % G;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  const int d4 = p.d4;
+  for (int base = s; base < e; base += 32) {
+    // next (col,val) batch of this item is requested before the current one is consumed
+    int cn = 0;
+    float wn = 0.f;
+    const int nidx = base + 32 + lane;
+    if (nidx < e) {
+      cn = ld_stream_i32(p.colidx + nidx);
+      wn = p.val ? ld_stream_f32(p.val + nidx) : 1.f;
+    }
+    const int cnt = min(32, e - base);
+    for (int j = 0; j < cnt; j += NG * UNROLL) {
+      float4 v[UNROLL][VPL];
+      float ww[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int k = j + u * NG + grp;
+        const int cc = __shfl_sync(FULL_MASK, c, k & 31);
+        const float wk = __shfl_sync(FULL_MASK, w, k & 31);
+        const bool ok = k < cnt;
+        ww[u] = ok ? wk : 0.f;
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int f = lig + q * G;
+          v[u][q] = (ok && f < d4) ? ld_gather_f4(X4 + (size_t)cc * d4 + f) : f4_zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) f4_fma(acc[q], ww[u], v[u][q]);
+    }
+    c = cn;
+    w = wn;
+  }
+#pragma unroll
+  for (int off = G; off < 32; off <<= 1)
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = f4_add(acc[q], f4_shfl_xor(acc[q], off));
+}
+
+template <int G, int VPL, int UNROLL>
+__global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * SPMM_WARPS;
+  const int64_t total = p.n_tasks + p.n_rows;
+  int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+
+  int r0, s0, e0, k0, r1, s1, e1, k1;
+  load_item(p, w, total, r0, s0, e0, k0);
+  load_item(p, w + nw, total, r1, s1, e1, k1);
+  int c0;
+  float v0;
+  load_first_batch(p, s0, e0, lane, c0, v0);
+
+  for (; w < total; w += nw) {
+    int r2, s2, e2, k2;
+    load_item(p, w + 2 * nw, total, r2, s2, e2, k2);   // row pointers two items ahead
+    if (k1 == ITEM_ROW && p.chunk > 0 && e1 - s1 > p.chunk) k1 = ITEM_SKIP;   // long row: its slices do the work
+    int c1 = 0;
+    float v1 = 0.f;
+    if (k1 != ITEM_SKIP) load_first_batch(p, s1, e1, lane, c1, v1);           // (col,val) one item ahead
+    if (k0 == ITEM_ROW && p.chunk > 0 && e0 - s0 > p.chunk) k0 = ITEM_SKIP;
+
+    if (k0 != ITEM_SKIP) {
+      // epilogue operands of THIS row are requested now and consumed after the gathers
+      float4 pre_acc[VPL], pre_res[VPL];
+      const bool row_out = (k0 == ITEM_ROW) && lane < G;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int f = lane + q * G;
+        const bool ok = row_out && f < p.d4;
+        pre_acc[q] = (ok && p.acc_in) ? ld_stream_f4(reinterpret_cast<const float4*>(p.acc_in) + (size_t)r0 * p.d4 + f) : f4_zero();
+        pre_res[q] = (ok && p.resid) ? ld_stream_f4(reinterpret_cast<const float4*>(p.resid) + (size_t)r0 * p.d4 + f) : f4_zero();
+      }
+      float4 acc[VPL];
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
+      accumulate_slice_pf<G, VPL, UNROLL>(p, s0, e0, lane, c0, v0, acc);
+      if (lane < G) {
+        if (k0 == ITEM_TASK) {
+          float4* out = reinterpret_cast<float4*>(p.partial) + (size_t)w * p.d4;
+#pragma unroll
+          for (int q = 0; q < VPL; ++q) {
+            const int f = lane + q * G;
+            if (f < p.d4) st_f4(out + f, acc[q]);
+          }
+        } else {
+          const size_t rowoff = (size_t)r0 * p.d4;
+          const int deg = e0 - s0;
+#pragma unroll
+          for (int q = 0; q < VPL; ++q) {
+            const int f = lane + q * G;
+            if (f >= p.d4) continue;
+            float4 y = acc[q];
+            if (p.mean) {
+              const float c = (float)max(deg, 1);
+              y.x = __fdiv_rn(y.x, c); y.y = __fdiv_rn(y.y, c); y.z = __fdiv_rn(y.z, c); y.w = __fdiv_rn(y.w, c);
+            }
+            if (p.resid) y = f4_add(y, pre_res[q]);
+            if (p.Y) st_f4(reinterpret_cast<float4*>(p.Y) + rowoff + f, y);
+            if (p.acc_out) {
+              float4 a = p.acc_in ? f4_add(pre_acc[q], y) : y;
+              if (p.acc_div != 1.0f) {
+                a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
+                a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
+              }
+              st_f4(reinterpret_cast<float4*>(p.acc_out) + rowoff + f, a);
+            }
+          }
+        }
+      }
+    }
+    r0 = r1; s0 = s1; e0 = e1; k0 = k1; c0 = c1; v0 = v1;
+    r1 = r2; s1 = s2; e1 = e2; k1 = k2;
+  }
 }
 
 // Stage 2: one CTA per long row sums that row's partials in a fixed order, then runs the epilogue.
@@ -210,13 +373,36 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_scalar_kernel(const Spmm
   }
 }
 
-template <int G, int VPL, int UNROLL>
-static int launch_vec(const SpmmParams& p, cudaStream_t stream) {
-  const int64_t warps = p.n_tasks + p.n_rows;
-  if (warps > 0) {
-    const int64_t blocks = (warps + SPMM_WARPS - 1) / SPMM_WARPS;
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_sm_count = n;
+    else
+      return 148;
+  }
+  return g_sm_count;
+}
+
+template <int G, int VPL, int UNROLL, int MINB = 1>
+static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
+  const int64_t items = p.n_tasks + p.n_rows;
+  if (items > 0) {
+    const int64_t blocks = (items + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_rows_kernel<G, VPL, UNROLL><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    if (variant == 1 || (p.n_tasks > 0 && !p.task_end)) {
+      spmm_rows_kernel<G, VPL, UNROLL, MINB><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    } else {
+      // persistent grid: every SM filled to the occupancy limit, each warp walks items w, w+W, ...
+      static int occ = 0;
+      if (occ == 0) {
+        LGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_pipe_kernel<G, VPL, UNROLL>, SPMM_WARPS * 32, 0));
+        if (occ <= 0) occ = 1;
+      }
+      const int64_t resident = (int64_t)sm_count() * occ;
+      spmm_pipe_kernel<G, VPL, UNROLL><<<(unsigned)std::min<int64_t>(blocks, resident), SPMM_WARPS * 32, 0, stream>>>(p);
+    }
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
@@ -314,7 +500,7 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
   if (g->n_rows == 0) return LGB_OK;
   SpmmParams p;
   p.rowptr = g->rowptr; p.colidx = g->colidx; p.val = g->val; p.row_order = g->row_order;
-  p.task_row = g->task_row; p.task_start = g->task_start; p.long_rows = g->long_rows; p.long_ptr = g->long_ptr;
+  p.task_row = g->task_row; p.task_start = g->task_start; p.task_end = g->task_end; p.long_rows = g->long_rows; p.long_ptr = g->long_ptr;
   p.n_rows = g->n_rows; p.n_tasks = g->chunk > 0 ? g->n_tasks : 0; p.n_long = g->chunk > 0 ? g->n_long : 0;
   p.chunk = g->chunk; p.d4 = d / 4;
   p.X = X; p.Y = Y; p.resid = resid; p.acc_in = acc_in; p.acc_out = acc_out; p.acc_div = acc_div;
@@ -331,11 +517,26 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
     return LGB_OK;
   }
   const int d4 = d / 4;
-  if (d4 <= 8) return launch_vec<8, 1, 4>(p, stream);
-  if (d4 <= 16) return launch_vec<16, 1, 8>(p, stream);
-  if (d4 <= 32) return launch_vec<32, 1, 8>(p, stream);
-  if (d4 <= 64) return launch_vec<32, 2, 4>(p, stream);
-  if (d4 <= 128) return launch_vec<32, 4, 2>(p, stream);
+  // Variant 0 is the tuned default.  Measured on B200 (profiles/r1b_*): the kernel is latency-bound, so the
+  // configuration that keeps 64 warps resident per SM (<= 32 registers: gather unroll 2, __launch_bounds__(128,16))
+  // beats deeper unrolls (72 regs -> 28 warps) by 1.3x and the software-pipelined persistent variant by 1.5x.
+  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xF;
+  if (d4 <= 8) return launch_vec<8, 1, 2, 16>(p, 1, stream);
+  if (d4 <= 16) {
+    switch (variant) {
+      case 0: return launch_vec<16, 1, 2, 16>(p, 1, stream);   // default
+      case 1: return launch_vec<16, 1, 8>(p, 1, stream);       // first version (r1a)
+      case 2: return launch_vec<16, 1, 8>(p, 0, stream);       // software-pipelined persistent warps, unroll 8
+      case 3: return launch_vec<16, 1, 4>(p, 0, stream);       // software-pipelined persistent warps, unroll 4
+      case 4: return launch_vec<16, 1, 4>(p, 1, stream);
+      case 5: return launch_vec<16, 1, 4, 12>(p, 1, stream);
+      case 6: return launch_vec<16, 1, 1, 16>(p, 1, stream);
+      default: return launch_vec<16, 1, 2, 16>(p, 1, stream);
+    }
+  }
+  if (d4 <= 32) return (variant == 1) ? launch_vec<32, 1, 8>(p, 1, stream) : launch_vec<32, 1, 2, 16>(p, 1, stream);
+  if (d4 <= 64) return launch_vec<32, 2, 2, 12>(p, 1, stream);
+  if (d4 <= 128) return launch_vec<32, 4, 1, 8>(p, 1, stream);
   set_error("lgb_spmm: d=%d > 512 not supported", d);
   return LGB_EINVAL;
 }

@@ -1,0 +1,59 @@
+"""Probe: time lgb_spmm on the H&M-shaped graph split into its two halves (user rows <- items, item rows <- users)
+for a list of kernel variants.  python tools/spmm_probe.py [--degree powerlaw|uniform] [--variants 1,3,6] [--d 64]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import laplace_gnn_recommendation_b200 as lg  # noqa: E402
+from bench import WORKLOADS, make_graph, spmm_bytes  # noqa: E402
+from laplace_gnn_recommendation_b200.dist import CudaOps  # noqa: E402
+
+
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--degree", default="powerlaw")
+    ap.add_argument("--variants", default="1,3,6")
+    ap.add_argument("--d", type=int, default=64)
+    ap.add_argument("--workload", default="hm")
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    U, I, E = WORKLOADS[a.workload]
+    users, items = make_graph(U, I, E, a.degree, 1234, dev)
+    row = torch.cat([users, items + U]); col = torch.cat([items + U, users])
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(U + I, U + I))
+    g = lg.gcn_norm(adj, add_self_loops=False).csr()
+    ops = CudaOps(dev)
+    gu, gi = ops.row_view(g, 0, U), ops.row_view(g, U, U + I)
+    N, d = U + I, a.d
+    X = torch.randn(N, d, device=dev); Y = torch.empty(N, d, device=dev); acc = torch.randn(N, d, device=dev)
+    print(f"graph: nnz={g.nnz} n_long={g.n_long} n_tasks={g.n_tasks} | users view nnz={gu.nnz} long={gu.n_long} tasks={gu.n_tasks}"
+          f" | items view nnz={gi.nnz} long={gi.n_long} tasks={gi.n_tasks}")
+    for v in [int(x) for x in a.variants.split(",")]:
+        t_full = timeit(lambda: g.spmm(X, Y=Y, acc_in=acc, acc_out=acc, variant=v))
+        t_plain = timeit(lambda: g.spmm(X, Y=Y, variant=v))
+        t_u = timeit(lambda: gu.spmm(X, Y=Y[:U], variant=v))
+        t_i = timeit(lambda: gi.spmm(X, Y=Y[U:], variant=v))
+        gb = spmm_bytes(g.nnz, N, d) / 1e9
+        print(f"variant {v}: full+acc {t_full:.3f} ms | plain {t_plain:.3f} ms ({gb / t_plain:.0f} GB/s alg) | "
+              f"user rows {t_u:.3f} ms ({spmm_bytes(gu.nnz, U, d) / 1e6 / t_u:.0f} GB/s) | "
+              f"item rows {t_i:.3f} ms ({spmm_bytes(gi.nnz, I, d) / 1e6 / t_i:.0f} GB/s)")
+
+
+if __name__ == "__main__":
+    main()
