@@ -315,6 +315,123 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
   }
 }
 
+
+// ---- async-copy (LDGSTS) gather pipeline --------------------------------------------------------------
+// The ncu captures (profiles/r1b_*) show the gather latency-bound even at 64 resident warps: a warp can only keep
+// UNROLL register-backed loads in flight.  Here every lane owns S 16-byte slots of shared memory and streams its
+// piece of the gathered rows through them with cp.async (SASS LDGSTS): S gathers per lane in flight at NO
+// register cost, the FMA reads the slot back with a conflict-free LDS.128.  Only the issuing lane ever touches its
+// slots, so cp.async.wait_group is the only synchronisation.  (col,val) batches are double-buffered in registers.
+// Summation order per row is the same as spmm_rows_kernel (entries ascending within a lane group).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int G, int S, int MINB>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_async_kernel(const SpmmParams p) {
+  constexpr int NG = 32 / G;
+  constexpr int STEPS_PER_BATCH = 32 / NG;
+  static_assert(S <= STEPS_PER_BATCH, "pipeline may run at most one (col,val) batch ahead");
+  __shared__ float4 ring[SPMM_WARPS][S][32];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int grp = lane / G, lig = lane % G;
+  const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + wib;
+  const int d4 = p.d4;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  float4* my = &ring[wib][0][lane];
+
+  int r, s, e;
+  bool is_task = false;
+  if (w < p.n_tasks) {
+    r = p.task_row[w]; s = p.task_start[w]; e = p.task_end[w]; is_task = true;
+  } else {
+    const int64_t ri = w - p.n_tasks;
+    if (ri >= p.n_rows) return;
+    r = p.row_order ? p.row_order[ri] : (int)ri;
+    s = p.rowptr[r]; e = p.rowptr[r + 1];
+    if (p.chunk > 0 && e - s > p.chunk) return;
+  }
+  const int n_ent = e - s;
+  const int T = (n_ent + NG - 1) / NG;   // pipeline steps of this item
+
+  // (col,val) of batch 0 and batch 1
+  int c_cur = 0, c_nxt = 0;
+  float w_cur = 0.f, w_nxt = 0.f;
+  if (lane < n_ent) { c_cur = ld_stream_i32(p.colidx + s + lane); w_cur = p.val ? ld_stream_f32(p.val + s + lane) : 1.f; }
+  if (32 + lane < n_ent) { c_nxt = ld_stream_i32(p.colidx + s + 32 + lane); w_nxt = p.val ? ld_stream_f32(p.val + s + 32 + lane) : 1.f; }
+
+  auto issue = [&](int ti, int consume_batch) {
+    if (ti < T) {
+      const int k = ti * NG + grp;
+      const int kk = k & 31;
+      const int cc = ((k >> 5) == consume_batch) ? __shfl_sync(FULL_MASK, c_cur, kk) : __shfl_sync(FULL_MASK, c_nxt, kk);
+      if (k < n_ent && lig < d4) cp_async_16(my + (ti % S) * 32, X4 + (size_t)cc * d4 + lig);
+    }
+    cp_async_commit();
+  };
+
+  float4 acc = f4_zero();
+#pragma unroll
+  for (int ti = 0; ti < S - 1; ++ti) issue(ti, 0);
+  for (int t = 0; t < T; ++t) {
+    const int cb = (t * NG) >> 5;
+    issue(t + S - 1, cb);
+    cp_async_wait<S - 1>();
+    const int k = t * NG + grp;
+    const float wk = __shfl_sync(FULL_MASK, w_cur, k & 31);
+    if (k < n_ent && lig < d4) {
+      const float4 v = my[(t % S) * 32];
+      f4_fma(acc, wk, v);
+    }
+    if (((t + 1) * NG & 31) == 0) {   // consume side crosses into the next batch: rotate and prefetch the one after
+      c_cur = c_nxt; w_cur = w_nxt;
+      c_nxt = 0; w_nxt = 0.f;
+      const int idx = (cb + 2) * 32 + lane;
+      if (idx < n_ent) { c_nxt = ld_stream_i32(p.colidx + s + idx); w_nxt = p.val ? ld_stream_f32(p.val + s + idx) : 1.f; }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int off = G; off < 32; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
+  float4 a1[1] = {acc};
+  if (lane < G) {
+    if (is_task) {
+      if (lane < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + lane, acc);
+    } else {
+      epilogue_row<G, 1>(p, r, n_ent, lane, a1);
+    }
+  }
+}
+
+template <int G, int VPL>
+__global__ void spmm_long_reduce_kernel(const SpmmParams p);
+
+template <int G, int S, int MINB>
+static int launch_async(const SpmmParams& p, cudaStream_t stream) {
+  const int64_t items = p.n_tasks + p.n_rows;
+  if (items > 0) {
+    const int64_t blocks = (items + SPMM_WARPS - 1) / SPMM_WARPS;
+    LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
+    static bool configured = false;
+    if (!configured) {
+      LGB_CUDA(cudaFuncSetAttribute(spmm_async_kernel<G, S, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      configured = true;
+    }
+    spmm_async_kernel<G, S, MINB><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  if (p.n_long > 0) {
+    spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  return LGB_OK;
+}
+
 // Stage 2: one CTA per long row sums that row's partials in a fixed order, then runs the epilogue.
 template <int G, int VPL>
 __global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams p) {
@@ -531,6 +648,11 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
       case 4: return launch_vec<16, 1, 4>(p, 1, stream);
       case 5: return launch_vec<16, 1, 4, 12>(p, 1, stream);
       case 6: return launch_vec<16, 1, 1, 16>(p, 1, stream);
+      case 7: return launch_async<16, 4, 16>(p, stream);
+      case 8: return launch_async<16, 6, 16>(p, stream);
+      case 9: return launch_async<16, 8, 12>(p, stream);
+      case 10: return launch_async<16, 12, 8>(p, stream);
+      case 11: return launch_async<16, 16, 6>(p, stream);
       default: return launch_vec<16, 1, 2, 16>(p, 1, stream);
     }
   }
