@@ -178,6 +178,8 @@ typedef struct lgb_bpr_args {
   float lambda;
   float gscale;            /* extra factor folded into the *_f gradients, e.g. 1/(K+1) */
   int32_t _pad;
+  int64_t user_lo;         /* with index arrays: only triples with user_lo <= iu[b] < user_hi are processed and the   */
+  int64_t user_hi;         /* user row becomes iu[b]-user_lo (a rank's shard of a global batch); user_hi == 0 = no filter */
   const float* gout;       /* device scalar upstream gradient or NULL */
   float* duf; float* du0; float* dpf; float* dp0; float* dnf; float* dn0;   /* each may be NULL */
   float* loss;             /* device float[1], may be NULL when only gradients are wanted */

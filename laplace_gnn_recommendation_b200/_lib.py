@@ -35,6 +35,7 @@ class LgbBprArgs(C.Structure):
         ("uf", c_vp), ("u0", c_vp), ("pf", c_vp), ("p0", c_vp), ("nf", c_vp), ("n0", c_vp),
         ("iu", c_vp), ("ip", c_vp), ("in_", c_vp),
         ("B", c_i64), ("B_norm", c_i64), ("d", c_i32), ("lambda_", c_f32), ("gscale", c_f32), ("_pad", c_i32),
+        ("user_lo", c_i64), ("user_hi", c_i64),
         ("gout", c_vp),
         ("duf", c_vp), ("du0", c_vp), ("dpf", c_vp), ("dp0", c_vp), ("dnf", c_vp), ("dn0", c_vp),
         ("loss", c_vp), ("ws", c_vp),

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
   const lgb_bpr_args& a = p.a;
   const int lig = threadIdx.x % G;
   const int64_t b = (int64_t)blockIdx.x * GROUPS + threadIdx.x / G;
-  const bool active = b < a.B;
+  bool active = b < a.B;
   const int d4 = p.d4;
   float sp = 0.f, reg = 0.f;
 
@@ -46,6 +46,10 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
     ru = INDEXED ? a.iu[b] : b;
     rp = INDEXED ? a.ip[b] : b;
     rn = INDEXED ? a.in[b] : b;
+    if (INDEXED && a.user_hi > 0) {   // this rank only owns users [user_lo, user_hi)
+      active = ru >= a.user_lo && ru < a.user_hi;
+      ru -= a.user_lo;
+    }
   }
   float4 uf[VPL], pf[VPL], nf[VPL], u0[VPL], p0[VPL], n0[VPL];
   float pos = 0.f, neg = 0.f, rsq = 0.f;
@@ -138,10 +142,13 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_scalar_kernel(const BprParams
   const lgb_bpr_args& a = p.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (BPR_THREADS / 32) + warp;
-  const bool active = b < a.B;
+  bool active = b < a.B;
   const int d = a.d;
   int64_t ru = 0, rp = 0, rn = 0;
-  if (active) { ru = INDEXED ? a.iu[b] : b; rp = INDEXED ? a.ip[b] : b; rn = INDEXED ? a.in[b] : b; }
+  if (active) {
+    ru = INDEXED ? a.iu[b] : b; rp = INDEXED ? a.ip[b] : b; rn = INDEXED ? a.in[b] : b;
+    if (INDEXED && a.user_hi > 0) { active = ru >= a.user_lo && ru < a.user_hi; ru -= a.user_lo; }
+  }
   float pos = 0.f, neg = 0.f, rsq = 0.f;
   if (active)
     for (int f = lane; f < d; f += 32) {

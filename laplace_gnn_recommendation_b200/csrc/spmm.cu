@@ -316,6 +316,118 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
 }
 
 
+
+// ---- sub-warp rows: one lane GROUP per short row ------------------------------------------------------------
+// Probe (tools/dist_probe.py, tools/spmm_probe.py): with many short rows the launch time is (#rows / resident warps) x
+// the per-row dependent chain rowptr -> (col,val) -> gathers -> epilogue, NOT bytes.  For d <= 64 a row is only G = d/4
+// lanes wide, so a warp can run 32/G independent row chains at once: warp w owns rows NG*w .. NG*w+NG-1, one per lane
+// group, when all of them are short (<= SUBW_MAX non-zeros); otherwise it walks them one by one with the whole warp
+// (the spmm_rows_kernel path).  No cross-group reduction in sub-warp mode; per-row summation order is plain ascending.
+constexpr int SUBW_MAX = 64;
+
+template <int G, int UNROLL, int MINB>
+__global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
+  constexpr int NG = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / G, lig = lane % G;
+  const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  const int d4 = p.d4;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+
+  if (w < p.n_tasks) {   // slices of long rows: whole warp, partial sums
+    float4 acc[1] = {f4_zero()};
+    const int r = p.task_row[w];
+    (void)r;
+    const int s = p.task_start[w], e = p.task_end[w];
+    accumulate_slice<G, 1, UNROLL>(p, s, e, lane, acc);
+    if (lane < G && lane < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + lane, acc[0]);
+    return;
+  }
+  const int64_t first = (w - p.n_tasks) * NG;
+  if (first >= p.n_rows) return;
+  // every group fetches the bounds of its own row
+  const int64_t ri = first + grp;
+  int r = -1, s = 0, e = 0;
+  if (ri < p.n_rows) {
+    r = p.row_order ? p.row_order[ri] : (int)ri;
+    s = p.rowptr[r];
+    e = p.rowptr[r + 1];
+  }
+  int deg = e - s;
+  const bool is_long = p.chunk > 0 && deg > p.chunk;   // handled by its slices + stage 2
+  if (is_long) { deg = 0; }
+  const bool all_short = __all_sync(FULL_MASK, deg <= SUBW_MAX);
+
+  if (all_short) {
+    int maxdeg = deg;
+#pragma unroll
+    for (int off = G; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL_MASK, maxdeg, off));
+    float4 acc = f4_zero();
+    for (int base = 0; base < maxdeg; base += G) {
+      const int idx = s + base + lig;
+      int c = 0;
+      float wv = 0.f;
+      if (base + lig < deg) {
+        c = ld_stream_i32(p.colidx + idx);
+        wv = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+      }
+      const int cnt = min(G, deg - base);          // may be <= 0 for the shorter row of the pair
+      const int cntmax = min(G, maxdeg - base);
+      for (int j = 0; j < cntmax; j += UNROLL) {
+        float4 v[UNROLL];
+        float ww[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const int k = j + u;
+          const int cc = __shfl_sync(FULL_MASK, c, k & (G - 1), G);
+          const float wk = __shfl_sync(FULL_MASK, wv, k & (G - 1), G);
+          const bool ok = k < cnt;
+          ww[u] = ok ? wk : 0.f;
+          v[u] = (ok && lig < d4) ? ld_gather_f4(X4 + (size_t)cc * d4 + lig) : f4_zero();
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) f4_fma(acc, ww[u], v[u]);
+      }
+    }
+    if (r >= 0 && !is_long) {
+      float4 a1[1] = {acc};
+      epilogue_row<G, 1>(p, r, e - s, lig, a1);
+    }
+    return;
+  }
+  // mixed / longer rows: the whole warp walks the NG rows one after the other
+#pragma unroll 1
+  for (int g2 = 0; g2 < NG; ++g2) {
+    const int rr = __shfl_sync(FULL_MASK, r, g2 * G);
+    const int ss = __shfl_sync(FULL_MASK, s, g2 * G);
+    const int ee = __shfl_sync(FULL_MASK, e, g2 * G);
+    if (rr < 0 || (p.chunk > 0 && ee - ss > p.chunk)) continue;
+    float4 acc[1] = {f4_zero()};
+    accumulate_slice<G, 1, UNROLL>(p, ss, ee, lane, acc);
+    if (lane < G) epilogue_row<G, 1>(p, rr, ee - ss, lane, acc);
+  }
+}
+
+template <int G, int VPL>
+__global__ void spmm_long_reduce_kernel(const SpmmParams p);
+
+template <int G, int UNROLL, int MINB>
+static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
+  constexpr int NG = 32 / G;
+  const int64_t warps = p.n_tasks + (p.n_rows + NG - 1) / NG;
+  if (warps > 0) {
+    const int64_t blocks = (warps + SPMM_WARPS - 1) / SPMM_WARPS;
+    LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
+    spmm_subwarp_kernel<G, UNROLL, MINB><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  if (p.n_long > 0) {
+    spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  return LGB_OK;
+}
+
 // ---- async-copy (LDGSTS) gather pipeline --------------------------------------------------------------
 // The ncu captures (profiles/r1b_*) show the gather latency-bound even at 64 resident warps: a warp can only keep
 // UNROLL register-backed loads in flight.  Here every lane owns S 16-byte slots of shared memory and streams its
@@ -638,10 +750,11 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
   // configuration that keeps 64 warps resident per SM (<= 32 registers: gather unroll 2, __launch_bounds__(128,16))
   // beats deeper unrolls (72 regs -> 28 warps) by 1.3x and the software-pipelined persistent variant by 1.5x.
   const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xF;
-  if (d4 <= 8) return launch_vec<8, 1, 2, 16>(p, 1, stream);
+  if (d4 <= 8) return (variant == 1) ? launch_vec<8, 1, 2, 16>(p, 1, stream) : launch_subwarp<8, 2, 16>(p, stream);
   if (d4 <= 16) {
     switch (variant) {
-      case 0: return launch_vec<16, 1, 2, 16>(p, 1, stream);   // default
+      case 0: return launch_subwarp<16, 2, 16>(p, stream);     // default: sub-warp rows, 64 resident warps
+      case 12: return launch_vec<16, 1, 2, 16>(p, 1, stream);  // warp per row, unroll 2, 64 resident warps (r1b best)
       case 1: return launch_vec<16, 1, 8>(p, 1, stream);       // first version (r1a)
       case 2: return launch_vec<16, 1, 8>(p, 0, stream);       // software-pipelined persistent warps, unroll 8
       case 3: return launch_vec<16, 1, 4>(p, 0, stream);       // software-pipelined persistent warps, unroll 4
@@ -653,7 +766,10 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
       case 9: return launch_async<16, 8, 12>(p, stream);
       case 10: return launch_async<16, 12, 8>(p, stream);
       case 11: return launch_async<16, 16, 6>(p, stream);
-      default: return launch_vec<16, 1, 2, 16>(p, 1, stream);
+      case 13: return launch_subwarp<16, 4, 12>(p, stream);
+      case 14: return launch_subwarp<16, 4, 10>(p, stream);
+      case 15: return launch_subwarp<16, 8, 8>(p, stream);
+      default: return launch_subwarp<16, 2, 16>(p, stream);
     }
   }
   if (d4 <= 32) return (variant == 1) ? launch_vec<32, 1, 8>(p, 1, stream) : launch_vec<32, 1, 2, 16>(p, 1, stream);

@@ -69,6 +69,7 @@ class CudaOps:
             raise RuntimeError("ShardedLightGCN needs CUDA devices (no CPU fallback); tests inject their own ops object")
         self.device, self.group = device, group
         self.comm = torch.cuda.Stream(device=device)
+        self._bpr_ws = None
 
     # graph ----------------------------------------------------------------------------------
     def build_graph(self, row, col, n, dinv):
@@ -99,14 +100,16 @@ class CudaOps:
         with torch.cuda.device(self.device):
             check(_lib.load().lgb_zero(ptr(t), t.numel() * t.element_size(), stream()), "zero")
 
-    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
+    def bpr(self, Ef, E0, Ug, lo, hi, u, p, n, lam, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
+        """BPR over the triples of the GLOBAL batch whose user this rank owns (lo <= u < hi); static shapes."""
         d = Ef.shape[1]
         off = Ug * d * 4
         a = LgbBprArgs()
         a.uf, a.pf, a.nf = Ef.data_ptr(), Ef.data_ptr() + off, Ef.data_ptr() + off
         a.u0, a.p0, a.n0 = E0.data_ptr(), E0.data_ptr() + off, E0.data_ptr() + off
         a.iu, a.ip, a.in_ = ptr(u), ptr(p), ptr(n)
-        a.B, a.B_norm, a.d, a.lambda_, a.gscale = u.numel(), int(B_norm), d, float(lam), float(gscale)
+        a.B, a.B_norm, a.d, a.lambda_, a.gscale = u.numel(), u.numel(), d, float(lam), float(gscale)
+        a.user_lo, a.user_hi = int(lo), int(hi)
         if dEf is not None:
             a.duf, a.dpf, a.dnf = dEf.data_ptr(), dEf.data_ptr() + off, dEf.data_ptr() + off
         if dE0_users is not None:
@@ -114,10 +117,10 @@ class CudaOps:
         if dE0_items is not None:
             a.dp0 = a.dn0 = dE0_items.data_ptr()
         if loss is not None:
-            ws = _bpr_ws(max(u.numel(), 1), Ef.device)
-            a.loss, a.ws = loss.data_ptr(), ptr(ws)
-            self._keep = ws
-        if u.numel() == 0:
+            if self._bpr_ws is None or self._bpr_ws.numel() < 2 * int(_lib.load().lgb_bpr_blocks(u.numel())):
+                self._bpr_ws = _bpr_ws(max(u.numel(), 1), Ef.device)
+            a.loss, a.ws = loss.data_ptr(), ptr(self._bpr_ws)
+        if hi <= lo or u.numel() == 0:      # this rank owns no user: contributes nothing
             if loss is not None:
                 self.zero(loss)
             return
@@ -133,7 +136,6 @@ class CudaOps:
         self.comm.wait_stream(cur)
         with torch.cuda.stream(self.comm):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        t.record_stream(self.comm)
         return _StreamWait(self.comm, cur)
 
     def all_reduce(self, t: torch.Tensor):
@@ -206,7 +208,7 @@ class ShardedLightGCN:
         self.E_f = torch.empty(n, self.d, **f32)
         self._ya = torch.empty(n, self.d, **f32)
         self._yb = torch.empty(n, self.d, **f32)
-        self._r = torch.empty(n, self.d, **f32)
+        self._r = torch.empty(n + 1, self.d, **f32)   # + one row that carries the scalar loss through the all-reduce
         self.loss = torch.zeros((), **f32)
 
     def graphs(self):
@@ -220,22 +222,44 @@ class ShardedLightGCN:
     def items_weight(self):
         return self.table[self.Ug:]
 
-    # ---- one propagation layer:  Y = A X (+resid) with the item rows all-reduced ------------------
-    def _layer(self, X, Y, resid=None, acc_in=None, acc_out=None, acc_div=1.0, write_y=True):
-        """Y[:Ug] = G_users X (+resid) ; Y[Ug:] = allreduce(G_items X) (+resid);
-        acc_out (optional) = (acc_in + that) / acc_div on both row blocks."""
+    # ---- propagation with the item-block all-reduce hidden behind TWO SpMM launches ---------------------------
+    # Bipartite dependencies:  users^{k+1} <- items^k (needs the all-reduced item rows)
+    #                          items^{k+1} <- users^k (local rows only)
+    # so all-reduce(items^{k+1}) is only needed by users^{k+2}: it overlaps with users^{k+1} AND items^{k+2}.
+    def _propagate(self, x0, K, resid=None, acc0=None, acc=None, acc_div_last=1.0, out_last=None, before_last_reduce=None):
+        """x_{k+1} = A x_k (+resid) for k < K.  With `acc`: acc = (acc0 + sum_k x_k) / acc_div_last (the last layer's
+        x_K is not materialised).  Without: returns x_K (written to `out_last`).  `before_last_reduce(items_partial)`
+        lets the caller fold extra partial item-row terms into the last all-reduce."""
         Ug, ops = self.Ug, self.ops
-        yi = Y[Ug:]
-        ops.spmm(self.g_items, X, Y=yi)                                     # partial item rows
-        h = ops.all_reduce_async(yi)                                          # ... summed over ranks (comm stream)
-        ops.spmm(self.g_users, X, Y=Y[:Ug] if write_y else None,              # overlaps with the all-reduce
-                 resid=None if resid is None else resid[:Ug],
-                 acc_in=None if acc_in is None else acc_in[:Ug],
-                 acc_out=None if acc_out is None else acc_out[:Ug], acc_div=acc_div)
+        bufs = [self._ya, self._yb]
+        x, pending = x0, None            # pending = (handle, y) of the layer whose item rows are still being reduced
+        for k in range(K):
+            last = k == K - 1
+            y = out_last if (last and out_last is not None) else bufs[k % 2]
+            ops.spmm(self.g_items, x, Y=y[Ug:])                               # items^{k+1} partial (reads user rows of x)
+            if last and before_last_reduce is not None:
+                before_last_reduce(y[Ug:])
+            if pending is not None:                                            # x's item rows must be complete now
+                self._finish_items(*pending)
+            h = ops.all_reduce_async(y[Ug:])
+            div = acc_div_last if last else 1.0
+            ops.spmm(self.g_users, x, Y=None if (last and acc is not None) else y[:Ug],
+                     resid=None if resid is None else resid[:Ug],
+                     acc_in=None if acc is None else (acc0 if k == 0 else acc)[:Ug],
+                     acc_out=None if acc is None else acc[:Ug], acc_div=div)
+            pending = (h, y, resid, None if acc is None else (acc0 if k == 0 else acc), acc, div)
+            x = y
+        if pending is not None:
+            self._finish_items(*pending)
+        return x
+
+    def _finish_items(self, h, y, resid, acc_in, acc_out, div):
+        """Wait for the all-reduce of y's item rows, then apply the epilogue the SpMM could not fuse for them."""
+        Ug, ops = self.Ug, self.ops
         h.wait()
+        yi = y[Ug:]
         if acc_out is not None:
-            ops.accumulate(yi, None if acc_in is None else acc_in[Ug:], None if resid is None else resid[Ug:], acc_div,
-                           acc_out[Ug:])
+            ops.accumulate(yi, None if acc_in is None else acc_in[Ug:], None if resid is None else resid[Ug:], div, acc_out[Ug:])
         elif resid is not None:
             ops.accumulate(yi, None, resid[Ug:], 1.0, yi)
 
@@ -245,53 +269,67 @@ class ShardedLightGCN:
         if K == 0:
             Ef.copy_(E0)
             return Ef
-        x, y = E0, self._ya
-        for k in range(K):
-            last = k == K - 1
-            self._layer(x, y, acc_in=E0 if k == 0 else Ef, acc_out=Ef, acc_div=float(K + 1) if last else 1.0,
-                        write_y=not last)
-            x, y = y, (self._yb if y is self._ya else self._ya)
+        self._propagate(E0, K, acc0=E0, acc=Ef, acc_div_last=float(K + 1))
         return Ef
 
-    def backward(self, r: torch.Tensor, reg=None) -> torch.Tensor:
+    def backward(self, r: torch.Tensor, before_last_reduce=None) -> torch.Tensor:
         """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (item rows already summed over ranks)."""
-        K = self.K
-        if K == 0:
+        if self.K == 0:
             self.grad.copy_(r)
             return self.grad
-        g = r
-        bufs = [self._ya, self._yb]
-        for k in range(K):
-            last = k == K - 1
-            dst = self.grad if last else bufs[k % 2]
-            self._layer(g, dst, resid=r)
-            g = dst
-        return self.grad
+        return self._propagate(r, self.K, resid=r, out_last=self.grad, before_last_reduce=before_last_reduce)
 
     @torch.no_grad()
     def fused_step(self, user_indices: torch.Tensor, pos_item_indices: torch.Tensor, neg_item_indices: torch.Tensor,
                    lambda_val: float) -> torch.Tensor:
-        """Global batch in, global loss out (0-dim tensor, identical on every rank); gradients in ``self.grad``
-        (rows [:Ug] for the owned users, rows [Ug:] for the replicated items, identical on every rank)."""
+        """Global batch in (the same B triples on every rank), global loss out (0-dim tensor, identical on every
+        rank); gradients in ``self.grad`` (rows [:Ug] owned users, rows [Ug:] replicated items, identical on every
+        rank).  Shapes are static (no host sync), so the whole step can be captured in a CUDA graph."""
         ops, Ug, K = self.ops, self.Ug, self.K
-        u, p, n = (t.to(self.device) for t in (user_indices, pos_item_indices, neg_item_indices))
-        B = u.numel()
-        mine = (u >= self.lo) & (u < self.hi)
-        lu, lp, ln = (u[mine] - self.lo).contiguous(), p[mine].contiguous(), n[mine].contiguous()
+        u, p, n = (_lib.i64c(t.to(self.device)) for t in (user_indices, pos_item_indices, neg_item_indices))
         Ef = self.forward()
-        r = self._r
+        r = self._r                                   # [n + 1, d]: the extra row carries the loss through the all-reduce
         ops.zero(r)
-        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, loss=self.loss, dEf=r, gscale=1.0 / (K + 1))
-        # item-row gradient contributions of the local triples are partial sums: reduce them (and the loss)
-        h = ops.all_reduce_async(r[Ug:])
-        ops.all_reduce(self.loss)
-        h.wait()
-        G = self.backward(r)
-        # + 2*lambda*E0 on the batch rows: users locally; items are partial over ranks -> reduce a small buffer
-        reg_items = self._ya[Ug:]
-        ops.zero(reg_items)
-        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, dE0_users=G, dE0_items=reg_items)
-        h = ops.all_reduce_async(reg_items)
-        h.wait()
-        ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
-        return self.loss
+        loss_slot = r[self.n, :1].view(())
+        ops.bpr(Ef, self.table, Ug, self.lo, self.hi, u, p, n, lambda_val, loss=loss_slot, dEf=r, gscale=1.0 / (K + 1))
+        # item-row gradient contributions of the local triples and the loss are partial sums: ONE all-reduce
+        ops.all_reduce_async(r[Ug:]).wait()
+        rr = r[: self.n]
+
+        def add_item_reg(items_partial):              # 2*lambda*E0[p], E0[n] of the local triples ride on the last all-reduce
+            ops.bpr(Ef, self.table, Ug, self.lo, self.hi, u, p, n, lambda_val, dE0_items=items_partial)
+        if K == 0:
+            G = self.backward(rr)
+            reg_items = self._ya[Ug:]
+            ops.zero(reg_items)
+            add_item_reg(reg_items)
+            ops.all_reduce_async(reg_items).wait()
+            ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
+        else:
+            G = self.backward(rr, before_last_reduce=add_item_reg)
+        ops.bpr(Ef, self.table, Ug, self.lo, self.hi, u, p, n, lambda_val, dE0_users=G)   # owned users: local
+        self.loss = loss_slot
+        return loss_slot
+
+    # ---- CUDA-graph replay of the whole step (launch-bound at 8 GPUs: ~40 launches of ~0.1-0.2 ms each) ----------
+    def capture(self, batch_size: int, lambda_val: float):
+        """Capture fused_step for a fixed batch size; returns step(u, p, n) -> loss that replays the graph."""
+        dev = self.device
+        su, sp, sn = (torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(3))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.fused_step(su, sp, sn, lambda_val)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.fused_step(su, sp, sn, lambda_val)
+
+        def step(u, p, n):
+            su.copy_(u, non_blocking=True); sp.copy_(p, non_blocking=True); sn.copy_(n, non_blocking=True)
+            graph.replay()
+            return loss
+        self._graph = graph
+        return step

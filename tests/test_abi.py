@@ -42,7 +42,7 @@ def test_ctypes_table_matches_header(lib):
 def test_struct_layouts():
     from laplace_gnn_recommendation_b200._lib import LgbBprArgs, LgbCsr
     assert C.sizeof(LgbCsr) == 3 * 8 + 4 * 8 + 8 + 2 * 8 + 5 * 8      # mirrors struct lgb_csr
-    assert C.sizeof(LgbBprArgs) == 9 * 8 + 8 + 8 + 4 * 4 + 8 + 6 * 8 + 2 * 8            # mirrors struct lgb_bpr_args
+    assert C.sizeof(LgbBprArgs) == 9 * 8 + 8 + 8 + 4 * 4 + 2 * 8 + 8 + 6 * 8 + 2 * 8            # mirrors struct lgb_bpr_args
 
 
 def test_argument_validation_without_gpu(lib):

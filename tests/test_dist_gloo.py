@@ -45,13 +45,16 @@ class CpuOracleOps:
     def zero(self, t):
         t.zero_()
 
-    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
+    def bpr(self, Ef, E0, Ug, lo_, hi, u, p, n, lam, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
+        B = u.numel()
+        mine = (u >= lo_) & (u < hi)
+        u, p, n = u[mine] - lo_, p[mine], n[mine]
         uf, pf, nf = Ef[u], Ef[Ug + p], Ef[Ug + n]
         u0, p0, n0 = E0[u], E0[Ug + p], E0[Ug + n]
         x = (uf * pf).sum(-1) - (uf * nf).sum(-1)
         if loss is not None:
-            loss.copy_(-F.softplus(x).sum() / B_norm + lam * ((u0 ** 2).sum() + (p0 ** 2).sum() + (n0 ** 2).sum()))
-        c = (-torch.sigmoid(x) / B_norm * gscale).unsqueeze(1)
+            loss.copy_(-F.softplus(x).sum() / B + lam * ((u0 ** 2).sum() + (p0 ** 2).sum() + (n0 ** 2).sum()))
+        c = (-torch.sigmoid(x) / B * gscale).unsqueeze(1)
         if dEf is not None:
             dEf.index_add_(0, u, c * (pf - nf))
             dEf.index_add_(0, Ug + p, c * uf)

@@ -151,14 +151,14 @@ def test_spmm_kernel_variants_agree(cuda_dev, d):
     g = g.with_values(val)
     X = torch.randn(n, d, device=cuda_dev); R = torch.randn(n, d, device=cuda_dev); A = torch.randn(n, d, device=cuda_dev)
     outs = {}
-    for variant in range(12):
+    for variant in range(16):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
     for v in (2, 3):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
-    for v in (1, 4, 5, 6, 7, 8, 9, 10, 11):
+    for v in (1, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
