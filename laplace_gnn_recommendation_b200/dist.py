@@ -100,16 +100,19 @@ class CudaOps:
         with torch.cuda.device(self.device):
             check(_lib.load().lgb_zero(ptr(t), t.numel() * t.element_size(), stream()), "zero")
 
-    def bpr(self, Ef, E0, Ug, lo, hi, u, p, n, lam, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
-        """BPR over the triples of the GLOBAL batch whose user this rank owns (lo <= u < hi); static shapes."""
+    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, user_lo=0, user_hi=0, loss=None, dEf=None, dE0_users=None,
+            dE0_items=None, gscale=1.0):
+        """BPR over triples (u, p, n).  Either the caller already compacted them to this rank's users (local user
+        ids, user_hi == 0), or it passes the GLOBAL batch with global user ids and the owned range
+        [user_lo, user_hi): the kernel then skips foreign triples (static shapes, no host sync).  B_norm = global B."""
         d = Ef.shape[1]
         off = Ug * d * 4
         a = LgbBprArgs()
         a.uf, a.pf, a.nf = Ef.data_ptr(), Ef.data_ptr() + off, Ef.data_ptr() + off
         a.u0, a.p0, a.n0 = E0.data_ptr(), E0.data_ptr() + off, E0.data_ptr() + off
         a.iu, a.ip, a.in_ = ptr(u), ptr(p), ptr(n)
-        a.B, a.B_norm, a.d, a.lambda_, a.gscale = u.numel(), u.numel(), d, float(lam), float(gscale)
-        a.user_lo, a.user_hi = int(lo), int(hi)
+        a.B, a.B_norm, a.d, a.lambda_, a.gscale = u.numel(), int(B_norm), d, float(lam), float(gscale)
+        a.user_lo, a.user_hi = int(user_lo), int(user_hi)
         if dEf is not None:
             a.duf, a.dpf, a.dnf = dEf.data_ptr(), dEf.data_ptr() + off, dEf.data_ptr() + off
         if dE0_users is not None:
@@ -117,10 +120,10 @@ class CudaOps:
         if dE0_items is not None:
             a.dp0 = a.dn0 = dE0_items.data_ptr()
         if loss is not None:
-            if self._bpr_ws is None or self._bpr_ws.numel() < 2 * int(_lib.load().lgb_bpr_blocks(u.numel())):
+            if self._bpr_ws is None or self._bpr_ws.numel() < 2 * int(_lib.load().lgb_bpr_blocks(max(u.numel(), 1))):
                 self._bpr_ws = _bpr_ws(max(u.numel(), 1), Ef.device)
             a.loss, a.ws = loss.data_ptr(), ptr(self._bpr_ws)
-        if hi <= lo or u.numel() == 0:      # this rank owns no user: contributes nothing
+        if u.numel() == 0 or (user_hi > 0 and user_hi <= user_lo):      # nothing to do on this rank
             if loss is not None:
                 self.zero(loss)
             return
@@ -165,9 +168,13 @@ class ShardedLightGCN:
 
     def __init__(self, num_users: int, num_items: int, embedding_dim: int, num_iterations: int,
                  users: torch.Tensor, items: torch.Tensor, device, group=None, ops=None,
-                 rank: Optional[int] = None, world: Optional[int] = None, init_tables=None):
+                 rank: Optional[int] = None, world: Optional[int] = None, init_tables=None,
+                 schedule: str = "layer", static_batch: bool = False):
         self.U, self.I, self.d, self.K = int(num_users), int(num_items), int(embedding_dim), int(num_iterations)
         self.device = torch.device(device)
+        if schedule not in ("layer", "pipelined"):
+            raise ValueError(f"schedule={schedule!r}")
+        self.schedule, self.static_batch = schedule, bool(static_batch)
         inited = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank(group) if inited else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if inited else 1)
@@ -209,7 +216,8 @@ class ShardedLightGCN:
         self._ya = torch.empty(n, self.d, **f32)
         self._yb = torch.empty(n, self.d, **f32)
         self._r = torch.empty(n + 1, self.d, **f32)   # + one row that carries the scalar loss through the all-reduce
-        self.loss = torch.zeros((), **f32)
+        self._loss = torch.zeros((), **f32)
+        self.loss = self._loss
 
     def graphs(self):
         return [self.g_users, self.g_items]
@@ -222,36 +230,19 @@ class ShardedLightGCN:
     def items_weight(self):
         return self.table[self.Ug:]
 
-    # ---- propagation with the item-block all-reduce hidden behind TWO SpMM launches ---------------------------
-    # Bipartite dependencies:  users^{k+1} <- items^k (needs the all-reduced item rows)
-    #                          items^{k+1} <- users^k (local rows only)
-    # so all-reduce(items^{k+1}) is only needed by users^{k+2}: it overlaps with users^{k+1} AND items^{k+2}.
-    def _propagate(self, x0, K, resid=None, acc0=None, acc=None, acc_div_last=1.0, out_last=None, before_last_reduce=None):
-        """x_{k+1} = A x_k (+resid) for k < K.  With `acc`: acc = (acc0 + sum_k x_k) / acc_div_last (the last layer's
-        x_K is not materialised).  Without: returns x_K (written to `out_last`).  `before_last_reduce(items_partial)`
-        lets the caller fold extra partial item-row terms into the last all-reduce."""
+    # ---- schedule "layer" (default; measured on 2/4/8 B200): one all-reduce per layer, overlapped with the users SpMM ----
+    def _layer(self, X, Y, resid=None, acc_in=None, acc_out=None, acc_div=1.0, write_y=True):
+        """Y[:Ug] = G_users X (+resid) ; Y[Ug:] = allreduce(G_items X) (+resid);
+        acc_out (optional) = (acc_in + that) / acc_div on both row blocks."""
         Ug, ops = self.Ug, self.ops
-        bufs = [self._ya, self._yb]
-        x, pending = x0, None            # pending = (handle, y) of the layer whose item rows are still being reduced
-        for k in range(K):
-            last = k == K - 1
-            y = out_last if (last and out_last is not None) else bufs[k % 2]
-            ops.spmm(self.g_items, x, Y=y[Ug:])                               # items^{k+1} partial (reads user rows of x)
-            if last and before_last_reduce is not None:
-                before_last_reduce(y[Ug:])
-            if pending is not None:                                            # x's item rows must be complete now
-                self._finish_items(*pending)
-            h = ops.all_reduce_async(y[Ug:])
-            div = acc_div_last if last else 1.0
-            ops.spmm(self.g_users, x, Y=None if (last and acc is not None) else y[:Ug],
-                     resid=None if resid is None else resid[:Ug],
-                     acc_in=None if acc is None else (acc0 if k == 0 else acc)[:Ug],
-                     acc_out=None if acc is None else acc[:Ug], acc_div=div)
-            pending = (h, y, resid, None if acc is None else (acc0 if k == 0 else acc), acc, div)
-            x = y
-        if pending is not None:
-            self._finish_items(*pending)
-        return x
+        yi = Y[Ug:]
+        ops.spmm(self.g_items, X, Y=yi)                                     # partial item rows
+        h = ops.all_reduce_async(yi)                                          # ... summed over ranks (comm stream)
+        ops.spmm(self.g_users, X, Y=Y[:Ug] if write_y else None,              # overlaps with the all-reduce
+                 resid=None if resid is None else resid[:Ug],
+                 acc_in=None if acc_in is None else acc_in[:Ug],
+                 acc_out=None if acc_out is None else acc_out[:Ug], acc_div=acc_div)
+        self._finish_items(h, Y, resid, acc_in, acc_out, acc_div)
 
     def _finish_items(self, h, y, resid, acc_in, acc_out, div):
         """Wait for the all-reduce of y's item rows, then apply the epilogue the SpMM could not fuse for them."""
@@ -263,41 +254,133 @@ class ShardedLightGCN:
         elif resid is not None:
             ops.accumulate(yi, None, resid[Ug:], 1.0, yi)
 
+    # ---- schedule "pipelined" (opt-in): the all-reduce hidden behind TWO SpMM launches -----------------------------
+    # Bipartite dependencies:  users^{k+1} <- items^k (needs the all-reduced item rows)
+    #                          items^{k+1} <- users^k (local rows only)
+    # so all-reduce(items^{k+1}) is only needed by users^{k+2}: it can overlap with users^{k+1} AND items^{k+2}.
+    # Validated against the oracle over gloo (tests/test_dist_gloo.py); B200 measurement pending.
+    def _propagate_pipelined(self, x0, K, resid=None, acc0=None, acc=None, acc_div_last=1.0, out_last=None,
+                             before_last_reduce=None):
+        Ug, ops = self.Ug, self.ops
+        bufs = [self._ya, self._yb]
+        x, pending = x0, None            # pending = epilogue of the layer whose item rows are still being reduced
+        for k in range(K):
+            last = k == K - 1
+            y = out_last if (last and out_last is not None) else bufs[k % 2]
+            ops.spmm(self.g_items, x, Y=y[Ug:])                               # items^{k+1} partial (reads user rows of x)
+            if last and before_last_reduce is not None:
+                before_last_reduce(y[Ug:])
+            if pending is not None:                                            # x's item rows must be complete now
+                self._finish_items(*pending)
+            h = ops.all_reduce_async(y[Ug:])
+            div = acc_div_last if last else 1.0
+            a_in = None if acc is None else (acc0 if k == 0 else acc)
+            ops.spmm(self.g_users, x, Y=None if (last and acc is not None) else y[:Ug],
+                     resid=None if resid is None else resid[:Ug],
+                     acc_in=None if a_in is None else a_in[:Ug],
+                     acc_out=None if acc is None else acc[:Ug], acc_div=div)
+            pending = (h, y, resid, a_in, acc, div)
+            x = y
+        if pending is not None:
+            self._finish_items(*pending)
+        return x
+
     def forward(self) -> torch.Tensor:
         """E_f = mean_k A^k E0 on the local rows (item rows replicated)."""
         K, E0, Ef = self.K, self.table, self.E_f
         if K == 0:
             Ef.copy_(E0)
             return Ef
-        self._propagate(E0, K, acc0=E0, acc=Ef, acc_div_last=float(K + 1))
+        if self.schedule == "pipelined":
+            self._propagate_pipelined(E0, K, acc0=E0, acc=Ef, acc_div_last=float(K + 1))
+            return Ef
+        x, y = E0, self._ya
+        for k in range(K):
+            last = k == K - 1
+            self._layer(x, y, acc_in=E0 if k == 0 else Ef, acc_out=Ef, acc_div=float(K + 1) if last else 1.0,
+                        write_y=not last)
+            x, y = y, (self._yb if y is self._ya else self._ya)
         return Ef
 
     def backward(self, r: torch.Tensor, before_last_reduce=None) -> torch.Tensor:
-        """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (item rows already summed over ranks)."""
-        if self.K == 0:
+        """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (item rows already summed over ranks).  The local block is
+        symmetric, so A^T is the same pair of row views."""
+        K = self.K
+        if K == 0:
             self.grad.copy_(r)
             return self.grad
-        return self._propagate(r, self.K, resid=r, out_last=self.grad, before_last_reduce=before_last_reduce)
+        if self.schedule == "pipelined":
+            return self._propagate_pipelined(r, K, resid=r, out_last=self.grad, before_last_reduce=before_last_reduce)
+        g = r
+        bufs = [self._ya, self._yb]
+        for k in range(K):
+            last = k == K - 1
+            dst = self.grad if last else bufs[k % 2]
+            if last and before_last_reduce is not None:
+                # fold the extra partial item-row terms into this layer's all-reduce
+                Ug, ops = self.Ug, self.ops
+                ops.spmm(self.g_items, g, Y=dst[Ug:])
+                before_last_reduce(dst[Ug:])
+                h = ops.all_reduce_async(dst[Ug:])
+                ops.spmm(self.g_users, g, Y=dst[:Ug], resid=r[:Ug])
+                self._finish_items(h, dst, r, None, None, 1.0)
+            else:
+                self._layer(g, dst, resid=r)
+            g = dst
+        return self.grad
 
     @torch.no_grad()
     def fused_step(self, user_indices: torch.Tensor, pos_item_indices: torch.Tensor, neg_item_indices: torch.Tensor,
                    lambda_val: float) -> torch.Tensor:
         """Global batch in (the same B triples on every rank), global loss out (0-dim tensor, identical on every
         rank); gradients in ``self.grad`` (rows [:Ug] owned users, rows [Ug:] replicated items, identical on every
-        rank).  Shapes are static (no host sync), so the whole step can be captured in a CUDA graph."""
+        rank)."""
+        if self.static_batch:
+            return self._fused_step_static(user_indices, pos_item_indices, neg_item_indices, lambda_val)
+        ops, Ug, K = self.ops, self.Ug, self.K
+        u, p, n = (t.to(self.device) for t in (user_indices, pos_item_indices, neg_item_indices))
+        B = u.numel()
+        mine = (u >= self.lo) & (u < self.hi)                               # triples of the users this rank owns
+        lu, lp, ln = (u[mine] - self.lo).contiguous(), p[mine].contiguous(), n[mine].contiguous()
+        Ef = self.forward()
+        r = self._r[: self.n]
+        ops.zero(r)
+        loss = self._loss
+        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, loss=loss, dEf=r, gscale=1.0 / (K + 1))
+        # item-row gradient contributions of the local triples are partial sums: reduce them (and the loss)
+        h = ops.all_reduce_async(r[Ug:])
+        ops.all_reduce(loss)
+        h.wait()
+        G = self.backward(r)
+        # + 2*lambda*E0 on the batch rows: users locally; items are partial over ranks -> reduce a small buffer
+        reg_items = self._ya[Ug:]
+        ops.zero(reg_items)
+        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, dE0_users=G, dE0_items=reg_items)
+        ops.all_reduce_async(reg_items).wait()
+        ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
+        self.loss = loss
+        return loss
+
+    @torch.no_grad()
+    def _fused_step_static(self, user_indices, pos_item_indices, neg_item_indices, lambda_val: float) -> torch.Tensor:
+        """Same step with static shapes and no host synchronisation (CUDA-graph capturable): the kernel filters the
+        global batch by the owned user range, the loss rides in an extra row of the residual buffer (one all-reduce
+        for item-row gradients + loss) and the item regulariser terms ride on the last backward all-reduce.
+        Validated over gloo (tests/test_dist_gloo.py); B200 measurement pending."""
         ops, Ug, K = self.ops, self.Ug, self.K
         u, p, n = (_lib.i64c(t.to(self.device)) for t in (user_indices, pos_item_indices, neg_item_indices))
+        B = u.numel()
         Ef = self.forward()
         r = self._r                                   # [n + 1, d]: the extra row carries the loss through the all-reduce
         ops.zero(r)
         loss_slot = r[self.n, :1].view(())
-        ops.bpr(Ef, self.table, Ug, self.lo, self.hi, u, p, n, lambda_val, loss=loss_slot, dEf=r, gscale=1.0 / (K + 1))
-        # item-row gradient contributions of the local triples and the loss are partial sums: ONE all-reduce
-        ops.all_reduce_async(r[Ug:]).wait()
+        flt = dict(user_lo=self.lo, user_hi=self.hi)
+        ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, loss=loss_slot, dEf=r, gscale=1.0 / (K + 1), **flt)
+        ops.all_reduce_async(r[Ug:]).wait()           # item-row gradients + loss: ONE all-reduce
         rr = r[: self.n]
 
-        def add_item_reg(items_partial):              # 2*lambda*E0[p], E0[n] of the local triples ride on the last all-reduce
-            ops.bpr(Ef, self.table, Ug, self.lo, self.hi, u, p, n, lambda_val, dE0_items=items_partial)
+        def add_item_reg(items_partial):              # 2*lambda*E0[p], E0[n] of the local triples
+            ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, dE0_items=items_partial, **flt)
         if K == 0:
             G = self.backward(rr)
             reg_items = self._ya[Ug:]
@@ -307,14 +390,16 @@ class ShardedLightGCN:
             ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
         else:
             G = self.backward(rr, before_last_reduce=add_item_reg)
-        ops.bpr(Ef, self.table, Ug, self.lo, self.hi, u, p, n, lambda_val, dE0_users=G)   # owned users: local
+        ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, dE0_users=G, **flt)   # owned users: local
         self.loss = loss_slot
         return loss_slot
 
-    # ---- CUDA-graph replay of the whole step (launch-bound at 8 GPUs: ~40 launches of ~0.1-0.2 ms each) ----------
+    # ---- CUDA-graph replay of the whole step (opt-in; the 8-GPU step is ~40 launches of 0.1-0.2 ms each) -------------
     def capture(self, batch_size: int, lambda_val: float):
-        """Capture fused_step for a fixed batch size; returns step(u, p, n) -> loss that replays the graph."""
+        """Capture the static-shape step for a fixed batch size; returns step(u, p, n) -> loss that replays the graph.
+        Opt-in and not yet measured on B200 (bench.py --graph)."""
         dev = self.device
+        self.static_batch = True
         su, sp, sn = (torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(3))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -45,10 +45,12 @@ class CpuOracleOps:
     def zero(self, t):
         t.zero_()
 
-    def bpr(self, Ef, E0, Ug, lo_, hi, u, p, n, lam, loss=None, dEf=None, dE0_users=None, dE0_items=None, gscale=1.0):
-        B = u.numel()
-        mine = (u >= lo_) & (u < hi)
-        u, p, n = u[mine] - lo_, p[mine], n[mine]
+    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, user_lo=0, user_hi=0, loss=None, dEf=None, dE0_users=None,
+            dE0_items=None, gscale=1.0):
+        B = B_norm
+        if user_hi > 0:
+            mine = (u >= user_lo) & (u < user_hi)
+            u, p, n = u[mine] - user_lo, p[mine], n[mine]
         uf, pf, nf = Ef[u], Ef[Ug + p], Ef[Ug + n]
         u0, p0, n0 = E0[u], E0[Ug + p], E0[Ug + n]
         x = (uf * pf).sum(-1) - (uf * nf).sum(-1)
@@ -94,14 +96,14 @@ def single_process_reference(pb):
     return lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, pb["K"], pb["u"], pb["p"], pb["n"], pb["lam"])
 
 
-def _worker(rank, world, port, K, out_dir):
+def _worker(rank, world, port, K, out_dir, schedule="layer", static_batch=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
         pb = make_problem(K=K)
         eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=CpuOracleOps(),
-                              init_tables=(pb["Wu"], pb["Wi"]))
+                              init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
         loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
         torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(),
                         bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"rank{rank}.pt"))
@@ -115,9 +117,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,K", [(2, 3), (3, 2), (2, 1)])
-def test_sharded_step_equals_single_process_oracle(tmp_path, world, K):
-    mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("world,K,schedule,static_batch", [(2, 3, "layer", False), (3, 2, "layer", False), (2, 1, "layer", True),
+                                                           (2, 3, "pipelined", True), (3, 2, "pipelined", False),
+                                                           (2, 1, "pipelined", True)])
+def test_sharded_step_equals_single_process_oracle(tmp_path, world, K, schedule, static_batch):
+    mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path), schedule, static_batch), nprocs=world, join=True)
     pb = make_problem(K=K)
     o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
     outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]

@@ -150,14 +150,16 @@ def test_batch_sized_aggregation_properties(cuda_dev):
     gen = torch.Generator().manual_seed(11)
     ns, nd, E, Fw = 16_000, 90_000, 400_000, 84
     ei = torch.stack([torch.randint(0, ns, (E,), generator=gen), torch.randint(0, nd, (E,), generator=gen)]).to(cuda_dev)
-    x = torch.randn(ns, Fw, device=cuda_dev, requires_grad=True)
-    y = torch.randn(nd, Fw, device=cuda_dev)
+    x = torch.randn(ns, Fw, generator=gen).to(cuda_dev).requires_grad_(True)
+    y = torch.randn(nd, Fw, generator=gen).to(cuda_dev)
     g = lg.build_edge_csr(ei, ns, nd)
     s = lg.aggregate(x, g, "add")
     (s * y).sum().backward()
     lhs = (s.detach().double() * y.double()).sum()
     rhs = (x.detach().double() * x.grad.double()).sum()
-    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0)
+    # <A x, y> == <x, A^T y>; both are sums of 7.6e6 products of fp32-rounded values (the inner product itself
+    # cancels to O(1e2)), so the allowance is 1e-6 of the accumulated magnitude, not of the result
+    assert abs(lhs - rhs) <= 1e-6 * float((s.detach().double() * y.double()).abs().sum())
     deg = torch.bincount(ei[1], minlength=nd).clamp(min=1).unsqueeze(1)
     close(lg.aggregate(x.detach(), g, "mean"), s.detach() / deg, atol=1e-6)
     ref = torch.zeros(nd, Fw, device=cuda_dev).index_add_(0, ei[1], x.detach()[ei[0]])

@@ -46,8 +46,14 @@ def main():
     res["accumulate_items"] = timeit(lambda: eng.ops.accumulate(Y[Ug:], eng.E_f[Ug:], None, 1.0, eng.E_f[Ug:]))
     res["forward"] = timeit(lambda: eng.forward())
     res["fused_step"] = timeit(lambda: eng.fused_step(ub, pb, nb, 1e-6))
-    gstep = eng.capture(B, 1e-6)
-    res["fused_step_graph"] = timeit(lambda: gstep(ub, pb, nb))
+    if os.environ.get("PROBE_PIPELINED"):
+        eng.schedule = "pipelined"
+        res["fused_step_pipelined"] = timeit(lambda: eng.fused_step(ub, pb, nb, 1e-6))
+        eng.static_batch = True
+        res["fused_step_pipelined_static"] = timeit(lambda: eng.fused_step(ub, pb, nb, 1e-6))
+    if os.environ.get("PROBE_GRAPH"):
+        gstep = eng.capture(B, 1e-6)
+        res["fused_step_graph"] = timeit(lambda: gstep(ub, pb, nb))
     if dist.get_rank() == 0:
         print(f"world={dist.get_world_size()} Ug={eng.Ug} local_edges={eng.local_edges} "
               f"items view: nnz={eng.g_items.nnz} long={eng.g_items.n_long} tasks={eng.g_items.n_tasks}; "
