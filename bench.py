@@ -207,7 +207,7 @@ def run_ours(args):
     else:
         from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
         torch.manual_seed(0)
-        eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule)
+        eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule, exchange=args.exchange)
         nnz = 2 * E
         if not args.graph:
             step = lambda: eng.fused_step(ub, pb, nb, lam)      # noqa: E731
@@ -375,6 +375,8 @@ def main():
     ap.add_argument("--degree-order", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="multi-GPU: replay the step from a CUDA graph (opt-in, not yet measured)")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "symm"],
+                    help="multi-GPU item-block exchange: NCCL all-reduce (measured default) or the symmetric-memory multimem kernel")
     ap.add_argument("--schedule", default="layer", choices=["layer", "pipelined"],
                     help="multi-GPU overlap schedule (dist.ShardedLightGCN); 'layer' is the measured default")
     args = ap.parse_args()

@@ -229,6 +229,17 @@ int lgb_sort_keys_ws_bytes(int64_t n, size_t* bytes_host);
 int lgb_edge_keys_sorted(const int64_t* row, const int64_t* col, int64_t n, int64_t num_nodes,
                          int64_t* keys_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU item-block exchange over CUDA symmetric memory (new: the reference is single-process).
+ * Sum-all-reduce, in place, of an fp32 buffer that every rank allocated symmetrically; rank g reduces and
+ * republishes slice g.  The caller brackets the call with symmetric-memory barriers on the same stream.
+ *   lgb_multimem_allreduce_f32 : NVSwitch multicast address (multimem.ld_reduce / multimem.st, NVLS)
+ *   lgb_peer_allreduce_f32     : per-peer UVA pointers (peer_ptrs_host[world], HOST array of device addresses)
+ * ------------------------------------------------------------------------------------------- */
+int lgb_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world, void* stream);
+int lgb_peer_allreduce_f32(const uint64_t* peer_ptrs_host, int64_t n_floats, int32_t rank, int32_t world,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,6 +146,55 @@ class CudaOps:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
 
+class SymmOps(CudaOps):
+    """Item-block exchange WITHOUT NCCL: the block is staged in CUDA symmetric memory and summed by
+    lgb_multimem_allreduce_f32 (NVSwitch multicast: multimem.ld_reduce + multimem.st, rank g owns slice g) or, when
+    the fabric has no multicast, lgb_peer_allreduce_f32 (P2P loads/stores over NVLink), bracketed by symmetric-memory
+    barriers.  Opt-in: ShardedLightGCN(..., exchange="symm").  Written in round 1 after the GPU budget was spent:
+    compiles (SASS shows LDGMC.E.ADD.F32x4), logic mirrors torch's two-shot multimem all-reduce, NOT yet run on B200."""
+
+    def __init__(self, device: torch.device, group=None):
+        super().__init__(device, group)
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm = symm_mem
+        self._stage = {}
+
+    def _staging(self, numel: int):
+        if numel not in self._stage:
+            t = self._symm.empty(numel, dtype=torch.float32, device=self.device)
+            h = self._symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self._stage[numel] = (t, h)
+        return self._stage[numel]
+
+    def all_reduce_async(self, t: torch.Tensor):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return _Done()
+        n = t.numel()
+        if n % 4 != 0 or not t.is_contiguous():
+            return super().all_reduce_async(t)
+        stage, h = self._staging(n)
+        lib = _lib.load()
+        cur = torch.cuda.current_stream(self.device)
+        self.comm.wait_stream(cur)
+        with torch.cuda.stream(self.comm):
+            stage.copy_(t.reshape(-1))
+            h.barrier(channel=0)                                   # every rank's partial sums are staged
+            off = int(getattr(h, "offset", 0))
+            mc = int(h.multicast_ptr) if h.multicast_ptr else 0
+            with torch.cuda.device(self.device):
+                if mc:
+                    check(lib.lgb_multimem_allreduce_f32(mc + off, n, h.rank, h.world_size, self.comm.cuda_stream),
+                          "multimem_allreduce")
+                else:
+                    import ctypes as C
+                    arr = (C.c_uint64 * h.world_size)(*[int(p) + off for p in h.buffer_ptrs])
+                    check(lib.lgb_peer_allreduce_f32(arr, n, h.rank, h.world_size, self.comm.cuda_stream), "peer_allreduce")
+            _lib.count_launch()
+            h.barrier(channel=1)                                   # every slice is republished on every rank
+            t.reshape(-1).copy_(stage)
+        return _StreamWait(self.comm, cur)
+
+
 class _Done:
     def wait(self):
         pass
@@ -169,7 +218,7 @@ class ShardedLightGCN:
     def __init__(self, num_users: int, num_items: int, embedding_dim: int, num_iterations: int,
                  users: torch.Tensor, items: torch.Tensor, device, group=None, ops=None,
                  rank: Optional[int] = None, world: Optional[int] = None, init_tables=None,
-                 schedule: str = "layer", static_batch: bool = False):
+                 schedule: str = "layer", static_batch: bool = False, exchange: str = "nccl"):
         self.U, self.I, self.d, self.K = int(num_users), int(num_items), int(embedding_dim), int(num_iterations)
         self.device = torch.device(device)
         if schedule not in ("layer", "pipelined"):
@@ -178,7 +227,9 @@ class ShardedLightGCN:
         inited = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank(group) if inited else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if inited else 1)
-        self.ops = ops if ops is not None else CudaOps(self.device, group)
+        if exchange not in ("nccl", "symm"):
+            raise ValueError(f"exchange={exchange!r}")
+        self.ops = ops if ops is not None else (SymmOps if exchange == "symm" else CudaOps)(self.device, group)
         users, items = users.to(self.device), items.to(self.device)
 
         udeg = torch.bincount(users, minlength=self.U)

@@ -59,6 +59,37 @@ def _reject_mask(row: torch.Tensor, cand: torch.Tensor, num_nodes: int, keys: to
     return mask
 
 
+def both_indexes_from_zero(edge_index: torch.Tensor) -> torch.Tensor:
+    """Item ids of a to_homogeneous() edge list shifted down by max(user id)+1 (data/lightgcn_loader.py:39-43)."""
+    out = torch.clone(edge_index)
+    out[1] = out[1] - (torch.max(out[0]) + 1)
+    return out
+
+
+def split(edge_index: torch.Tensor):
+    """80/10/10 edge split, sklearn ``train_test_split`` with random_state=1 twice (data/lightgcn_loader.py:13-31):
+    the same index permutation as the reference, hence bit-identical splits."""
+    from sklearn.model_selection import train_test_split
+    n = edge_index.shape[1]
+    train_idx, rest = train_test_split(list(range(n)), test_size=0.2, random_state=1)
+    val_idx, test_idx = train_test_split(rest, test_size=0.5, random_state=1)
+    dev = edge_index.device
+    pick = lambda idx: edge_index[:, torch.tensor(idx, dtype=torch.long, device=dev)]   # noqa: E731
+    return pick(train_idx), pick(val_idx), pick(test_idx), edge_index
+
+
+def make_lightgcn_splits(homogeneous_edge_index: torch.Tensor, num_users: int, num_items: int):
+    """create_dataloaders_lightgcn (data/lightgcn_loader.py:54-91) from an in-memory edge list instead of the
+    data/derived/*.pt files: the same 9-tuple, with the reference's wiring (rows = user ids, cols = item ids in
+    [0, I), matrix (U+I)^2)."""
+    from .sparse import SparseTensor
+    edge_index = both_indexes_from_zero(homogeneous_edge_index)
+    train_ei, val_ei, test_ei, edge_index = split(edge_index)
+    n = num_users + num_items
+    mk = lambda ei: SparseTensor(row=ei[0], col=ei[1], sparse_sizes=(n, n))   # noqa: E731
+    return mk(train_ei), mk(val_ei), mk(test_ei), train_ei, val_ei, test_ei, edge_index, num_users, num_items
+
+
 def structured_negative_sampling(edge_index: torch.Tensor, num_nodes=None, contains_neg_self_loops: bool = True
                                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """PyG semantics: for every edge (i, j) a node k with (i, k) not an edge.

@@ -16,10 +16,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    # DIST_CHECK_MODE = "schedule,static,exchange", e.g. "pipelined,1,symm"; default = the measured configuration
+    mode = os.environ.get("DIST_CHECK_MODE", "layer,0,nccl").split(",")
     for K in (3, 2):
         pb = make_problem(seed=K, U=2000, I=300, E=40000, d=64, K=K, B=512)
         eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], dev,
-                              init_tables=(pb["Wu"].to(dev), pb["Wi"].to(dev)))
+                              init_tables=(pb["Wu"].to(dev), pb["Wi"].to(dev)),
+                              schedule=mode[0], static_batch=mode[1] == "1", exchange=mode[2])
         loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
         torch.cuda.synchronize()
         o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)

@@ -403,3 +403,29 @@ def test_sharded_engine_two_gpus_nccl(cuda_dev, tmp_path):
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("DIST_OK") == 2
+
+
+# ------------------------------------------------------------------ evaluation() (run_pipeline_lightgcn.py:20-73)
+def test_evaluation_matches_oracle(cuda_dev):
+    gen = torch.Generator().manual_seed(21)
+    U, I, d, K, k, lam = 60, 40, 32, 2, 5, 1e-4
+    E = 300
+    ei = torch.stack([torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)])
+    excl = torch.stack([torch.randint(0, U, (200,), generator=gen), torch.randint(0, I, (200,), generator=gen)])
+    row, col, n = lo.wiring_reference(ei[0], ei[1], U, I)
+    torch.manual_seed(3)
+    model = lg.LightGCN(U, I, d, K)
+    Wu, Wi = model.users_emb.weight.detach().clone(), model.items_emb.weight.detach().clone()
+    model = model.to(cuda_dev).eval()
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(n, n)).to(cuda_dev)
+    torch.manual_seed(77)
+    loss, recall, precision, ndcg = lg.evaluation(model, ei.to(cuda_dev), adj, [excl.to(cuda_dev)], k, lam)
+    # oracle: same CPU RNG stream for the negatives, forward + bpr over every edge, per-user top-k loop
+    torch.manual_seed(77)
+    u, p, neg = so.structured_negative_sampling(ei, num_nodes=torch.max(ei[1]), contains_neg_self_loops=False)
+    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+    u_f, u_0, i_f, i_0 = lo.lightgcn_forward(Wu, Wi, rowptr, c, K)
+    o_loss = lo.bpr_loss(u_f[u], u_0[u], i_f[p], i_0[p], i_f[neg], i_0[neg], lam)
+    o_recall, o_precision, o_ndcg, _ = to.metrics_lightgcn(Wu, Wi, ei, [excl], k)
+    assert loss == pytest.approx(o_loss.item(), rel=1e-5)
+    assert (recall, precision, ndcg) == pytest.approx((o_recall, o_precision, o_ndcg), rel=1e-5)

@@ -1,0 +1,32 @@
+#!/usr/bin/env bash
+# GPU measurement plan for the next round.  EVERY command carries its own `timeout`: in round 1 an un-timed 8-rank probe
+# hung (NCCL / CUDA-graph capture) and burned 151 GPU-minutes.  Run pieces with:
+#   gpurun --timeout 900 -- 'bash tools/round2_gpu_plan.sh single'
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/round2_gpu_plan.sh dist2'
+#   gpurun --gpus 8 --timeout 600 -- 'bash tools/round2_gpu_plan.sh dist8'
+set -u
+mkdir -p gpurun_out
+T() { timeout "$@"; echo "[rc=$?] ${*:2}" | cut -c1-160; }
+TR() { local n=$1; shift; timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) "$@"; echo "[rc=$?] torchrun x$n $*" | cut -c1-160; }
+case "${1:-single}" in
+  single)
+    T 600 python -m pytest tests -m gpu -q 2>&1 | tail -15
+    T 200 python bench.py --steps 20 --warmup 5 | tail -1 > gpurun_out/bench_hm.json
+    T 200 python bench.py --steps 20 --warmup 5 --degree uniform --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_uniform.json
+    T 200 python bench.py --steps 50 --warmup 5 --workload ml1m --no-cpu-baseline | tail -1 > gpurun_out/bench_ml1m.json
+    T 200 python tools/spmm_probe.py --variants 0,12,13 2>&1 | grep -v Warn
+    T 300 python tools/hetero_bench.py 2>&1 | tail -12
+    T 600 python tools/sweep.py 2>&1 | tail -12
+    ;;
+  dist2|dist4|dist8)
+    n=${1#dist}
+    for mode in "layer,0,nccl" "layer,1,nccl" "pipelined,0,nccl" "pipelined,1,nccl" "layer,0,symm" "pipelined,1,symm"; do
+      DIST_CHECK_MODE=$mode TR "$n" tests/dist_gpu_check.py 2>&1 | grep -E "DIST_OK|Error|error|rc=" | head -6
+    done
+    TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 | tail -2 | cut -c1-300
+    TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule pipelined | tail -2 | cut -c1-300
+    TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule pipelined --exchange symm | tail -2 | cut -c1-300
+    TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule pipelined --graph | tail -2 | cut -c1-300
+    PROBE_PIPELINED=1 TR "$n" tools/dist_probe.py 2>&1 | grep -v -i warn | tail -12
+    ;;
+esac
