@@ -230,6 +230,14 @@ int lgb_edge_keys_sorted(const int64_t* row, const int64_t* col, int64_t n, int6
                          int64_t* keys_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused Adam step -- optim.Adam(model.parameters(), lr) + optimizer.step() of run_pipeline_lightgcn.py:103,159
+ * (betas/eps as given, no weight decay, no amsgrad), torch's single-tensor arithmetic in one streaming pass.
+ * `step` is the 1-based step count AFTER the increment (torch's state["step"]).
+ * ------------------------------------------------------------------------------------------- */
+int lgb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int32_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU item-block exchange over CUDA symmetric memory (new: the reference is single-process).
  * Sum-all-reduce, in place, of an fp32 buffer that every rank allocated symmetrically; rank g reduces and
  * republishes slice g.  The caller brackets the call with symmetric-memory barriers on the same stream.

@@ -429,3 +429,55 @@ def test_evaluation_matches_oracle(cuda_dev):
     o_recall, o_precision, o_ndcg, _ = to.metrics_lightgcn(Wu, Wi, ei, [excl], k)
     assert loss == pytest.approx(o_loss.item(), rel=1e-5)
     assert (recall, precision, ndcg) == pytest.approx((o_recall, o_precision, o_ndcg), rel=1e-5)
+
+
+# ------------------------------------------------------------------ fused Adam (run_pipeline_lightgcn.py:103,159,178)
+def test_fused_adam_matches_torch_adam(cuda_dev):
+    """Same trajectory as torch.optim.Adam (CPU, the reference's optimizer) incl. an ExponentialLR decay step."""
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(37, 64), (5, 6), (1000, 32)]
+    ref = [torch.randn(s, generator=gen).requires_grad_(True) for s in shapes]
+    mine = [r.detach().clone().to(cuda_dev).requires_grad_(True) for r in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2)
+    o_mine = lg.FusedAdam(mine, lr=1e-2)
+    s_ref = torch.optim.lr_scheduler.ExponentialLR(o_ref, gamma=0.95)
+    s_mine = torch.optim.lr_scheduler.ExponentialLR(o_mine, gamma=0.95)
+    for it in range(6):
+        grads = [torch.randn(s, generator=gen) * (10.0 ** (it % 3 - 1)) for s in shapes]
+        for r, m, g in zip(ref, mine, grads):
+            r.grad = g.clone(); m.grad = g.to(cuda_dev)
+        o_ref.step(); o_mine.step()
+        if it == 2:
+            s_ref.step(); s_mine.step()
+        for r, m in zip(ref, mine):
+            close(m, r, rtol=1e-5, atol=2e-6)   # per-step update is lr = 1e-2: an ulp or two of the parameter value
+    assert o_mine.param_groups[0]["lr"] == pytest.approx(o_ref.param_groups[0]["lr"])
+
+
+def test_training_loop_with_fused_step_and_fused_adam(cuda_dev):
+    """A few iterations of the reference loop shape (forward, BPR, backward, Adam) with fused_step + FusedAdam follow
+    the oracle loop (autograd + torch.optim.Adam on the CPU)."""
+    gen = torch.Generator().manual_seed(8)
+    U, I, E, d, K, B, lam = 120, 80, 1500, 32, 2, 64, 1e-4
+    users, items = torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)
+    row, col, n = lo.wiring_symmetric(users, items, U, I)
+    torch.manual_seed(1)
+    model = lg.LightGCN(U, I, d, K)
+    Wu = model.users_emb.weight.detach().clone().requires_grad_(True)
+    Wi = model.items_emb.weight.detach().clone().requires_grad_(True)
+    model = model.to(cuda_dev)
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(n, n)).to(cuda_dev)
+    opt = lg.FusedAdam(model.parameters(), lr=5e-3)
+    o_opt = torch.optim.Adam([Wu, Wi], lr=5e-3)
+    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+    for it in range(4):
+        pick = torch.randint(0, E, (B,), generator=gen)
+        ub, pb, nb = users[pick], items[pick], torch.randint(0, I, (B,), generator=gen)
+        loss = model.fused_step(adj, ub.to(cuda_dev), pb.to(cuda_dev), nb.to(cuda_dev), lam)
+        opt.step()
+        o_loss, gu, gi, _, _ = lo.train_iteration(Wu.detach(), Wi.detach(), rowptr, c, K, ub, pb, nb, lam)
+        Wu.grad, Wi.grad = gu, gi
+        o_opt.step()
+        close(loss, o_loss, rtol=1e-5)
+        close(model.users_emb.weight, Wu, rtol=1e-4, atol=1e-6)
+        close(model.items_emb.weight, Wi, rtol=1e-4, atol=1e-6)
