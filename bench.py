@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="multi-GPU: replay the step from a CUDA graph (opt-in, not yet measured)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "symm"],
                     help="multi-GPU item-block exchange: NCCL all-reduce (measured default) or the symmetric-memory multimem kernel")
-    ap.add_argument("--schedule", default="layer", choices=["layer", "pipelined"],
+    ap.add_argument("--schedule", default="layer", choices=["layer", "pipelined", "merged"],
                     help="multi-GPU overlap schedule (dist.ShardedLightGCN); 'layer' is the measured default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

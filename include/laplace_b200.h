@@ -132,6 +132,13 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
              const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws,
              void* stream);
 
+/* Same kernel with a split epilogue: rows >= split_row skip the epilogue and store their raw sums to
+ * y_tail[(r - split_row), :] -- multi-GPU: one launch computes the owned user rows (fused epilogue) AND the partial
+ * item rows that go to the exchange buffer.  d % 4 == 0; variants 2/3 are not available. */
+int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
+                   float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
+                   void* stream);
+
 /* scatter-max per destination (PyG aggr="max"): Y[r,:] = max_e X[colidx[e],:] (0 for empty rows),
  * argmax[r,:] = the winning source row (or -1), used by the backward. */
 int lgb_segment_max(const lgb_csr* g, const float* X, int32_t d, float* Y, int32_t* argmax, void* stream);

@@ -190,7 +190,8 @@ class DeviceCSR:
     # ---- the hot call -------------------------------------------------------------------
     def spmm(self, X: torch.Tensor, Y: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
              acc_in: Optional[torch.Tensor] = None, acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0,
-             mean: bool = False, want_y: bool = True, variant: Optional[int] = None) -> Optional[torch.Tensor]:
+             mean: bool = False, want_y: bool = True, variant: Optional[int] = None, split_row: Optional[int] = None,
+             y_tail: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Y = A @ X with the fused epilogue of lgb_spmm.  Allocates Y when want_y and Y is None."""
         _lib.require_cuda(X)
         if X.dim() != 2 or X.shape[0] != self.n_cols:
@@ -203,9 +204,17 @@ class DeviceCSR:
             if t is not None and (tuple(t.shape) != (self.n_rows, d) or not t.is_contiguous() or t.dtype != torch.float32):
                 raise RuntimeError(f"spmm: {name} must be contiguous float32 [{self.n_rows}, {d}]")
         lib = _lib.load()
+        flags = (1 if mean else 0) | ((SPMM_VARIANT if variant is None else variant) << 4)
         with torch.cuda.device(self.device):
-            check(lib.lgb_spmm(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
-                               float(acc_div), (1 if mean else 0) | ((SPMM_VARIANT if variant is None else variant) << 4),
-                               ptr(self._partial_ws(d)), stream()), "spmm")
+            if y_tail is not None:
+                # split epilogue: rows >= split_row write raw sums to y_tail (see lgb_spmm_split)
+                if tuple(y_tail.shape) != (self.n_rows - int(split_row), d) or not y_tail.is_contiguous():
+                    raise RuntimeError(f"spmm: y_tail must be contiguous float32 [{self.n_rows - int(split_row)}, {d}]")
+                check(lib.lgb_spmm_split(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
+                                         float(acc_div), flags, ptr(self._partial_ws(d)), int(split_row), ptr(y_tail),
+                                         stream()), "spmm_split")
+            else:
+                check(lib.lgb_spmm(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
+                                   float(acc_div), flags, ptr(self._partial_ws(d)), stream()), "spmm")
         _lib.count_launch(2 if self.n_long else 1)
         return Y

@@ -46,6 +46,8 @@ struct SpmmParams {
   float acc_div;
   int32_t mean;
   float* partial;
+  int64_t split_row;   // rows >= split_row skip the epilogue and store their raw sums to y_tail[r - split_row] (0 = off)
+  float* y_tail;
 };
 
 template <int G, int VPL, int UNROLL>
@@ -95,6 +97,15 @@ __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int
 
 template <int G, int VPL>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg, int lig, float4 (&acc)[VPL]) {
+  if (p.y_tail && r >= p.split_row) {   // multi-GPU item rows: partial sums go to the exchange buffer untouched
+    float4* out = reinterpret_cast<float4*>(p.y_tail) + (size_t)(r - p.split_row) * p.d4;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int f = lig + q * G;
+      if (f < p.d4) st_f4(out + f, acc[q]);
+    }
+    return;
+  }
   const size_t rowoff = (size_t)r * p.d4;
 #pragma unroll
   for (int q = 0; q < VPL; ++q) {
@@ -716,8 +727,31 @@ using namespace lgb;
 
 extern "C" {
 
+static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
+                     float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
+                     void* stream_);
+
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
              float* acc_out, float acc_div, int32_t flags, float* partial_ws, void* stream_) {
+  return spmm_impl(g, X, d, Y, resid, acc_in, acc_out, acc_div, flags, partial_ws, 0, nullptr, stream_);
+}
+
+int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
+                   float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
+                   void* stream_) {
+  LGB_REQUIRE(g && y_tail && split_row >= 0 && split_row <= g->n_rows, LGB_EINVAL, "lgb_spmm_split: bad split_row / y_tail");
+  LGB_REQUIRE(y_tail != X, LGB_EINVAL, "lgb_spmm_split: y_tail aliases the gathered operand");
+  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xF;
+  LGB_REQUIRE(variant != 2 && variant != 3, LGB_EINVAL, "lgb_spmm_split: the software-pipelined variants have no split epilogue");
+  LGB_REQUIRE(d % 4 == 0, LGB_EINVAL, "lgb_spmm_split: d %% 4 != 0");
+  return spmm_impl(g, X, d, Y, resid, acc_in, acc_out, acc_div, flags, partial_ws, split_row, y_tail, stream_);
+}
+
+}  // extern "C"
+
+static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
+                     float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
+                     void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LGB_REQUIRE(g && g->rowptr && X && d > 0, LGB_EINVAL, "lgb_spmm: null graph/X or d <= 0");
   LGB_REQUIRE(g->nnz == 0 || g->colidx, LGB_EINVAL, "lgb_spmm: null colidx");
@@ -734,6 +768,7 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
   p.chunk = g->chunk; p.d4 = d / 4;
   p.X = X; p.Y = Y; p.resid = resid; p.acc_in = acc_in; p.acc_out = acc_out; p.acc_div = acc_div;
   p.mean = (flags & LGB_SPMM_MEAN) ? 1 : 0; p.partial = partial_ws;
+  p.split_row = split_row; p.y_tail = y_tail;
   if (p.n_tasks > 0) {
     LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->long_rows && g->long_ptr, LGB_EINVAL,
                 "lgb_spmm: plan has %lld tasks but plan arrays / partial workspace missing", (long long)p.n_tasks);
@@ -778,6 +813,8 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
   set_error("lgb_spmm: d=%d > 512 not supported", d);
   return LGB_EINVAL;
 }
+
+extern "C" {
 
 int lgb_segment_max(const lgb_csr* g, const float* X, int32_t d, float* Y, int32_t* argmax, void* stream) {
   LGB_REQUIRE(g && g->rowptr && X && Y && d > 0, LGB_EINVAL, "lgb_segment_max: bad argument");

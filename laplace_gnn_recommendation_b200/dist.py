@@ -91,6 +91,12 @@ class CudaOps:
     def spmm(self, g, X, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
         g.spmm(X, Y=Y, resid=resid, acc_in=acc_in, acc_out=acc_out, acc_div=acc_div, want_y=Y is not None)
 
+    def spmm_split(self, g, X, split_row, y_tail, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
+        """One launch over ALL local rows: rows < split_row get the fused epilogue, rows >= split_row (the partial item
+        rows) are stored raw to y_tail."""
+        g.spmm(X, Y=Y, resid=resid, acc_in=acc_in, acc_out=acc_out, acc_div=acc_div, want_y=Y is not None,
+               split_row=split_row, y_tail=y_tail)
+
     def accumulate(self, y, acc, resid, div, out):
         with torch.cuda.device(self.device):
             check(_lib.load().lgb_accumulate(ptr(y), ptr(acc), ptr(resid), y.numel(), float(div), ptr(out), stream()), "accumulate")
@@ -221,7 +227,7 @@ class ShardedLightGCN:
                  schedule: str = "layer", static_batch: bool = False, exchange: str = "nccl"):
         self.U, self.I, self.d, self.K = int(num_users), int(num_items), int(embedding_dim), int(num_iterations)
         self.device = torch.device(device)
-        if schedule not in ("layer", "pipelined"):
+        if schedule not in ("layer", "pipelined", "merged"):
             raise ValueError(f"schedule={schedule!r}")
         self.schedule, self.static_batch = schedule, bool(static_batch)
         inited = dist.is_available() and dist.is_initialized()
@@ -249,6 +255,7 @@ class ShardedLightGCN:
         self.g_users = self.ops.row_view(g, 0, self.Ug)
         self.g_items = self.ops.row_view(g, self.Ug, n)
         self.g_full = g
+        self.g_all = self.ops.row_view(g, 0, n) if schedule == "merged" else None   # all rows + split plan
 
         # parameters: one local table; the item block is identical on every rank
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -336,11 +343,31 @@ class ShardedLightGCN:
             self._finish_items(*pending)
         return x
 
+    # ---- schedule "merged" (opt-in): ONE launch per layer over all local rows (split epilogue), exchange exposed ------
+    # Halves the launch count and doubles the work per launch (at 1/8 of the graph a launch is bound by per-row latency
+    # chains, not bytes); pays with a fully exposed exchange, so it is meant for the fast multimem exchange.
+    # Validated over gloo; B200 measurement pending.
+    def _layer_merged(self, X, Y, resid=None, acc_in=None, acc_out=None, acc_div=1.0, write_y=True, before_reduce=None):
+        Ug, ops = self.Ug, self.ops
+        ops.spmm_split(self.g_all, X, Ug, Y[Ug:], Y=Y if write_y else None, resid=resid, acc_in=acc_in, acc_out=acc_out,
+                       acc_div=acc_div)
+        if before_reduce is not None:
+            before_reduce(Y[Ug:])
+        self._finish_items(ops.all_reduce_async(Y[Ug:]), Y, resid, acc_in, acc_out, acc_div)
+
     def forward(self) -> torch.Tensor:
         """E_f = mean_k A^k E0 on the local rows (item rows replicated)."""
         K, E0, Ef = self.K, self.table, self.E_f
         if K == 0:
             Ef.copy_(E0)
+            return Ef
+        if self.schedule == "merged":
+            x, y = E0, self._ya
+            for k in range(K):
+                last = k == K - 1
+                self._layer_merged(x, y, acc_in=E0 if k == 0 else Ef, acc_out=Ef, acc_div=float(K + 1) if last else 1.0,
+                                   write_y=not last)
+                x, y = y, (self._yb if y is self._ya else self._ya)
             return Ef
         if self.schedule == "pipelined":
             self._propagate_pipelined(E0, K, acc0=E0, acc=Ef, acc_div_last=float(K + 1))
@@ -367,6 +394,10 @@ class ShardedLightGCN:
         for k in range(K):
             last = k == K - 1
             dst = self.grad if last else bufs[k % 2]
+            if self.schedule == "merged":
+                self._layer_merged(g, dst, resid=r, before_reduce=before_last_reduce if last else None)
+                g = dst
+                continue
             if last and before_last_reduce is not None:
                 # fold the extra partial item-row terms into this layer's all-reduce
                 Ug, ops = self.Ug, self.ops

@@ -36,6 +36,15 @@ class CpuOracleOps:
         if Y is not None:
             Y.copy_(y)
 
+    def spmm_split(self, g, X, split_row, y_tail, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
+        y = lo.spmm(g["rowptr"], g["col"], g["val"], X)
+        y_tail.copy_(y[split_row:])
+        yu = y[:split_row] if resid is None else y[:split_row] + resid[:split_row]
+        if acc_out is not None:
+            acc_out[:split_row].copy_(((acc_in[:split_row] if acc_in is not None else 0) + yu) / acc_div)
+        if Y is not None:
+            Y[:split_row].copy_(yu)
+
     def accumulate(self, y, acc, resid, div, out):
         v = y if resid is None else y + resid
         if acc is not None:
@@ -119,6 +128,7 @@ def _free_port():
 
 @pytest.mark.parametrize("world,K,schedule,static_batch", [(2, 3, "layer", False), (3, 2, "layer", False), (2, 1, "layer", True),
                                                            (2, 3, "pipelined", True), (3, 2, "pipelined", False),
+                                                           (2, 3, "merged", True), (3, 2, "merged", False), (2, 1, "merged", False),
                                                            (2, 1, "pipelined", True)])
 def test_sharded_step_equals_single_process_oracle(tmp_path, world, K, schedule, static_batch):
     mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path), schedule, static_batch), nprocs=world, join=True)
