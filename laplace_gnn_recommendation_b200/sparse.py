@@ -69,9 +69,7 @@ class SparseTensor:
     def csr(self) -> DeviceCSR:
         """Build (once) and return the device CSR.  Raises on a CPU tensor: there is no CPU fallback."""
         if self._csr is None:
-            if self._row.device.type != "cuda":
-                raise RuntimeError("SparseTensor is on the CPU: move it with .to('cuda') first "
-                                   "(laplace_gnn_recommendation_b200 has no CPU propagation path)")
+            _lib.require_cuda(self._row)   # a CPU SparseTensor must be moved with .to('cuda') first: no CPU fallback
             g = DeviceCSR.from_coo(self._row, self._col, self._sizes[0], self._sizes[1], chunk=self.chunk,
                                    want_perm=self._value is not None)
             if self._value is not None:

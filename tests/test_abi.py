@@ -78,3 +78,5 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                # ... nor the CPU emulation of the kernels that tests/ uses (tests/emu/): the product has no CPU path
+                assert not re.search(r"tests\.emu|liblaplace_b200_emu|LGB_CPU_EMU|cuda_emu", txt), f

@@ -105,15 +105,40 @@ def single_process_reference(pb):
     return lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, pb["K"], pb["u"], pb["p"], pb["n"], pb["lam"])
 
 
-def _worker(rank, world, port, K, out_dir, schedule="layer", static_batch=False):
+def make_emu_ops():
+    """dist.CudaOps itself -- row views, lgb_gcn_values, lgb_spmm(_split), lgb_accumulate, lgb_bpr with B_norm and the
+    owned-user filter -- with the kernels served by the CPU emulation of the library (tests/emu/) and the collectives by
+    gloo.  Only the two CUDA-stream specifics of the class are replaced."""
+    from laplace_gnn_recommendation_b200.dist import CudaOps, _Done
+
+    class EmuOps(CudaOps):
+        def __init__(self, device, group=None):
+            self.device, self.group, self.comm, self._bpr_ws = device, group, None, None
+
+        def all_reduce_async(self, t):
+            self.all_reduce(t)
+            return _Done()
+
+    return EmuOps(torch.device("cpu"))
+
+
+def _worker(rank, world, port, K, out_dir, schedule="layer", static_batch=False, ops_kind="oracle", d=16):
+    import contextlib
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
-        pb = make_problem(K=K)
-        eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=CpuOracleOps(),
-                              init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
-        loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        pb = make_problem(K=K, d=d)
+        if ops_kind == "emu":
+            from tests.emu.harness import emulated
+            ctx = emulated()
+        else:
+            ctx = contextlib.nullcontext()
+        with ctx:
+            ops = make_emu_ops() if ops_kind == "emu" else CpuOracleOps()
+            eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=ops,
+                                  init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
+            loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
         torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(),
                         bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
@@ -131,8 +156,24 @@ def _free_port():
                                                            (2, 3, "merged", True), (3, 2, "merged", False), (2, 1, "merged", False),
                                                            (2, 1, "pipelined", True)])
 def test_sharded_step_equals_single_process_oracle(tmp_path, world, K, schedule, static_batch):
-    mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path), schedule, static_batch), nprocs=world, join=True)
-    pb = make_problem(K=K)
+    _run_and_check(tmp_path, world, K, schedule, static_batch, "oracle", 16)
+
+
+@pytest.mark.parametrize("world,K,schedule,static_batch,d", [(2, 3, "layer", False, 64), (2, 3, "merged", True, 64),
+                                                             (3, 2, "pipelined", True, 64), (2, 2, "merged", False, 32),
+                                                             (3, 1, "layer", True, 128)])
+def test_sharded_step_with_emulated_kernels(tmp_path, world, K, schedule, static_batch, d):
+    """Same check with dist.CudaOps driving the REAL kernel sources (CPU emulation, tests/emu/) instead of the oracle ops:
+    covers lgb_spmm_split, the BPR owned-user filter / B_norm and the row views under every schedule without a GPU."""
+    _run_and_check(tmp_path, world, K, schedule, static_batch, "emu", d)
+
+
+def _run_and_check(tmp_path, world, K, schedule, static_batch, ops_kind, d):
+    if ops_kind == "emu":
+        from tests.emu import build_emu
+        build_emu.build()          # once, in the parent: the spawned ranks only load it
+    mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path), schedule, static_batch, ops_kind, d), nprocs=world, join=True)
+    pb = make_problem(K=K, d=d)
     o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
     outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
     assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == pb["U"]

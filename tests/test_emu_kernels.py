@@ -1,0 +1,97 @@
+"""Kernel-logic tier (runs WITHOUT a GPU): the parity tests of tests/test_gpu_*.py executed against the CPU emulation
+of liblaplace_b200 -- the unmodified csrc/*.cu kernel sources compiled with g++ against a warp-lockstep CUDA emulator
+(tests/emu/).  Same test bodies, same oracle, same tolerances; only the ``cuda_dev`` fixture differs.
+
+What this tier proves: index arithmetic, warp-shuffle data flow, split plans, fused epilogues, reductions and the Python
+host logic above them are right, and no kernel issues a divergent or partially-exited warp collective (the emulator turns
+those into launch errors).  What it cannot prove: anything about memory-model races, performance, or PTX-level behaviour
+(cache hints, red.global.add.v4, cp.async are replaced by their plain meaning) -- that is what `pytest -m gpu` is for.
+"""
+import platform
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emulator's context switch is x86-64 only")
+
+from tests.emu.harness import emulated  # noqa: E402
+import tests.test_gpu_hetero as TH  # noqa: E402
+import tests.test_gpu_lightgcn as TL  # noqa: E402
+
+
+@pytest.fixture
+def cuda_dev():
+    """Overrides conftest's fixture inside this module: the 'device' is the CPU, served by the emulated library."""
+    with emulated() as dev:
+        yield dev
+
+
+# ---- LightGCN path -----------------------------------------------------------------------------------------------
+test_csr_build_bit_exact = TL.test_csr_build_bit_exact
+test_csr_reference_fixture_and_gcn_norm_bit_exact = TL.test_csr_reference_fixture_and_gcn_norm_bit_exact
+test_spmm_vs_oracle = TL.test_spmm_vs_oracle
+test_spmm_fused_epilogue_and_degree_order = TL.test_spmm_fused_epilogue_and_degree_order
+test_lightgcn_against_reference_golden = TL.test_lightgcn_against_reference_golden
+test_lightgcn_against_oracle = TL.test_lightgcn_against_oracle
+test_bpr_against_reference_golden = TL.test_bpr_against_reference_golden
+test_module_contract = TL.test_module_contract
+test_sample_mini_batch_bit_exact_vs_reference_golden = TL.test_sample_mini_batch_bit_exact_vs_reference_golden
+test_structured_negative_sampling_bit_exact = TL.test_structured_negative_sampling_bit_exact
+test_topk_against_reference_golden = TL.test_topk_against_reference_golden
+test_topk_against_oracle = TL.test_topk_against_oracle
+test_evaluation_matches_oracle = TL.test_evaluation_matches_oracle
+test_fused_adam_matches_torch_adam = TL.test_fused_adam_matches_torch_adam
+test_training_loop_with_fused_step_and_fused_adam = TL.test_training_loop_with_fused_step_and_fused_adam
+
+# ---- hetero encoder-decoder path ---------------------------------------------------------------------------------
+test_aggregate_fwd_bwd_vs_oracle = TH.test_aggregate_fwd_bwd_vs_oracle
+test_encoder_decoder_against_reference_golden = TH.test_encoder_decoder_against_reference_golden
+test_infer_rebatch_matches_oracle = TH.test_infer_rebatch_matches_oracle
+test_decoder_concat_and_dot = TH.test_decoder_concat_and_dot
+test_hetero_fan_in_three_edge_types = TH.test_hetero_fan_in_three_edge_types
+# full-size property tests (B = 200 003 BPR triples; a 400 k-edge, 84-wide hetero batch): seconds under the emulator
+test_bpr_full_split_size = TL.test_bpr_full_split_size
+test_batch_sized_aggregation_properties = TH.test_batch_sized_aggregation_properties
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_spmm_kernel_variants_agree(cuda_dev, d):
+    TL.test_spmm_kernel_variants_agree(cuda_dev, d, n=1200, nnz=30000)   # smaller than on the GPU: 16 variants x 4 launches
+
+
+def test_spmm_empty_and_single_heavy_row(cuda_dev):
+    """tests/test_gpu_lightgcn.py::test_spmm_empty_and_ragged without its "CPU tensors are refused" half (under the
+    emulator CPU tensors ARE the device tensors)."""
+    d = 64
+    e = torch.empty(0, dtype=torch.long)
+    g = TL.DeviceCSR.from_coo(e, e, 10, 10)
+    assert torch.count_nonzero(g.spmm(torch.randn(10, d))) == 0
+    n, nnz = 40, 5000
+    row = torch.full((nnz,), 7); col = torch.randint(0, n, (nnz,), generator=torch.Generator().manual_seed(3))
+    g = TL.DeviceCSR.from_coo(row, col, n, n, chunk=128)
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(4))
+    TL.spmm_close(g.spmm(X), g.rowptr.long(), g.colidx.long(), None, X)
+    with pytest.raises(RuntimeError):
+        g.spmm(torch.randn(n + 1, d))
+
+
+def test_sharded_engine_single_rank(cuda_dev):
+    """tests/test_gpu_lightgcn.py::test_sharded_engine_single_rank_matches_oracle with dist.CudaOps on the emulated library
+    (multi-rank runs of the same ops object: tests/test_dist_gloo.py::test_sharded_step_with_emulated_kernels)."""
+    from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
+    from tests.test_dist_gloo import make_emu_ops, make_problem, single_process_reference
+    for K, schedule, static in ((3, "layer", False), (1, "merged", True), (2, "pipelined", True)):
+        pb = make_problem(seed=K, U=500, I=120, E=9000, d=64, K=K, B=256)
+        eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], cuda_dev, ops=make_emu_ops(),
+                              init_tables=(pb["Wu"], pb["Wi"]), rank=0, world=1, schedule=schedule, static_batch=static)
+        loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
+        TL.close(loss, o_loss)
+        TL.close(eng.E_f[: pb["U"]], o_uf); TL.close(eng.E_f[pb["U"]:], o_if)
+        TL.close(eng.grad[: pb["U"]], o_gu, atol=1e-9); TL.close(eng.grad[pb["U"]:], o_gi, atol=1e-9)
+
+
+def test_emulator_reports_undefined_warp_collectives():
+    """The emulator itself: a launch error must surface through the library's own error path."""
+    from tests.emu.selftest import run_selftest
+    run_selftest()

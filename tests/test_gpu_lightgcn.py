@@ -140,11 +140,9 @@ def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
 
 
 @pytest.mark.parametrize("d", [32, 64, 128])
-def test_spmm_kernel_variants_agree(cuda_dev, d):
-    """All kernel variants compute the same operator.  The one-warp-per-item variants (0, 1, 4, 5, 6) differ only in
-    unroll depth / occupancy and add every row in the same order: bit-identical.  The software-pipelined variants
-    (2, 3) must match to rtol 1e-5."""
-    n, nnz = 5000, 200000
+def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
+    """All 16 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    cp.async rings, sub-warp rows) compute the same operator with the same fused epilogue: rtol 1e-5 against the default."""
     row, col = random_graph(d + 1, n, n, nnz, skew=True)
     g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
     _, val = g.gcn_norm()
@@ -156,10 +154,7 @@ def test_spmm_kernel_variants_agree(cuda_dev, d):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
-    for v in (2, 3):
-        for a, b in zip(outs[0], outs[v]):
-            close(a, b, rtol=1e-5, atol=1e-5)
-    for v in (1, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15):
+    for v in range(1, 16):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
@@ -258,14 +253,14 @@ def test_lightgcn_against_oracle(cuda_dev, wiring, K, d):
 
 def test_bpr_against_reference_golden(cuda_dev, golden):
     for c in golden["bpr"]:
-        xs = [x.to(cuda_dev).requires_grad_(True) for x in c["inputs"]]
+        xs = [x.clone().to(cuda_dev).requires_grad_(True) for x in c["inputs"]]
         loss = lg.bpr_loss(*xs, c["lam"])
         (loss * 1.0).backward()
         close(loss, c["loss"])
         for x, g in zip(xs, c["grads"]):
             close(x.grad, g, atol=1e-9)
     # upstream gradient is honoured
-    xs = [x.to(cuda_dev).requires_grad_(True) for x in golden["bpr"][0]["inputs"]]
+    xs = [x.clone().to(cuda_dev).requires_grad_(True) for x in golden["bpr"][0]["inputs"]]
     (lg.bpr_loss(*xs, 1e-6) * 3.0).backward()
     close(xs[0].grad, 3.0 * golden["bpr"][0]["grads"][0], atol=1e-9)
 
@@ -479,5 +474,7 @@ def test_training_loop_with_fused_step_and_fused_adam(cuda_dev):
         Wu.grad, Wi.grad = gu, gi
         o_opt.step()
         close(loss, o_loss, rtol=1e-5)
-        close(model.users_emb.weight, Wu, rtol=1e-4, atol=1e-6)
-        close(model.items_emb.weight, Wi, rtol=1e-4, atol=1e-6)
+        # Adam turns a gradient element g into a step lr*g/(|g|+eps): where |g| ~ eps = 1e-8 an fp32-rounding-sized change
+        # of g moves the step by a visible fraction of lr, so allow 0.1 % of lr per element on top of rtol
+        close(model.users_emb.weight, Wu, rtol=1e-4, atol=5e-6)
+        close(model.items_emb.weight, Wi, rtol=1e-4, atol=5e-6)
