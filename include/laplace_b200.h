@@ -124,9 +124,11 @@ typedef struct lgb_csr {
  * X/Y/resid/acc_* are [n, d] row-major.  partial_ws must hold n_tasks*d floats when g->n_tasks > 0.
  * ------------------------------------------------------------------------------------------- */
 #define LGB_SPMM_MEAN 1
-/* bits 4..7 of flags pick a kernel variant for A/B measurements (d in 33..64 only): 0 = tuned default
- * (one warp per row / slice, 64 resident warps per SM), 1 = first version (unroll 8), 2/3 = software-pipelined
- * persistent warps, 4..6 = other unroll / occupancy points.  Variants 0,1,4,5,6 are bit-identical. */
+/* bits 4..11 of flags pick a kernel variant for A/B measurements (all of them for d in 33..64; 0, 1 and 16 for d <= 32):
+ * 0 = tuned default (sub-warp rows: one lane group per short row, 64 resident warps per SM), 1 = first version (warp per
+ * row, unroll 8), 2/3 = software-pipelined persistent warps, 4..6, 12 = warp per row at other unroll / occupancy points,
+ * 7..11 = cp.async rings, 13..15 = sub-warp rows at other unroll depths, 16 = sub-warp rows + one CTA per slice of a long
+ * row.  Every variant computes the same operator (rtol 1e-5); summation order inside a row differs between families. */
 #define LGB_SPMM_VARIANT_SHIFT 4
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid,
              const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws,

@@ -50,14 +50,16 @@ struct SpmmParams {
   float* y_tail;
 };
 
-template <int G, int VPL, int UNROLL>
+// STEP = distance between the 32-entry batches this warp takes (32: the whole range; 32*SPMM_WARPS: every SPMM_WARPS-th
+// batch, when the warps of a CTA share one slice).
+template <int G, int VPL, int UNROLL, int STEP = 32>
 __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int e, int lane, float4 (&acc)[VPL]) {
   constexpr int NG = 32 / G;
   const int grp = lane / G;
   const int lig = lane % G;
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   const int d4 = p.d4;
-  for (int base = s; base < e; base += 32) {
+  for (int base = s; base < e; base += STEP) {
     const int idx = base + lane;
     int c = 0;
     float w = 0.f;
@@ -334,18 +336,46 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
 // lanes wide, so a warp can run 32/G independent row chains at once: warp w owns rows NG*w .. NG*w+NG-1, one per lane
 // group, when all of them are short (<= SUBW_MAX non-zeros); otherwise it walks them one by one with the whole warp
 // (the spmm_rows_kernel path).  No cross-group reduction in sub-warp mode; per-row summation order is plain ascending.
+//
+// WIDE (variant 16, measurement pending): a slice of a long row is shared by the SPMM_WARPS warps of ONE CTA (warp i takes
+// the 32-entry batches i, i+4, ...; the four sums are added in warp order through shared memory).  Scaling measurements
+// (profiles/README.md r1c) fit  t_launch = 0.09 ms + nnz / 34 G/s : the constant is the dependent-iteration chain of one
+// chunk-sized slice at gather-unroll 2, which bounds the launch from below once the graph is sharded 4-8 ways.  Sharing
+// the slice cuts that chain by SPMM_WARPS without more registers, more partial rows or more long rows.
 constexpr int SUBW_MAX = 64;
 
-template <int G, int UNROLL, int MINB>
+template <int G, int UNROLL, int MINB, bool WIDE = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
   constexpr int NG = 32 / G;
   const int lane = threadIdx.x & 31;
   const int grp = lane / G, lig = lane % G;
-  const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
   const int d4 = p.d4;
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  int64_t w;
+  if (WIDE) {
+    if ((int64_t)blockIdx.x < p.n_tasks) {   // one CTA per slice
+      __shared__ float4 wsum[SPMM_WARPS][G];
+      const int wi = threadIdx.x >> 5;
+      const int64_t t = blockIdx.x;
+      const int s = p.task_start[t], e = p.task_end[t];
+      float4 acc[1] = {f4_zero()};
+      accumulate_slice<G, 1, UNROLL, 32 * SPMM_WARPS>(p, s + 32 * wi, e, lane, acc);
+      if (lane < G) wsum[wi][lane] = acc[0];
+      __syncthreads();
+      if (wi == 0 && lane < G && lane < d4) {
+        float4 sum = wsum[0][lane];
+#pragma unroll
+        for (int k = 1; k < SPMM_WARPS; ++k) sum = f4_add(sum, wsum[k][lane]);
+        st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)t * d4 + lane, sum);
+      }
+      return;
+    }
+    w = p.n_tasks + ((int64_t)blockIdx.x - p.n_tasks) * SPMM_WARPS + (threadIdx.x >> 5);
+  } else {
+    w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
+  }
 
-  if (w < p.n_tasks) {   // slices of long rows: whole warp, partial sums
+  if (!WIDE && w < p.n_tasks) {   // slices of long rows: whole warp, partial sums
     float4 acc[1] = {f4_zero()};
     const int r = p.task_row[w];
     (void)r;
@@ -422,14 +452,15 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
-template <int G, int UNROLL, int MINB>
+template <int G, int UNROLL, int MINB, bool WIDE = false>
 static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
   constexpr int NG = 32 / G;
-  const int64_t warps = p.n_tasks + (p.n_rows + NG - 1) / NG;
+  const int64_t row_warps = (p.n_rows + NG - 1) / NG;
+  const int64_t warps = p.n_tasks + row_warps;
   if (warps > 0) {
-    const int64_t blocks = (warps + SPMM_WARPS - 1) / SPMM_WARPS;
+    const int64_t blocks = WIDE ? p.n_tasks + (row_warps + SPMM_WARPS - 1) / SPMM_WARPS : (warps + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_subwarp_kernel<G, UNROLL, MINB><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
@@ -741,7 +772,7 @@ int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const 
                    void* stream_) {
   LGB_REQUIRE(g && y_tail && split_row >= 0 && split_row <= g->n_rows, LGB_EINVAL, "lgb_spmm_split: bad split_row / y_tail");
   LGB_REQUIRE(y_tail != X, LGB_EINVAL, "lgb_spmm_split: y_tail aliases the gathered operand");
-  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xF;
+  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xFF;
   LGB_REQUIRE(variant != 2 && variant != 3, LGB_EINVAL, "lgb_spmm_split: the software-pipelined variants have no split epilogue");
   LGB_REQUIRE(d % 4 == 0, LGB_EINVAL, "lgb_spmm_split: d %% 4 != 0");
   return spmm_impl(g, X, d, Y, resid, acc_in, acc_out, acc_div, flags, partial_ws, split_row, y_tail, stream_);
@@ -784,8 +815,12 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   // Variant 0 is the tuned default.  Measured on B200 (profiles/r1b_*): the kernel is latency-bound, so the
   // configuration that keeps 64 warps resident per SM (<= 32 registers: gather unroll 2, __launch_bounds__(128,16))
   // beats deeper unrolls (72 regs -> 28 warps) by 1.3x and the software-pipelined persistent variant by 1.5x.
-  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xF;
-  if (d4 <= 8) return (variant == 1) ? launch_vec<8, 1, 2, 16>(p, 1, stream) : launch_subwarp<8, 2, 16>(p, stream);
+  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xFF;
+  if (d4 <= 8) {
+    if (variant == 1) return launch_vec<8, 1, 2, 16>(p, 1, stream);
+    if (variant == 16) return launch_subwarp<8, 2, 16, true>(p, stream);
+    return launch_subwarp<8, 2, 16>(p, stream);
+  }
   if (d4 <= 16) {
     switch (variant) {
       case 0: return launch_subwarp<16, 2, 16>(p, stream);     // default: sub-warp rows, 64 resident warps
@@ -804,6 +839,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
       case 13: return launch_subwarp<16, 4, 12>(p, stream);
       case 14: return launch_subwarp<16, 4, 10>(p, stream);
       case 15: return launch_subwarp<16, 8, 8>(p, stream);
+      case 16: return launch_subwarp<16, 2, 16, true>(p, stream);   // sub-warp rows + one CTA per slice (measurement pending)
       default: return launch_subwarp<16, 2, 16>(p, stream);
     }
   }

@@ -92,7 +92,7 @@ def test_csr_reference_fixture_and_gcn_norm_bit_exact(cuda_dev):
 # ------------------------------------------------------------------ SpMM
 @pytest.mark.parametrize("d", [4, 8, 32, 64, 84, 128, 256, 6])
 @pytest.mark.parametrize("chunk", [256, 8, 0])
-def test_spmm_vs_oracle(cuda_dev, d, chunk):
+def test_spmm_vs_oracle(cuda_dev, d, chunk, variant=None):
     seq = chunk == 0 or d % 4 != 0
     n, nnz = 700, 30000
     row, col = random_graph(d, n, n, nnz, skew=True)
@@ -103,16 +103,25 @@ def test_spmm_vs_oracle(cuda_dev, d, chunk):
     g = g.with_values(val)
     X = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
     rowptr, c = g.rowptr.cpu().long(), g.colidx.cpu().long()
-    spmm_close(g.spmm(X.to(cuda_dev)), rowptr, c, val.cpu(), X, sequential=seq)
+    spmm_close(g.spmm(X.to(cuda_dev), variant=variant), rowptr, c, val.cpu(), X, sequential=seq)
     # unweighted sum and mean (hetero aggregation) on the same structure
     g1 = g.with_values(None)
-    spmm_close(g1.spmm(X.to(cuda_dev)), rowptr, c, None, X, sequential=seq)
+    spmm_close(g1.spmm(X.to(cuda_dev), variant=variant), rowptr, c, None, X, sequential=seq)
     deg = (rowptr[1:] - rowptr[:-1]).clamp(min=1).float().unsqueeze(1)
-    spmm_close(g1.spmm(X.to(cuda_dev), mean=True), rowptr, c, None, X, post=lambda y: y / deg.to(y.dtype), sequential=seq)
+    spmm_close(g1.spmm(X.to(cuda_dev), mean=True, variant=variant), rowptr, c, None, X, post=lambda y: y / deg.to(y.dtype),
+               sequential=seq)
     # transposed operator (the backward)
     gt = g.transpose()
     colptr, r, csr2csc = lo.csc_from_csr(rowptr, c, n)
-    spmm_close(gt.spmm(X.to(cuda_dev)), colptr, r, val.cpu()[csr2csc], X, sequential=seq)
+    spmm_close(gt.spmm(X.to(cuda_dev), variant=variant), colptr, r, val.cpu()[csr2csc], X, sequential=seq)
+
+
+@pytest.mark.parametrize("d", [8, 32, 48, 64])
+@pytest.mark.parametrize("chunk", [256, 8, 40])
+def test_spmm_wide_slice_variant_vs_oracle(cuda_dev, d, chunk):
+    """Variant 16 (one CTA per slice of a long row, opt-in until measured) against the oracle, incl. slices shorter than
+    one 32-entry batch per warp (chunk 8) and slices that leave some of the four warps without work (chunk 40)."""
+    test_spmm_vs_oracle(cuda_dev, d, chunk, variant=16)
 
 
 def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
@@ -141,8 +150,9 @@ def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
-    """All 16 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
-    cp.async rings, sub-warp rows) compute the same operator with the same fused epilogue: rtol 1e-5 against the default."""
+    """All 17 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    cp.async rings, sub-warp rows, CTA-wide slices) compute the same operator with the same fused epilogue: rtol 1e-5
+    against the default."""
     row, col = random_graph(d + 1, n, n, nnz, skew=True)
     g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
     _, val = g.gcn_norm()
@@ -150,11 +160,11 @@ def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
     gen = torch.Generator().manual_seed(d)
     X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
     outs = {}
-    for variant in range(16):
+    for variant in range(17):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
-    for v in range(1, 16):
+    for v in range(1, 17):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
