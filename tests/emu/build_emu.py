@@ -8,8 +8,8 @@ rewrites happen on the way, on copies under tests/emu/_build/gen/:
   * the bodies of the handful of helper functions written in inline PTX (cache-hinted loads/stores, red.global.add.v4,
     cp.async) are replaced by their plain C++ meaning (table ``ASM_BODIES``); any other ``asm`` makes the build fail.
 
-csrc/peer.cu (multimem / peer-memory collectives) needs several devices and is replaced by stubs that return an error.
-The result, tests/emu/_build/liblaplace_b200_emu.so, exports the same C ABI as the real library and is loaded ONLY by
+For csrc/peer.cu the peers are plain host buffers of one process and the NVSwitch multicast address is a key registered
+with emu_multicast_bind() (engine.cpp).  The result, tests/emu/_build/liblaplace_b200_emu.so, exports the same C ABI as the real library and is loaded ONLY by
 tests (tests/emu/harness.py); the product package never references it.
 """
 from __future__ import annotations
@@ -26,7 +26,7 @@ HEADER = os.path.join(REPO, "include", "laplace_b200.h")
 BUILD = os.path.join(HERE, "_build")
 GEN = os.path.join(BUILD, "gen")
 LIB_PATH = os.path.join(BUILD, "liblaplace_b200_emu.so")
-SKIP = {"peer.cu"}
+SKIP = set()
 
 # helper name -> C++ body with the meaning of the PTX it wraps
 ASM_BODIES = {
@@ -39,21 +39,12 @@ ASM_BODIES = {
     "cp_async_16": "*reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);",
     "cp_async_commit": "",
     "cp_async_wait": "",
+    # NVSwitch multicast (csrc/peer.cu): the "multicast address" is a key registered with emu_multicast_bind(); a load-reduce
+    # sums the peers' copies, a store writes all of them
+    "multimem_ld_reduce_f4": "return emu::mc_ld_reduce(mc);",
+    "multimem_st_f4": "emu::mc_st(mc, v);",
 }
 
-PEER_STUBS = r'''
-#include "common.cuh"
-extern "C" {
-int lgb_multimem_allreduce_f32(void*, int64_t, int32_t, int32_t, void*) {
-  lgb::set_error("lgb_multimem_allreduce_f32: not available in the CPU emulator (needs NVSwitch multicast)");
-  return LGB_ECUDA;
-}
-int lgb_peer_allreduce_f32(const uint64_t*, int64_t, int32_t, int32_t, void*) {
-  lgb::set_error("lgb_peer_allreduce_f32: not available in the CPU emulator (needs peer devices)");
-  return LGB_ECUDA;
-}
-}
-'''
 
 
 def _skip_string(src: str, i: int) -> int:
@@ -197,9 +188,7 @@ def build(force: bool = False) -> str:
         open(dst, "w").write(text)
         if dst.endswith(".cpp"):
             units.append(dst)
-    stub = os.path.join(GEN, "peer_stubs.cpp")
-    open(stub, "w").write(PEER_STUBS)
-    units += [stub, os.path.join(HERE, "engine.cpp")]
+    units += [os.path.join(HERE, "engine.cpp")]
     flags = ["-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-strict-aliasing", "-Wno-unknown-pragmas",
              "-Wno-unused-variable", "-I", os.path.join(HERE, "include"), "-I", GEN]
 

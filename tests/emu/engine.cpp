@@ -269,6 +269,36 @@ void note_inactive_read(const char* what) {
   abort();
 }
 
+// ---- emulated NVSwitch multicast object: [mc_base, mc_base + bytes) fans out to `world` peer buffers -------------------
+namespace {
+struct Multicast { char* base; size_t bytes; std::vector<char*> peers; };
+std::vector<Multicast> g_mc;
+const Multicast* find_mc(const void* p) {
+  for (const Multicast& m : g_mc)
+    if ((const char*)p >= m.base && (const char*)p < m.base + m.bytes) return &m;
+  return nullptr;
+}
+}  // namespace
+
+float4 mc_ld_reduce(const float4* mc) {
+  const Multicast* m = find_mc(mc);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!m) { fail("multimem.ld_reduce on an address that is not a bound multicast object"); return acc; }
+  const size_t off = (const char*)mc - m->base;
+  for (char* peer : m->peers) {
+    const float4 v = *reinterpret_cast<const float4*>(peer + off);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  return acc;
+}
+
+void mc_st(float4* mc, const float4& v) {
+  const Multicast* m = find_mc(mc);
+  if (!m) { fail("multimem.st on an address that is not a bound multicast object"); return; }
+  const size_t off = (const char*)mc - m->base;
+  for (char* peer : m->peers) *reinterpret_cast<float4*>(peer + off) = v;
+}
+
 cudaError_t take_error() {
   if (g_error.empty()) return cudaSuccess;
   g_last_error_text = g_error;
@@ -279,3 +309,13 @@ cudaError_t take_error() {
 const char* error_string() { return g_last_error_text.c_str(); }
 
 }  // namespace emu
+
+extern "C" void emu_multicast_bind(void* mc_base, size_t bytes, int world, void** peer_bases) {
+  emu::Multicast m;
+  m.base = (char*)mc_base;
+  m.bytes = bytes;
+  for (int r = 0; r < world; ++r) m.peers.push_back((char*)peer_bases[r]);
+  for (auto& old : emu::g_mc)
+    if (old.base == m.base) { old = m; return; }
+  emu::g_mc.push_back(m);
+}

@@ -60,6 +60,8 @@ void block_barrier();
 cudaError_t take_error();            // returns and clears the sticky launch error
 const char* error_string();
 void note_inactive_read(const char* what);
+float4 mc_ld_reduce(const float4* mc);   // emulated NVSwitch multicast: see emu_multicast_bind() in engine.cpp
+void mc_st(float4* mc, const float4& v);
 extern uint3 g_threadIdx, g_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 

@@ -96,3 +96,30 @@ def test_emulator_reports_undefined_warp_collectives():
     """The emulator itself: a launch error must surface through the library's own error path."""
     from tests.emu.selftest import run_selftest
     run_selftest()
+
+
+@pytest.mark.parametrize("world,n_floats", [(8, 105_542 * 64), (3, 1000), (4, 8), (16, 4 * 16 * 3 + 4)])
+def test_item_block_exchange_kernels(world, n_floats):
+    """csrc/peer.cu (the NCCL-free exchange of the replicated item block): every rank reduces ITS slice over all peers and
+    republishes it to all peers.  Peers are host buffers here and the NVSwitch multicast address is an emulated key, so this
+    checks the slice arithmetic and the kernels' data flow, not the multimem PTX itself."""
+    import ctypes as C
+    from tests.emu.harness import load_emu
+    lib = load_emu()
+    gen = torch.Generator().manual_seed(world)
+    for kind in ("peer", "multimem"):
+        bufs = [torch.randn(n_floats, generator=gen) for _ in range(world)]
+        want = torch.stack(bufs).sum(0) if n_floats else torch.zeros(0)
+        if kind == "peer":
+            arr = (C.c_uint64 * world)(*[b.data_ptr() for b in bufs])
+            for rank in range(world):          # ranks run one after the other: their slices are disjoint
+                assert lib.lgb_peer_allreduce_f32(arr, n_floats, rank, world, None) == 0, lib.lgb_last_error()
+        else:
+            key = torch.empty(max(n_floats, 4))   # stands for the multicast mapping: only its address range is used
+            ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+            lib.emu_multicast_bind(C.c_void_p(key.data_ptr()), C.c_size_t(key.numel() * 4), world, ptrs)
+            for rank in range(world):
+                assert lib.lgb_multimem_allreduce_f32(key.data_ptr(), n_floats, rank, world, None) == 0, lib.lgb_last_error()
+        for b in bufs:
+            torch.testing.assert_close(b, want, rtol=1e-6, atol=1e-6)
+            assert torch.equal(b, bufs[0])      # one reducer per slice: bit-identical on every rank
