@@ -184,7 +184,7 @@ class SymmOps(CudaOps):
         self.comm.wait_stream(cur)
         with torch.cuda.stream(self.comm):
             stage.copy_(t.reshape(-1))
-            h.barrier(channel=0)                                   # every rank's partial sums are staged
+            h.barrier(channel=0, timeout_ms=20000)                                   # every rank's partial sums are staged
             off = int(getattr(h, "offset", 0))
             mc = int(h.multicast_ptr) if h.multicast_ptr else 0
             with torch.cuda.device(self.device):
@@ -196,7 +196,7 @@ class SymmOps(CudaOps):
                     arr = (C.c_uint64 * h.world_size)(*[int(p) + off for p in h.buffer_ptrs])
                     check(lib.lgb_peer_allreduce_f32(arr, n, h.rank, h.world_size, self.comm.cuda_stream), "peer_allreduce")
             _lib.count_launch()
-            h.barrier(channel=1)                                   # every slice is republished on every rank
+            h.barrier(channel=1, timeout_ms=20000)                                   # every slice is republished on every rank
             t.reshape(-1).copy_(stage)
         return _StreamWait(self.comm, cur)
 
