@@ -13,7 +13,8 @@ import time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _common  # noqa: E402
 import laplace_gnn_recommendation_b200 as lg  # noqa: E402
 from laplace_gnn_recommendation_b200 import hetero  # noqa: E402
 from laplace_gnn_recommendation_b200.csr import DeviceCSR  # noqa: E402
@@ -47,7 +48,11 @@ def main():
     ap.add_argument("--aggr", default="add")
     ap.add_argument("--steps", type=int, default=20)
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    dev = _common.device()
+    if _common.DRYRUN:
+        for k, v in list(SIZES.items()):
+            SIZES[k] = tuple(max(x // 200, 16) for x in v)
+        a.steps = 1
     metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
     for size in a.sizes.split(","):
         x, ei, eli, y = make_batch(size, dev)
@@ -67,20 +72,20 @@ def main():
         orig = DeviceCSR.spmm
 
         def timed(self, *args, **kw):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1 = _common.Event(), _common.Event()
             e0.record(); out = orig(self, *args, **kw); e1.record()
             events.append((e0, e1, self.nnz, self.n_rows, args[0].shape[1]))
             return out
         for _ in range(5):
             step()
-        torch.cuda.synchronize()
+        _common.sync()
         DeviceCSR.spmm = timed
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0, t1 = _common.Event(), _common.Event()
         t0.record()
         for _ in range(a.steps):
             loss = step()
         t1.record()
-        torch.cuda.synchronize()
+        _common.sync()
         DeviceCSR.spmm = orig
         ms = t0.elapsed_time(t1) / a.steps
         agg_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in events) / a.steps

@@ -14,16 +14,23 @@ case "${1:-single}" in
     T 200 python bench.py --steps 20 --warmup 5 | tail -1 > gpurun_out/bench_hm.json
     T 200 python bench.py --steps 20 --warmup 5 --degree uniform --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_uniform.json
     T 200 python bench.py --steps 50 --warmup 5 --workload ml1m --no-cpu-baseline | tail -1 > gpurun_out/bench_ml1m.json
-    T 200 python tools/spmm_probe.py --variants 0,12,13 2>&1 | grep -v Warn
+    LGB_SPMM_VARIANT=16 T 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_v16.json
+    T 200 python tools/spmm_probe.py --variants 0,16,12,13 2>&1 | grep -v Warn
+    # one GPU standing in for rank r of an 8- / 4-way sharded run: per-launch latency floor, slice size, CTA-wide slices
+    T 400 python tools/shard_probe.py --world 8 --ranks 0,7 --variants 0,16,12 --chunks 1024,256 2>&1 | grep -v Warn
+    T 300 python tools/shard_probe.py --world 4 --ranks 0 --variants 0,16 --chunks 1024,512 2>&1 | grep -v Warn
     T 300 python tools/hetero_bench.py 2>&1 | tail -12
     T 600 python tools/sweep.py 2>&1 | tail -12
     ;;
   dist2|dist4|dist8)
     n=${1#dist}
-    for mode in "layer,0,nccl" "layer,1,nccl" "pipelined,0,nccl" "pipelined,1,nccl" "layer,0,symm" "pipelined,1,symm"; do
+    for mode in "layer,0,nccl" "layer,1,nccl" "pipelined,0,nccl" "pipelined,1,nccl" "merged,0,nccl" "merged,1,nccl" "layer,0,symm" "pipelined,1,symm" "merged,1,symm"; do
       DIST_CHECK_MODE=$mode TR "$n" tests/dist_gpu_check.py 2>&1 | grep -E "DIST_OK|Error|error|rc=" | head -6
     done
     TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 | tail -2 | cut -c1-300
+    LGB_SPMM_VARIANT=16 TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 | tail -2 | cut -c1-300
+    LGB_SPMM_VARIANT=16 TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule merged | tail -2 | cut -c1-300
+    LGB_SPMM_VARIANT=16 TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule merged --exchange symm | tail -2 | cut -c1-300
     TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule pipelined | tail -2 | cut -c1-300
     TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule pipelined --exchange symm | tail -2 | cut -c1-300
     TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 --schedule pipelined --graph | tail -2 | cut -c1-300

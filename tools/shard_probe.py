@@ -14,23 +14,12 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _common  # noqa: E402
+from _common import timeit  # noqa: E402
 from bench import WORKLOADS, make_graph  # noqa: E402
 from laplace_gnn_recommendation_b200.csr import DeviceCSR  # noqa: E402
 from laplace_gnn_recommendation_b200.dist import ShardedLightGCN  # noqa: E402
-
-
-def timeit(fn, reps=20):
-    for _ in range(5):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
 
 
 def main():
@@ -42,11 +31,13 @@ def main():
     ap.add_argument("--degree", default="powerlaw")
     ap.add_argument("--d", type=int, default=64)
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    dev = _common.device()
     U, I, E = WORKLOADS["hm"]
+    if _common.DRYRUN:
+        U, I, E = U // 400, I // 400, E // 400
     users, items = make_graph(U, I, E, a.degree, 1234, dev)
     for rank in [int(x) for x in a.ranks.split(",")]:
-        eng = ShardedLightGCN(U, I, a.d, 3, users, items, dev, rank=rank, world=a.world)   # no process group: local degrees
+        eng = ShardedLightGCN(U, I, a.d, 3, users, items, dev, rank=rank, world=a.world, ops=_common.make_ops(dev))   # no process group: local degrees
         g, Ug, n = eng.g_full, eng.Ug, eng.n
         X, Y, acc = eng.table, eng._ya, eng.E_f
         X.normal_(0, 0.1); acc.normal_(0, 0.1)
@@ -65,7 +56,7 @@ def main():
                 print(f"    variant {v:2d}: items {t_i * 1e3:7.1f} us | users {t_u * 1e3:7.1f} us | sum {(t_i + t_u) * 1e3:7.1f} us | "
                       f"merged launch {t_m * 1e3:7.1f} us   ({eng.local_edges / 1e6:.2f} M edges per direction)")
         del eng
-        torch.cuda.empty_cache()
+        _common.empty_cache()
 
 
 if __name__ == "__main__":

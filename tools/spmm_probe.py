@@ -6,23 +6,12 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _common  # noqa: E402
+from _common import timeit  # noqa: E402
 import laplace_gnn_recommendation_b200 as lg  # noqa: E402
 from bench import WORKLOADS, make_graph, spmm_bytes  # noqa: E402
 from laplace_gnn_recommendation_b200.dist import CudaOps  # noqa: E402
-
-
-def timeit(fn, reps=10):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
 
 
 def main():
@@ -32,13 +21,15 @@ def main():
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--workload", default="hm")
     a = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    dev = _common.device()
     U, I, E = WORKLOADS[a.workload]
+    if _common.DRYRUN:
+        U, I, E = U // 400 + 8, I // 400 + 8, E // 400
     users, items = make_graph(U, I, E, a.degree, 1234, dev)
     row = torch.cat([users, items + U]); col = torch.cat([items + U, users])
     adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(U + I, U + I))
     g = lg.gcn_norm(adj, add_self_loops=False).csr()
-    ops = CudaOps(dev)
+    ops = _common.make_ops(dev)
     gu, gi = ops.row_view(g, 0, U), ops.row_view(g, U, U + I)
     N, d = U + I, a.d
     X = torch.randn(N, d, device=dev); Y = torch.empty(N, d, device=dev); acc = torch.randn(N, d, device=dev)
