@@ -318,7 +318,7 @@ class ShardedLightGCN:
     # so all-reduce(items^{k+1}) is only needed by users^{k+2}: it can overlap with users^{k+1} AND items^{k+2}.
     # Validated against the oracle over gloo (tests/test_dist_gloo.py); B200 measurement pending.
     def _propagate_pipelined(self, x0, K, resid=None, acc0=None, acc=None, acc_div_last=1.0, out_last=None,
-                             before_last_reduce=None):
+                             before_last_reduce=None, x0_items_pending=None):
         Ug, ops = self.Ug, self.ops
         bufs = [self._ya, self._yb]
         x, pending = x0, None            # pending = epilogue of the layer whose item rows are still being reduced
@@ -326,6 +326,8 @@ class ShardedLightGCN:
             last = k == K - 1
             y = out_last if (last and out_last is not None) else bufs[k % 2]
             ops.spmm(self.g_items, x, Y=y[Ug:])                               # items^{k+1} partial (reads user rows of x)
+            if k == 0 and x0_items_pending is not None:                        # x0's item rows were still being all-reduced
+                x0_items_pending.wait()
             if last and before_last_reduce is not None:
                 before_last_reduce(y[Ug:])
             if pending is not None:                                            # x's item rows must be complete now
@@ -380,15 +382,21 @@ class ShardedLightGCN:
             x, y = y, (self._yb if y is self._ya else self._ya)
         return Ef
 
-    def backward(self, r: torch.Tensor, before_last_reduce=None) -> torch.Tensor:
-        """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (item rows already summed over ranks).  The local block is
-        symmetric, so A^T is the same pair of row views."""
+    def backward(self, r: torch.Tensor, before_last_reduce=None, r_items_pending=None) -> torch.Tensor:
+        """grad = sum_k (A^T)^k r with r = dE_f/(K+1).  The local block is symmetric, so A^T is the same pair of row views.
+        r's item rows must be the sum over ranks: either already (r_items_pending None) or once r_items_pending.wait()
+        returns -- the first layer's items SpMM only reads r's USER rows, so that all-reduce is hidden behind it."""
         K = self.K
+        if K == 0 or self.schedule == "merged":
+            if r_items_pending is not None:          # nothing to hide it behind
+                r_items_pending.wait()
+                r_items_pending = None
         if K == 0:
             self.grad.copy_(r)
             return self.grad
         if self.schedule == "pipelined":
-            return self._propagate_pipelined(r, K, resid=r, out_last=self.grad, before_last_reduce=before_last_reduce)
+            return self._propagate_pipelined(r, K, resid=r, out_last=self.grad, before_last_reduce=before_last_reduce,
+                                             x0_items_pending=r_items_pending)
         g = r
         bufs = [self._ya, self._yb]
         for k in range(K):
@@ -398,11 +406,13 @@ class ShardedLightGCN:
                 self._layer_merged(g, dst, resid=r, before_reduce=before_last_reduce if last else None)
                 g = dst
                 continue
-            if last and before_last_reduce is not None:
-                # fold the extra partial item-row terms into this layer's all-reduce
+            if (last and before_last_reduce is not None) or (k == 0 and r_items_pending is not None):
                 Ug, ops = self.Ug, self.ops
-                ops.spmm(self.g_items, g, Y=dst[Ug:])
-                before_last_reduce(dst[Ug:])
+                ops.spmm(self.g_items, g, Y=dst[Ug:])                     # reads user rows of g only
+                if k == 0 and r_items_pending is not None:
+                    r_items_pending.wait()                                # from here on r's item rows are needed
+                if last and before_last_reduce is not None:
+                    before_last_reduce(dst[Ug:])                          # fold extra partial item-row terms into this all-reduce
                 h = ops.all_reduce_async(dst[Ug:])
                 ops.spmm(self.g_users, g, Y=dst[:Ug], resid=r[:Ug])
                 self._finish_items(h, dst, r, None, None, 1.0)
@@ -458,20 +468,20 @@ class ShardedLightGCN:
         loss_slot = r[self.n, :1].view(())
         flt = dict(user_lo=self.lo, user_hi=self.hi)
         ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, loss=loss_slot, dEf=r, gscale=1.0 / (K + 1), **flt)
-        ops.all_reduce_async(r[Ug:]).wait()           # item-row gradients + loss: ONE all-reduce
-        rr = r[: self.n]
+        h_r = ops.all_reduce_async(r[Ug:])            # item-row gradients + loss: ONE all-reduce, hidden behind the first
+        rr = r[: self.n]                              # backward layer's items SpMM (which only reads r's user rows)
 
         def add_item_reg(items_partial):              # 2*lambda*E0[p], E0[n] of the local triples
             ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, dE0_items=items_partial, **flt)
         if K == 0:
-            G = self.backward(rr)
+            G = self.backward(rr, r_items_pending=h_r)
             reg_items = self._ya[Ug:]
             ops.zero(reg_items)
             add_item_reg(reg_items)
             ops.all_reduce_async(reg_items).wait()
             ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
         else:
-            G = self.backward(rr, before_last_reduce=add_item_reg)
+            G = self.backward(rr, before_last_reduce=add_item_reg, r_items_pending=h_r)
         ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, dE0_users=G, **flt)   # owned users: local
         self.loss = loss_slot
         return loss_slot

@@ -105,17 +105,32 @@ def single_process_reference(pb):
     return lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, pb["K"], pb["u"], pb["p"], pb["n"], pb["lam"])
 
 
-def make_emu_ops():
+def make_emu_ops(lazy: bool = True):
     """dist.CudaOps itself -- row views, lgb_gcn_values, lgb_spmm(_split), lgb_accumulate, lgb_bpr with B_norm and the
     owned-user filter -- with the kernels served by the CPU emulation of the library (tests/emu/) and the collectives by
     gloo.  Only the two CUDA-stream specifics of the class are replaced."""
     from laplace_gnn_recommendation_b200.dist import CudaOps, _Done
+
+    class _Lazy:
+        """Handle of an all-reduce that only happens when somebody waits for it: the latest moment a real asynchronous
+        collective may complete.  Code that reads the buffer before wait() sees the un-reduced partial sums and fails the
+        parity check -- the CPU stand-in for a missing stream dependency."""
+
+        def __init__(self, ops, t):
+            self.ops, self.t = ops, t
+
+        def wait(self):
+            if self.t is not None:
+                self.ops.all_reduce(self.t)
+                self.t = None
 
     class EmuOps(CudaOps):
         def __init__(self, device, group=None):
             self.device, self.group, self.comm, self._bpr_ws = device, group, None, None
 
         def all_reduce_async(self, t):
+            if lazy:
+                return _Lazy(self, t)
             self.all_reduce(t)
             return _Done()
 
