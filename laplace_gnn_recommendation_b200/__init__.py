@@ -15,7 +15,7 @@ from .hetero import (EdgeDecoder, Encoder_Decoder_Model, GNNEncoder, HeteroEncod
 from .lightgcn import LightGCN  # noqa: F401
 from .loader import (both_indexes_from_zero, make_lightgcn_splits, sample_mini_batch, split,  # noqa: F401
                      structured_negative_sampling)
-from .metrics import evaluation, get_metrics_lightgcn, recall_precision_ndcg  # noqa: F401
+from .metrics import evaluation, get_metrics_lightgcn, get_metrics_universal, recall_precision_ndcg  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .sparse import SparseTensor, gcn_norm, matmul  # noqa: F401
 from .topk import SeenItems, make_predictions_for_user, recommend_topk, topk_dict  # noqa: F401
@@ -26,5 +26,5 @@ __all__ = [
     "SeenItems", "topk_dict", "SAGEConv", "to_hetero", "GNNEncoder", "HeteroEncoder", "EdgeDecoder",
     "Encoder_Decoder_Model", "get_SAGEConv_layers", "get_linear_layers", "aggregate", "build_edge_csr",
     "edge_concat", "edge_dot", "both_indexes_from_zero", "split", "make_lightgcn_splits", "evaluation",
-    "get_metrics_lightgcn", "recall_precision_ndcg", "FusedAdam",
+    "get_metrics_lightgcn", "get_metrics_universal", "recall_precision_ndcg", "FusedAdam",
 ]

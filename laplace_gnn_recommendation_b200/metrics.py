@@ -44,6 +44,47 @@ def recall_precision_ndcg(topk_ids: torch.Tensor, users: torch.Tensor, edge_inde
     return recall.item(), precision.item(), torch.mean(ndcg).item()
 
 
+def _recall_precision_ndcg_from_hits(r: torch.Tensor, n_liked: torch.Tensor, k: int) -> Tuple[float, float, float]:
+    dev = r.device
+    num_correct = r.sum(dim=-1).float()
+    recall = torch.mean(num_correct / n_liked)
+    precision = torch.mean(num_correct) / k
+    discount = 1.0 / torch.log2(torch.arange(2, k + 2, device=dev, dtype=torch.float32))
+    ideal = (torch.arange(k, device=dev).unsqueeze(0) < torch.clamp(n_liked, max=k).unsqueeze(1)).float()
+    idcg = (ideal * discount).sum(dim=1)
+    dcg = (r.float() * discount).sum(dim=1)
+    idcg[idcg == 0.0] = 1.0
+    ndcg = dcg / idcg
+    ndcg[torch.isnan(ndcg)] = 0.0
+    return recall.item(), precision.item(), torch.mean(ndcg).item()
+
+
+def get_metrics_universal(model_output: torch.Tensor, edge_index: torch.Tensor, edge_label_index: torch.Tensor,
+                          exclude_edge_indices: List[torch.Tensor], k: int) -> Tuple[float, float, float]:
+    """Ranking-model metrics with the reference's signature and semantics (utils/metrics_encoder_decoder.py:29-86, called
+    by training.py:38-56 on ``Encoder_Decoder_Model.infer`` output), vectorised on the device of ``model_output`` instead
+    of per-edge / per-user Python loops on the CPU.  Reference quirks kept: excluded pairs address row
+    ``user`` / column ``item`` of the padded [users, max_candidates] score matrix; the top-k entries are column positions
+    and are matched against the item ids of ``edge_index``.  The caller's tensor is never modified."""
+    ratings = model_output.detach()
+    ratings = (ratings.unsqueeze(0) if ratings.dim() < 2 else ratings).clone()
+    dev = ratings.device
+    for ex in exclude_edge_indices:
+        if ex.numel():
+            ex = ex.to(dev)
+            ratings[ex[0], ex[1]] = -(1 << 10)
+    _, top = torch.topk(ratings, k=k)
+    ei = edge_index.detach().to(dev)
+    users = edge_label_index.detach().to(dev)[0].unique(sorted=True)
+    top = top[: users.numel()]
+    m = int(max(ratings.shape[1], int(ei[1].max()) + 1 if ei.numel() else 1))
+    r = torch.isin(users.unsqueeze(1) * m + top, ei[0] * m + ei[1])                      # hit matrix [n_users, k]
+    slot = torch.searchsorted(users, ei[0]).clamp(max=max(users.numel() - 1, 0))
+    mine = users[slot] == ei[0] if users.numel() else torch.zeros_like(ei[0], dtype=torch.bool)
+    n_liked = torch.bincount(slot[mine], minlength=users.numel()).to(torch.float32)    # duplicate edges counted, like len()
+    return _recall_precision_ndcg_from_hits(r, n_liked, k)
+
+
 def get_metrics_lightgcn(model, edge_index: torch.Tensor, exclude_edge_indices: List[torch.Tensor], k: int
                          ) -> Tuple[float, float, float]:
     """utils/metrics_lightgcn.py:79-122: top-k on the LAYER-0 tables (reference quirk), seen items excluded."""

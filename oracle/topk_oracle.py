@@ -66,3 +66,23 @@ def metrics_lightgcn(user_emb: Tensor, item_emb: Tensor, edge_index: Tensor,
     r = torch.stack([torch.isin(top[int(u)], positives[int(u)]) for u in users])
     recall, precision = recall_precision_at_k(pos_list, r, k)
     return recall, precision, ndcg_at_k(pos_list, r, k), top
+
+
+def metrics_universal(model_output: Tensor, edge_index: Tensor, edge_label_index: Tensor,
+                      exclude_edge_indices: List[Tensor], k: int):
+    """utils/metrics_encoder_decoder.py:29-86 (ranking model, called from training.py:38-56 on ``model.infer`` output),
+    restated with the same per-user loops.  Quirks kept: excluded (user, item) pairs address ROW ``user`` / COLUMN ``item``
+    of the padded [users, max_candidates] matrix and are set to -(1 << 10); the top-k entries are column positions and
+    are matched against the ITEM IDS of ``edge_index``; the first ``len(users)`` rows are scored."""
+    ratings = model_output.detach().clone()
+    if ratings.dim() < 2:
+        ratings = ratings.unsqueeze(0)
+    for ex in exclude_edge_indices:
+        for j in range(ex.shape[1]):
+            ratings[int(ex[0][j]), int(ex[1][j])] = -(1 << 10)
+    _, top = torch.topk(ratings, k=k)
+    users = edge_label_index[0].unique(sorted=True)
+    truth = [edge_index[1][edge_index[0] == u] for u in users]
+    r = torch.stack([torch.isin(top[i], truth[i]) for i in range(len(users))])
+    recall, precision = recall_precision_at_k(truth, r, k)
+    return recall, precision, ndcg_at_k(truth, r, k)

@@ -71,3 +71,24 @@ def test_hetero_module_names_match_reference_checkpoint(golden):
     assert sorted(model.state_dict().keys()) == sorted(h["cases"][0]["state_dict"].keys())
     assert lg.get_SAGEConv_layers(3, 16, 8, "mean")[-1].out_channels == 8
     assert [l.out_features for l in lg.get_linear_layers(3, 16, 32, 1)] == [32, 32, 1]
+
+
+def test_ranking_metrics_match_reference_golden():
+    """get_metrics_universal (utils/metrics_encoder_decoder.py:29-86) -- oracle AND the vectorised mirror against values the
+    real reference function produced (tests/golden/make_golden_ranking.py), incl. the infer() re-batching that feeds it."""
+    import os
+    import laplace_gnn_recommendation_b200 as lg
+    from oracle import topk_oracle as to
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_golden_ranking.pt")
+    for c in torch.load(path, weights_only=False)["universal"]:
+        want = (c["recall"], c["precision"], c["ndcg"])
+        before = c["infer_out"].clone()
+        got_o = to.metrics_universal(c["infer_out"], c["edge_index"], c["edge_label_index"], c["exclude"], c["k"])
+        got = lg.get_metrics_universal(c["infer_out"], c["edge_index"], c["edge_label_index"], c["exclude"], c["k"])
+        assert got_o == pytest.approx(want, rel=1e-6, abs=1e-7)
+        assert got == pytest.approx(want, rel=1e-6, abs=1e-7)
+        assert torch.equal(before, c["infer_out"])           # the caller's scores are left alone
+        if c["infer_out"].dim() == 2:                        # the re-batching of model.infer (padded_stack of per-user scores)
+            users = c["edge_label_index"][0].unique(sorted=True)
+            rebatched = lg.hetero.padded_stack([c["scores"][c["edge_label_index"][0] == u] for u in users], value=-(1 << 50))
+            assert torch.equal(rebatched, c["infer_out"])
