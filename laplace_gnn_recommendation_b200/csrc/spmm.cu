@@ -52,13 +52,22 @@ struct SpmmParams {
 
 // STEP = distance between the 32-entry batches this warp takes (32: the whole range; 32*SPMM_WARPS: every SPMM_WARPS-th
 // batch, when the warps of a CTA share one slice).
-template <int G, int VPL, int UNROLL, int STEP = 32>
+// IT = type of the element index into X: uint32_t whenever n_cols*d/4 < 2^31 (two integer instructions per gather address
+// instead of seven for the sign-extended 64-bit form -- the ncu capture of round 1 shows the SM issue slots 58 % busy, so
+// the instruction count of this loop is a first-order term), size_t for tables beyond that.
+// Loads and FMAs of the entries past the end of a row are predicated off (no zero-filled registers, no weight select).
+// D4C = d/4 when it is known at compile time (the row is exactly one float4 per lane of the group: d = 4*G*VPL, e.g. d = 64
+// with G = 16): the column-bound predicates disappear and the row offset becomes a shift; 0 = read it from the parameters.
+template <int G, int VPL, int UNROLL, int STEP = 32, typename IT = uint32_t, int D4C = 0>
 __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int e, int lane, float4 (&acc)[VPL]) {
   constexpr int NG = 32 / G;
+  static_assert(32 % (NG * UNROLL) == 0, "a batch of 32 entries must be a whole number of unrolled steps");
+  static_assert(D4C == 0 || D4C == G * VPL, "a compile-time d/4 must fill the lane group exactly");
   const int grp = lane / G;
   const int lig = lane % G;
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
-  const int d4 = p.d4;
+  const int d4 = D4C ? D4C : p.d4;
+  const IT d4i = (IT)d4;
   for (int base = s; base < e; base += STEP) {
     const int idx = base + lane;
     int c = 0;
@@ -71,23 +80,25 @@ __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int
     for (int j = 0; j < cnt; j += NG * UNROLL) {
       float4 v[UNROLL][VPL];
       float ww[UNROLL];
+      bool ok[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) {
-        const int k = j + u * NG + grp;
-        const int cc = __shfl_sync(FULL_MASK, c, k & 31);
-        const float wk = __shfl_sync(FULL_MASK, w, k & 31);
-        const bool ok = k < cnt;
-        ww[u] = ok ? wk : 0.f;
+        const int k = j + u * NG + grp;                 // < 32: j is a multiple of NG*UNROLL, which divides 32
+        const int cc = __shfl_sync(FULL_MASK, c, k);
+        ww[u] = __shfl_sync(FULL_MASK, w, k);
+        ok[u] = k < cnt;
+        const IT row = (IT)cc * d4i;
 #pragma unroll
         for (int q = 0; q < VPL; ++q) {
           const int f = lig + q * G;
-          v[u][q] = (ok && f < d4) ? ld_gather_f4(X4 + (size_t)cc * d4 + f) : f4_zero();
+          if (ok[u] && f < d4) v[u][q] = ld_gather_f4(X4 + (row + (IT)f));
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
-        for (int q = 0; q < VPL; ++q) f4_fma(acc[q], ww[u], v[u][q]);
+        for (int q = 0; q < VPL; ++q)
+          if (ok[u] && lig + q * G < d4) f4_fma(acc[q], ww[u], v[u][q]);
     }
   }
   // combine the groups (fixed butterfly order)
@@ -133,7 +144,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
 }
 
 // Stage 1: slices of long rows first (heaviest work is scheduled first), then one warp per ordinary row.
-template <int G, int VPL, int UNROLL, int MINB>
+template <int G, int VPL, int UNROLL, int MINB, typename IT = uint32_t>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const SpmmParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const 
     const int r = p.task_row[w];
     const int s = p.task_start[w];
     const int e = min(s + p.chunk, p.rowptr[r + 1]);
-    accumulate_slice<G, VPL, UNROLL>(p, s, e, lane, acc);
+    accumulate_slice<G, VPL, UNROLL, 32, IT>(p, s, e, lane, acc);
     if (lane < G) {
       float4* out = reinterpret_cast<float4*>(p.partial) + (size_t)w * p.d4;
 #pragma unroll
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const 
   const int s = p.rowptr[r];
   const int e = p.rowptr[r + 1];
   if (p.chunk > 0 && e - s > p.chunk) return;  // long row: handled by its slices + stage 2
-  accumulate_slice<G, VPL, UNROLL>(p, s, e, lane, acc);
+  accumulate_slice<G, VPL, UNROLL, 32, IT>(p, s, e, lane, acc);
   if (lane < G) epilogue_row<G, VPL>(p, r, e - s, lane, acc);
 }
 
@@ -344,12 +355,14 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
 // the slice cuts that chain by SPMM_WARPS without more registers, more partial rows or more long rows.
 constexpr int SUBW_MAX = 64;
 
-template <int G, int UNROLL, int MINB, bool WIDE = false>
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
+  static_assert(G % UNROLL == 0, "the unrolled gather step must divide the lane-group width");
+  static_assert(D4C == 0 || D4C == G, "a compile-time d/4 must fill the lane group exactly");
   constexpr int NG = 32 / G;
   const int lane = threadIdx.x & 31;
   const int grp = lane / G, lig = lane % G;
-  const int d4 = p.d4;
+  const int d4 = D4C ? D4C : p.d4;
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
   int64_t w;
   if (WIDE) {
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
       const int64_t t = blockIdx.x;
       const int s = p.task_start[t], e = p.task_end[t];
       float4 acc[1] = {f4_zero()};
-      accumulate_slice<G, 1, UNROLL, 32 * SPMM_WARPS>(p, s + 32 * wi, e, lane, acc);
+      accumulate_slice<G, 1, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C>(p, s + 32 * wi, e, lane, acc);
       if (lane < G) wsum[wi][lane] = acc[0];
       __syncthreads();
       if (wi == 0 && lane < G && lane < d4) {
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     const int r = p.task_row[w];
     (void)r;
     const int s = p.task_start[w], e = p.task_end[w];
-    accumulate_slice<G, 1, UNROLL>(p, s, e, lane, acc);
+    accumulate_slice<G, 1, UNROLL, 32, uint32_t, D4C>(p, s, e, lane, acc);
     if (lane < G && lane < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + lane, acc[0]);
     return;
   }
@@ -404,6 +417,8 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
 #pragma unroll
     for (int off = G; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL_MASK, maxdeg, off));
     float4 acc = f4_zero();
+    const uint32_t d4u = (uint32_t)d4;
+    const bool col_ok = lig < d4;
     for (int base = 0; base < maxdeg; base += G) {
       const int idx = s + base + lig;
       int c = 0;
@@ -414,20 +429,21 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
       }
       const int cnt = min(G, deg - base);          // may be <= 0 for the shorter row of the pair
       const int cntmax = min(G, maxdeg - base);
-      for (int j = 0; j < cntmax; j += UNROLL) {
+      for (int j = 0; j < cntmax; j += UNROLL) {    // j + u < G: UNROLL divides G
         float4 v[UNROLL];
         float ww[UNROLL];
+        bool ok[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
           const int k = j + u;
-          const int cc = __shfl_sync(FULL_MASK, c, k & (G - 1), G);
-          const float wk = __shfl_sync(FULL_MASK, wv, k & (G - 1), G);
-          const bool ok = k < cnt;
-          ww[u] = ok ? wk : 0.f;
-          v[u] = (ok && lig < d4) ? ld_gather_f4(X4 + (size_t)cc * d4 + lig) : f4_zero();
+          const int cc = __shfl_sync(FULL_MASK, c, k, G);
+          ww[u] = __shfl_sync(FULL_MASK, wv, k, G);
+          ok[u] = col_ok && k < cnt;
+          if (ok[u]) v[u] = ld_gather_f4(X4 + ((uint32_t)cc * d4u + (uint32_t)lig));
         }
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) f4_fma(acc, ww[u], v[u]);
+        for (int u = 0; u < UNROLL; ++u)
+          if (ok[u]) f4_fma(acc, ww[u], v[u]);
       }
     }
     if (r >= 0 && !is_long) {
@@ -444,7 +460,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     const int ee = __shfl_sync(FULL_MASK, e, g2 * G);
     if (rr < 0 || (p.chunk > 0 && ee - ss > p.chunk)) continue;
     float4 acc[1] = {f4_zero()};
-    accumulate_slice<G, 1, UNROLL>(p, ss, ee, lane, acc);
+    accumulate_slice<G, 1, UNROLL, 32, uint32_t, D4C>(p, ss, ee, lane, acc);
     if (lane < G) epilogue_row<G, 1>(p, rr, ee - ss, lane, acc);
   }
 }
@@ -452,15 +468,24 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0>
+static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream);
+
+// d/4 == G (d = 64 with G = 16, d = 32 with G = 8) gets the kernel specialised on that constant
 template <int G, int UNROLL, int MINB, bool WIDE = false>
 static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
+  return p.d4 == G ? launch_subwarp_impl<G, UNROLL, MINB, WIDE, G>(p, stream) : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0>(p, stream);
+}
+
+template <int G, int UNROLL, int MINB, bool WIDE, int D4C>
+static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   constexpr int NG = 32 / G;
   const int64_t row_warps = (p.n_rows + NG - 1) / NG;
   const int64_t warps = p.n_tasks + row_warps;
   if (warps > 0) {
     const int64_t blocks = WIDE ? p.n_tasks + (row_warps + SPMM_WARPS - 1) / SPMM_WARPS : (warps + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
@@ -656,14 +681,14 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int G, int VPL, int UNROLL, int MINB = 1>
+template <int G, int VPL, int UNROLL, int MINB = 1, typename IT = uint32_t>
 static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
   const int64_t items = p.n_tasks + p.n_rows;
   if (items > 0) {
     const int64_t blocks = (items + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
     if (variant == 1 || (p.n_tasks > 0 && !p.task_end)) {
-      spmm_rows_kernel<G, VPL, UNROLL, MINB><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+      spmm_rows_kernel<G, VPL, UNROLL, MINB, IT><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     } else {
       // persistent grid: every SM filled to the occupancy limit, each warp walks items w, w+W, ...
       static int occ = 0;
@@ -816,6 +841,17 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   // configuration that keeps 64 warps resident per SM (<= 32 registers: gather unroll 2, __launch_bounds__(128,16))
   // beats deeper unrolls (72 regs -> 28 warps) by 1.3x and the software-pipelined persistent variant by 1.5x.
   const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xFF;
+  if ((int64_t)g->n_cols * d4 > 0x7fffffffll || variant == 17) {
+    // element index into X does not fit 32 bits (a table of > 34 GB): the one kernel family compiled with 64-bit indexing
+    // (variant 17 forces it, so the tests can reach it with small tables)
+    if (d4 <= 8) return launch_vec<8, 1, 2, 16, size_t>(p, 1, stream);
+    if (d4 <= 16) return launch_vec<16, 1, 2, 16, size_t>(p, 1, stream);
+    if (d4 <= 32) return launch_vec<32, 1, 2, 16, size_t>(p, 1, stream);
+    if (d4 <= 64) return launch_vec<32, 2, 2, 12, size_t>(p, 1, stream);
+    if (d4 <= 128) return launch_vec<32, 4, 1, 8, size_t>(p, 1, stream);
+    set_error("lgb_spmm: d=%d > 512 not supported", d);
+    return LGB_EINVAL;
+  }
   if (d4 <= 8) {
     if (variant == 1) return launch_vec<8, 1, 2, 16>(p, 1, stream);
     if (variant == 16) return launch_subwarp<8, 2, 16, true>(p, stream);

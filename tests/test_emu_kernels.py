@@ -31,6 +31,7 @@ test_csr_build_bit_exact = TL.test_csr_build_bit_exact
 test_csr_reference_fixture_and_gcn_norm_bit_exact = TL.test_csr_reference_fixture_and_gcn_norm_bit_exact
 test_spmm_vs_oracle = TL.test_spmm_vs_oracle
 test_spmm_wide_slice_variant_vs_oracle = TL.test_spmm_wide_slice_variant_vs_oracle
+test_spmm_64bit_index_family_vs_oracle = TL.test_spmm_64bit_index_family_vs_oracle
 test_spmm_fused_epilogue_and_degree_order = TL.test_spmm_fused_epilogue_and_degree_order
 test_lightgcn_against_reference_golden = TL.test_lightgcn_against_reference_golden
 test_lightgcn_against_oracle = TL.test_lightgcn_against_oracle

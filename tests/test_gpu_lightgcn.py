@@ -124,6 +124,12 @@ def test_spmm_wide_slice_variant_vs_oracle(cuda_dev, d, chunk):
     test_spmm_vs_oracle(cuda_dev, d, chunk, variant=16)
 
 
+@pytest.mark.parametrize("d", [8, 64, 84, 128, 256])
+def test_spmm_64bit_index_family_vs_oracle(cuda_dev, d):
+    """Variant 17 = the kernels a table with n_cols*d/4 >= 2^31 elements is routed to (64-bit element index)."""
+    test_spmm_vs_oracle(cuda_dev, d, 256, variant=17)
+
+
 def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
     n, nnz, d = 500, 20000, 64
     row, col = random_graph(5, n, n, nnz, skew=True)
@@ -150,9 +156,9 @@ def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
-    """All 17 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
-    cp.async rings, sub-warp rows, CTA-wide slices) compute the same operator with the same fused epilogue: rtol 1e-5
-    against the default."""
+    """All 18 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    cp.async rings, sub-warp rows, CTA-wide slices, 64-bit element indexing) compute the same operator with the same fused
+    epilogue: rtol 1e-5 against the default."""
     row, col = random_graph(d + 1, n, n, nnz, skew=True)
     g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
     _, val = g.gcn_norm()
@@ -160,11 +166,11 @@ def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
     gen = torch.Generator().manual_seed(d)
     X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
     outs = {}
-    for variant in range(17):
+    for variant in range(18):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
-    for v in range(1, 17):
+    for v in range(1, 18):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
