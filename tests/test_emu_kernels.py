@@ -17,6 +17,7 @@ pytestmark = pytest.mark.skipif(platform.machine() != "x86_64", reason="the emul
 from tests.emu.harness import emulated  # noqa: E402
 import tests.test_gpu_hetero as TH  # noqa: E402
 import tests.test_gpu_lightgcn as TL  # noqa: E402
+import tests.test_gpu_zz_unmeasured as TZ  # noqa: E402
 
 
 @pytest.fixture
@@ -30,8 +31,8 @@ def cuda_dev():
 test_csr_build_bit_exact = TL.test_csr_build_bit_exact
 test_csr_reference_fixture_and_gcn_norm_bit_exact = TL.test_csr_reference_fixture_and_gcn_norm_bit_exact
 test_spmm_vs_oracle = TL.test_spmm_vs_oracle
-test_spmm_wide_slice_variant_vs_oracle = TL.test_spmm_wide_slice_variant_vs_oracle
-test_spmm_64bit_index_family_vs_oracle = TL.test_spmm_64bit_index_family_vs_oracle
+test_spmm_wide_slice_variant_vs_oracle = TZ.test_spmm_wide_slice_variant_vs_oracle
+test_spmm_64bit_index_family_vs_oracle = TZ.test_spmm_64bit_index_family_vs_oracle
 test_spmm_fused_epilogue_and_degree_order = TL.test_spmm_fused_epilogue_and_degree_order
 test_lightgcn_against_reference_golden = TL.test_lightgcn_against_reference_golden
 test_lightgcn_against_oracle = TL.test_lightgcn_against_oracle
@@ -41,9 +42,9 @@ test_sample_mini_batch_bit_exact_vs_reference_golden = TL.test_sample_mini_batch
 test_structured_negative_sampling_bit_exact = TL.test_structured_negative_sampling_bit_exact
 test_topk_against_reference_golden = TL.test_topk_against_reference_golden
 test_topk_against_oracle = TL.test_topk_against_oracle
-test_evaluation_matches_oracle = TL.test_evaluation_matches_oracle
-test_fused_adam_matches_torch_adam = TL.test_fused_adam_matches_torch_adam
-test_training_loop_with_fused_step_and_fused_adam = TL.test_training_loop_with_fused_step_and_fused_adam
+test_evaluation_matches_oracle = TZ.test_evaluation_matches_oracle
+test_fused_adam_matches_torch_adam = TZ.test_fused_adam_matches_torch_adam
+test_training_loop_with_fused_step_and_fused_adam = TZ.test_training_loop_with_fused_step_and_fused_adam
 
 # ---- hetero encoder-decoder path ---------------------------------------------------------------------------------
 test_aggregate_fwd_bwd_vs_oracle = TH.test_aggregate_fwd_bwd_vs_oracle
@@ -58,7 +59,7 @@ test_batch_sized_aggregation_properties = TH.test_batch_sized_aggregation_proper
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d):
-    TL.test_spmm_kernel_variants_agree(cuda_dev, d, n=1200, nnz=30000)   # smaller than on the GPU: 16 variants x 4 launches
+    TZ.test_spmm_kernel_variants_agree(cuda_dev, d, n=1200, nnz=30000)   # smaller than on the GPU: 16 variants x 4 launches
 
 
 def test_spmm_empty_and_single_heavy_row(cuda_dev):

@@ -1,0 +1,140 @@
+"""GPU parity tests that sort LAST on purpose (`pytest -x` stops at the first failure): everything here exercises code
+that has not yet had B200 time -- the opt-in SpMM kernel variants (cp.async rings, sub-warp unroll points, CTA-wide slices,
+64-bit indexing), evaluation(), the fused Adam step and the fused training loop.  Their logic is covered without a GPU by
+the emulator tier (tests/test_emu_kernels.py runs these very functions); a failure here must not hide the parity results
+of the measured default path in tests/test_gpu_hetero.py / tests/test_gpu_lightgcn.py."""
+import pytest
+import torch
+
+import laplace_gnn_recommendation_b200 as lg
+from laplace_gnn_recommendation_b200.csr import DeviceCSR
+from oracle import lightgcn_oracle as lo
+from oracle import sampler_oracle as so
+from oracle import topk_oracle as to
+from tests.test_gpu_lightgcn import close, random_graph, test_spmm_vs_oracle as _spmm_vs_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("d", [8, 32, 48, 64])
+@pytest.mark.parametrize("chunk", [256, 8, 40])
+def test_spmm_wide_slice_variant_vs_oracle(cuda_dev, d, chunk):
+    """Variant 16 (one CTA per slice of a long row, opt-in until measured) against the oracle, incl. slices shorter than
+    one 32-entry batch per warp (chunk 8) and slices that leave some of the four warps without work (chunk 40)."""
+    _spmm_vs_oracle(cuda_dev, d, chunk, variant=16)
+
+
+@pytest.mark.parametrize("d", [8, 64, 84, 128, 256])
+def test_spmm_64bit_index_family_vs_oracle(cuda_dev, d):
+    """Variant 17 = the kernels a table with n_cols*d/4 >= 2^31 elements is routed to (64-bit element index)."""
+    _spmm_vs_oracle(cuda_dev, d, 256, variant=17)
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
+    """All 18 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    cp.async rings, sub-warp rows, CTA-wide slices, 64-bit element indexing) compute the same operator with the same fused
+    epilogue: rtol 1e-5 against the default."""
+    row, col = random_graph(d + 1, n, n, nnz, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
+    _, val = g.gcn_norm()
+    g = g.with_values(val)
+    gen = torch.Generator().manual_seed(d)
+    X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
+    outs = {}
+    for variant in range(18):
+        Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
+        g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
+        outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
+    for v in range(1, 18):
+        for a, b in zip(outs[0], outs[v]):
+            close(a, b, rtol=1e-5, atol=1e-5)
+
+# ------------------------------------------------------------------ evaluation() (run_pipeline_lightgcn.py:20-73)
+def test_evaluation_matches_oracle(cuda_dev):
+    gen = torch.Generator().manual_seed(21)
+    U, I, d, K, k, lam = 60, 40, 32, 2, 5, 1e-4
+    E = 300
+    ei = torch.stack([torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)])
+    excl = torch.stack([torch.randint(0, U, (200,), generator=gen), torch.randint(0, I, (200,), generator=gen)])
+    row, col, n = lo.wiring_reference(ei[0], ei[1], U, I)
+    torch.manual_seed(3)
+    model = lg.LightGCN(U, I, d, K)
+    Wu, Wi = model.users_emb.weight.detach().clone(), model.items_emb.weight.detach().clone()
+    model = model.to(cuda_dev).eval()
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(n, n)).to(cuda_dev)
+    torch.manual_seed(77)
+    loss, recall, precision, ndcg = lg.evaluation(model, ei.to(cuda_dev), adj, [excl.to(cuda_dev)], k, lam)
+    # oracle: same CPU RNG stream for the negatives, forward + bpr over every edge, per-user top-k loop
+    torch.manual_seed(77)
+    u, p, neg = so.structured_negative_sampling(ei, num_nodes=torch.max(ei[1]), contains_neg_self_loops=False)
+    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+    u_f, u_0, i_f, i_0 = lo.lightgcn_forward(Wu, Wi, rowptr, c, K)
+    o_loss = lo.bpr_loss(u_f[u], u_0[u], i_f[p], i_0[p], i_f[neg], i_0[neg], lam)
+    o_recall, o_precision, o_ndcg, _ = to.metrics_lightgcn(Wu, Wi, ei, [excl], k)
+    assert loss == pytest.approx(o_loss.item(), rel=1e-5)
+    assert (recall, precision, ndcg) == pytest.approx((o_recall, o_precision, o_ndcg), rel=1e-5)
+
+
+# ------------------------------------------------------------------ fused Adam (run_pipeline_lightgcn.py:103,159,178)
+def test_fused_adam_matches_torch_adam(cuda_dev):
+    """Same trajectory as torch.optim.Adam (CPU, the reference's optimizer) incl. an ExponentialLR decay step."""
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(37, 64), (5, 6), (1000, 32)]
+    ref = [torch.randn(s, generator=gen).requires_grad_(True) for s in shapes]
+    mine = [r.detach().clone().to(cuda_dev).requires_grad_(True) for r in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2)
+    o_mine = lg.FusedAdam(mine, lr=1e-2)
+    s_ref = torch.optim.lr_scheduler.ExponentialLR(o_ref, gamma=0.95)
+    s_mine = torch.optim.lr_scheduler.ExponentialLR(o_mine, gamma=0.95)
+    for it in range(6):
+        grads = [torch.randn(s, generator=gen) * (10.0 ** (it % 3 - 1)) for s in shapes]
+        for r, m, g in zip(ref, mine, grads):
+            r.grad = g.clone(); m.grad = g.to(cuda_dev)
+        o_ref.step(); o_mine.step()
+        if it == 2:
+            s_ref.step(); s_mine.step()
+        for r, m in zip(ref, mine):
+            close(m, r, rtol=1e-5, atol=2e-6)   # per-step update is lr = 1e-2: an ulp or two of the parameter value
+    assert o_mine.param_groups[0]["lr"] == pytest.approx(o_ref.param_groups[0]["lr"])
+
+
+def test_training_loop_with_fused_step_and_fused_adam(cuda_dev):
+    """A few iterations of the reference loop shape (forward, BPR, backward, Adam) with fused_step + FusedAdam follow
+    the oracle loop (autograd + torch.optim.Adam on the CPU)."""
+    gen = torch.Generator().manual_seed(8)
+    U, I, E, d, K, B, lam = 120, 80, 1500, 32, 2, 64, 1e-4
+    users, items = torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)
+    row, col, n = lo.wiring_symmetric(users, items, U, I)
+    torch.manual_seed(1)
+    model = lg.LightGCN(U, I, d, K)
+    Wu = model.users_emb.weight.detach().clone().requires_grad_(True)
+    Wi = model.items_emb.weight.detach().clone().requires_grad_(True)
+    model = model.to(cuda_dev)
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(n, n)).to(cuda_dev)
+    opt = lg.FusedAdam(model.parameters(), lr=5e-3)
+    o_opt = torch.optim.Adam([Wu, Wi], lr=5e-3)
+    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+    for it in range(4):
+        pick = torch.randint(0, E, (B,), generator=gen)
+        ub, pb, nb = users[pick], items[pick], torch.randint(0, I, (B,), generator=gen)
+        loss = model.fused_step(adj, ub.to(cuda_dev), pb.to(cuda_dev), nb.to(cuda_dev), lam)
+        opt.step()
+        o_loss, gu, gi, _, _ = lo.train_iteration(Wu.detach(), Wi.detach(), rowptr, c, K, ub, pb, nb, lam)
+        Wu.grad, Wi.grad = gu, gi
+        o_opt.step()
+        close(loss, o_loss, rtol=1e-5)
+        # Adam turns a gradient element g into a step lr*g/(|g|+eps): where |g| ~ eps = 1e-8 an fp32-rounding-sized change
+        # of g moves the step by a visible fraction of lr, so allow 0.1 % of lr per element on top of rtol
+        close(model.users_emb.weight, Wu, rtol=1e-4, atol=5e-6)
+        close(model.items_emb.weight, Wi, rtol=1e-4, atol=5e-6)
+
+
+def test_ranking_metrics_on_device_match_reference_golden(cuda_dev):
+    """get_metrics_universal on device tensors (what training.py's test loop hands over) against the real reference's
+    numbers (tests/golden/make_golden_ranking.py)."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "reference_golden_ranking.pt")
+    for c in torch.load(path, weights_only=False)["universal"]:
+        got = lg.get_metrics_universal(c["infer_out"].to(cuda_dev), c["edge_index"].to(cuda_dev), c["edge_label_index"].to(cuda_dev),
+                                       [e.to(cuda_dev) for e in c["exclude"]], c["k"])
+        assert got == pytest.approx((c["recall"], c["precision"], c["ndcg"]), rel=1e-6, abs=1e-7)
