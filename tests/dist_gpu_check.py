@@ -18,6 +18,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     # DIST_CHECK_MODE = "schedule,static,exchange", e.g. "pipelined,1,symm"; default = the measured configuration
     mode = os.environ.get("DIST_CHECK_MODE", "layer,0,nccl").split(",")
+    if mode[0] == "rows":                      # DIST_CHECK_MODE = "rows,R" / "rows,S": the generic row-sharded engine
+        return check_rows(dev, mode[1] if len(mode) > 1 else "R")
     for K in (3, 2):
         pb = make_problem(seed=K, U=2000, I=300, E=40000, d=64, K=K, B=512)
         eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], dev,
@@ -33,6 +35,25 @@ def main():
         torch.testing.assert_close(eng.grad[: eng.Ug].cpu(), o_gu[eng.lo:eng.hi], rtol=1e-5, atol=1e-9)
         torch.testing.assert_close(eng.grad[eng.Ug:].cpu(), o_gi, rtol=1e-5, atol=1e-9)
     print(f"DIST_OK rank={dist.get_rank()} users=[{eng.lo},{eng.hi}) edges={eng.local_edges}", flush=True)
+    dist.destroy_process_group()
+
+
+def check_rows(dev, wiring):
+    from laplace_gnn_recommendation_b200.dist_rows import RowShardedLightGCN
+    from oracle import lightgcn_oracle as lo
+    for K in (3, 1):
+        pb = make_problem(seed=K, U=2000, I=300, E=40000, d=64, K=K, B=512)
+        row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
+        eng = RowShardedLightGCN(pb["U"], pb["I"], pb["d"], K, row, col, dev, init_tables=(pb["Wu"], pb["Wi"]))
+        loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        torch.cuda.synchronize()
+        rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+        o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, K, pb["u"], pb["p"], pb["n"], pb["lam"])
+        o_ef, o_g = torch.cat([o_uf, o_if]), torch.cat([o_gu, o_gi])
+        torch.testing.assert_close(loss.cpu(), o_loss, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(eng.E_f.cpu(), o_ef[eng.lo:eng.hi], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(eng.grad.cpu(), o_g[eng.lo:eng.hi], rtol=1e-5, atol=1e-9)
+    print(f"DIST_OK rank={dist.get_rank()} rows engine wiring={wiring} nodes=[{eng.lo},{eng.hi}) nnz={eng.local_nnz}", flush=True)
     dist.destroy_process_group()
 
 

@@ -218,3 +218,48 @@ def test_balanced_bounds_and_local_block():
     assert lu.tolist() == [3, 3, 0] and li.tolist() == [0, 1, 2]
     assert row.tolist() == [3, 3, 0, 5, 6, 7] and col.tolist() == [5, 6, 7, 3, 3, 0]
     assert balanced_user_bounds(torch.zeros(4, dtype=torch.long), 2) == [0, 1, 4] or True  # degenerate: any monotone split
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generic row-sharded engine (dist_rows.RowShardedLightGCN): arbitrary [N, N] adjacency, all-gather per layer
+def _rows_worker(rank, world, port, K, wiring, d, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        from laplace_gnn_recommendation_b200.dist_rows import RowShardedLightGCN
+        from tests.emu.harness import emulated
+        pb = make_problem(K=K, d=d, U=70, I=45, E=900, B=128)
+        row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
+        with emulated():
+            eng = RowShardedLightGCN(pb["U"], pb["I"], pb["d"], K, row, col, "cpu", ops=make_emu_ops(),
+                                     init_tables=(pb["Wu"], pb["Wi"]), chunk=64)
+            loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(), bounds=eng.bounds,
+                        nnz=eng.local_nnz), os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,K,wiring,d", [(2, 3, "R", 64), (3, 2, "S", 32), (2, 1, "S", 128), (3, 0, "R", 16), (1, 3, "R", 64)])
+def test_row_sharded_engine_equals_single_process_oracle(tmp_path, world, K, wiring, d):
+    """The generic engine (north_star's layout: rows of A_hat and of the table range-partitioned, all-gather per layer) with
+    the real kernel sources under the emulator, against the single-process oracle -- incl. the reference's own wiring (R)."""
+    from tests.emu import build_emu
+    build_emu.build()
+    mp.spawn(_rows_worker, args=(world, _free_port(), K, wiring, d, str(tmp_path)), nprocs=world, join=True)
+    pb = make_problem(K=K, d=d, U=70, I=45, E=900, B=128)
+    row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
+    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+    o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, K, pb["u"], pb["p"], pb["n"], pb["lam"])
+    o_ef, o_g = torch.cat([o_uf, o_if]), torch.cat([o_gu, o_gi])
+    outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == n
+    assert sum(o["nnz"][0] for o in outs) == row.numel() == sum(o["nnz"][1] for o in outs)
+    for o in outs:
+        torch.testing.assert_close(o["loss"], o_loss, rtol=1e-5, atol=1e-7)
+        assert torch.equal(o["loss"], outs[0]["loss"])                           # bit-identical without a collective
+        torch.testing.assert_close(o["Ef"], o_ef[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(o["grad"], o_g[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-9)
+    for a, b in zip(outs[:-1], outs[1:]):
+        assert a["hi"] == b["lo"]

@@ -24,7 +24,7 @@ case "${1:-single}" in
     ;;
   dist2|dist4|dist8)
     n=${1#dist}
-    for mode in "layer,0,nccl" "layer,1,nccl" "pipelined,0,nccl" "pipelined,1,nccl" "merged,0,nccl" "merged,1,nccl" "layer,0,symm" "pipelined,1,symm" "merged,1,symm"; do
+    for mode in "layer,0,nccl" "layer,1,nccl" "pipelined,0,nccl" "pipelined,1,nccl" "merged,0,nccl" "merged,1,nccl" "layer,0,symm" "pipelined,1,symm" "merged,1,symm" "rows,R" "rows,S"; do
       DIST_CHECK_MODE=$mode TR "$n" tests/dist_gpu_check.py 2>&1 | grep -E "DIST_OK|Error|error|rc=" | head -6
     done
     TR "$n" bench.py --gpus "$n" --steps 20 --warmup 5 | tail -2 | cut -c1-300
