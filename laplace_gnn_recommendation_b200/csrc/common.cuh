@@ -61,6 +61,8 @@ __device__ __forceinline__ float4 ld_gather_f4(const float4* p) {
                : "l"(p));
   return v;
 }
+// Ask L2 for a line that will be read later in this thread's dependent chain (no register, no scoreboard entry).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Streaming 128-bit store (written once, read by a later kernel).
 __device__ __forceinline__ void st_f4(float4* p, const float4& v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

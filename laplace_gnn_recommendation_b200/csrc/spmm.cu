@@ -355,7 +355,10 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
 // the slice cuts that chain by SPMM_WARPS without more registers, more partial rows or more long rows.
 constexpr int SUBW_MAX = 64;
 
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0>
+// PF (variant 18, measurement pending): shortens the dependent chain of a short row by two memory round trips -- the
+// epilogue operands (acc_in / resid rows, streamed from DRAM) are requested into L2 as soon as the row id is known, and the
+// second batch of (col,val) pairs of rows with more than G entries is loaded before the first batch is consumed.
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
   static_assert(G % UNROLL == 0, "the unrolled gather step must divide the lane-group width");
   static_assert(D4C == 0 || D4C == G, "a compile-time d/4 must fill the lane group exactly");
@@ -410,6 +413,11 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   int deg = e - s;
   const bool is_long = p.chunk > 0 && deg > p.chunk;   // handled by its slices + stage 2
   if (is_long) { deg = 0; }
+  if (PF && r >= 0 && (lig & 7) == 0 && lig < d4 && !(p.y_tail && r >= p.split_row)) {   // one request per 128-byte line
+    const size_t o = (size_t)r * d4 + lig;
+    if (p.acc_in) prefetch_l2(reinterpret_cast<const float4*>(p.acc_in) + o);
+    if (p.resid) prefetch_l2(reinterpret_cast<const float4*>(p.resid) + o);
+  }
   const bool all_short = __all_sync(FULL_MASK, deg <= SUBW_MAX);
 
   if (all_short) {
@@ -419,13 +427,25 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     float4 acc = f4_zero();
     const uint32_t d4u = (uint32_t)d4;
     const bool col_ok = lig < d4;
+    int c = 0, cn = 0;
+    float wv = 0.f, wn = 0.f;
+    if (PF && lig < deg) {                         // batch 0 of the (col,val) pairs
+      c = ld_stream_i32(p.colidx + s + lig);
+      wv = p.val ? ld_stream_f32(p.val + s + lig) : 1.f;
+    }
     for (int base = 0; base < maxdeg; base += G) {
-      const int idx = s + base + lig;
-      int c = 0;
-      float wv = 0.f;
-      if (base + lig < deg) {
-        c = ld_stream_i32(p.colidx + idx);
-        wv = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+      if (PF) {                                    // the NEXT batch is requested before this one is consumed
+        cn = 0; wn = 0.f;
+        if (base + G + lig < deg) {
+          cn = ld_stream_i32(p.colidx + s + base + G + lig);
+          wn = p.val ? ld_stream_f32(p.val + s + base + G + lig) : 1.f;
+        }
+      } else {
+        c = 0; wv = 0.f;
+        if (base + lig < deg) {
+          c = ld_stream_i32(p.colidx + s + base + lig);
+          wv = p.val ? ld_stream_f32(p.val + s + base + lig) : 1.f;
+        }
       }
       const int cnt = min(G, deg - base);          // may be <= 0 for the shorter row of the pair
       const int cntmax = min(G, maxdeg - base);
@@ -445,6 +465,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
         for (int u = 0; u < UNROLL; ++u)
           if (ok[u]) f4_fma(acc, ww[u], v[u]);
       }
+      if (PF) { c = cn; wv = wn; }
     }
     if (r >= 0 && !is_long) {
       float4 a1[1] = {acc};
@@ -468,16 +489,17 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0>
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream);
 
 // d/4 == G (d = 64 with G = 16, d = 32 with G = 8) gets the kernel specialised on that constant
-template <int G, int UNROLL, int MINB, bool WIDE = false>
+template <int G, int UNROLL, int MINB, bool WIDE = false, bool PF = false>
 static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
-  return p.d4 == G ? launch_subwarp_impl<G, UNROLL, MINB, WIDE, G>(p, stream) : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0>(p, stream);
+  return p.d4 == G ? launch_subwarp_impl<G, UNROLL, MINB, WIDE, G, PF>(p, stream)
+                   : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0, PF>(p, stream);
 }
 
-template <int G, int UNROLL, int MINB, bool WIDE, int D4C>
+template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   constexpr int NG = 32 / G;
   const int64_t row_warps = (p.n_rows + NG - 1) / NG;
@@ -485,7 +507,7 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   if (warps > 0) {
     const int64_t blocks = WIDE ? p.n_tasks + (row_warps + SPMM_WARPS - 1) / SPMM_WARPS : (warps + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
@@ -855,6 +877,8 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   if (d4 <= 8) {
     if (variant == 1) return launch_vec<8, 1, 2, 16>(p, 1, stream);
     if (variant == 16) return launch_subwarp<8, 2, 16, true>(p, stream);
+    if (variant == 18) return launch_subwarp<8, 2, 16, false, true>(p, stream);
+    if (variant == 19) return launch_subwarp<8, 2, 16, true, true>(p, stream);
     return launch_subwarp<8, 2, 16>(p, stream);
   }
   if (d4 <= 16) {
@@ -876,6 +900,8 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
       case 14: return launch_subwarp<16, 4, 10>(p, stream);
       case 15: return launch_subwarp<16, 8, 8>(p, stream);
       case 16: return launch_subwarp<16, 2, 16, true>(p, stream);   // sub-warp rows + one CTA per slice (measurement pending)
+      case 18: return launch_subwarp<16, 2, 16, false, true>(p, stream);   // sub-warp rows + chain-shortening prefetches
+      case 19: return launch_subwarp<16, 2, 16, true, true>(p, stream);    // 16 + 18
       default: return launch_subwarp<16, 2, 16>(p, stream);
     }
   }

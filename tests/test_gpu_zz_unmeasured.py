@@ -20,8 +20,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("chunk", [256, 8, 40])
 def test_spmm_wide_slice_variant_vs_oracle(cuda_dev, d, chunk):
     """Variant 16 (one CTA per slice of a long row, opt-in until measured) against the oracle, incl. slices shorter than
-    one 32-entry batch per warp (chunk 8) and slices that leave some of the four warps without work (chunk 40)."""
+    one 32-entry batch per warp (chunk 8) and slices that leave some of the four warps without work (chunk 40); variant 19
+    adds the chain-shortening prefetches of variant 18 on top."""
     _spmm_vs_oracle(cuda_dev, d, chunk, variant=16)
+    _spmm_vs_oracle(cuda_dev, d, chunk, variant=19)
 
 
 @pytest.mark.parametrize("d", [8, 64, 84, 128, 256])
@@ -31,7 +33,7 @@ def test_spmm_64bit_index_family_vs_oracle(cuda_dev, d):
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
-    """All 18 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    """All 20 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
     cp.async rings, sub-warp rows, CTA-wide slices, 64-bit element indexing) compute the same operator with the same fused
     epilogue: rtol 1e-5 against the default."""
     row, col = random_graph(d + 1, n, n, nnz, skew=True)
@@ -41,11 +43,11 @@ def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
     gen = torch.Generator().manual_seed(d)
     X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
     outs = {}
-    for variant in range(18):
+    for variant in range(20):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
-    for v in range(1, 18):
+    for v in range(1, 20):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
