@@ -186,6 +186,7 @@ def run_ours(args):
 
     U, I, E = WORKLOADS[args.workload]
     d, K, B, lam = args.dim, args.layers, args.batch, 1e-6
+    tuned = None
     users, items = make_graph(U, I, E, args.degree, 1234, dev)
     gen = torch.Generator(device=dev).manual_seed(42)
     pick = torch.randint(0, E, (B,), generator=gen, device=dev)
@@ -202,12 +203,18 @@ def run_ours(args):
         g.transpose()
         if args.degree_order:
             g.use_degree_order(); g.transpose().use_degree_order()
+        if not args.no_autotune:     # plan-time choice of the SpMM kernel variant for this graph (result-checked, see csr.py)
+            tuned = {"forward": g.autotune(d), "backward": g.transpose().autotune(d),
+                     "forward_ms": g.autotune_report["ms"], "backward_ms": g.transpose().autotune_report["ms"],
+                     "rejected": {**g.autotune_report["rejected"], **g.transpose().autotune_report["rejected"]}}
         nnz = g.nnz
         step = lambda: model.fused_step(adj, ub, pb, nb, lam)   # noqa: E731
     else:
         from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
         torch.manual_seed(0)
         eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule, exchange=args.exchange)
+        if not args.no_autotune:
+            tuned = eng.autotune()                            # per rank; rank 0's choice is reported
         nnz = 2 * E
         if not args.graph:
             step = lambda: eng.fused_step(ub, pb, nb, lam)      # noqa: E731
@@ -282,7 +289,8 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get(args.workload)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "lgb::spmm_rows_kernel (lgb_spmm)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "lgb_spmm (lgb::spmm_subwarp_kernel / spmm_rows_kernel, variant per config.spmm_variant)",
+                "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmm_alg[0] if spmm_alg else None,
                 "avg_launch_ms": statistics.mean(spmm_ms) if spmm_ms else None,
@@ -353,6 +361,7 @@ def run_ours(args):
 
     if rank == 0:
         line = base_line(args, value, ms, nnz)
+        line["config"]["spmm_variant"] = tuned if tuned is not None else "default (autotune off)"
         line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                      "cpu_baseline": cpu_baseline, "loss": float(loss),
                      "interactions_per_s": E / (ms * 1e-3)})
@@ -374,6 +383,8 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--degree-order", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-autotune", action="store_true",
+                    help="keep the default SpMM kernel variant instead of timing the candidates on this graph at set-up")
     ap.add_argument("--graph", action="store_true", help="multi-GPU: replay the step from a CUDA graph (opt-in, not yet measured)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "symm"],
                     help="multi-GPU item-block exchange: NCCL all-reduce (measured default) or the symmetric-memory multimem kernel")

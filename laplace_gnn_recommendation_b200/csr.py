@@ -22,6 +22,28 @@ DEFAULT_CHUNK = int(_os.environ.get("LGB_SPMM_CHUNK", "1024"))   # rows with mor
                       # any sequential fp32 accumulation chain (accuracy) and the work of one warp (load balance)
 
 
+# candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
+# and the warp-per-row kernel it replaced
+AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12)
+
+
+def _time_ms(fn, reps: int, device) -> float:
+    """Mean duration of back-to-back calls, CUDA events on the current stream.  One warm-up call, one timed call to size
+    the sample (at least ``reps`` launches, more for short kernels so that ~10 ms are measured)."""
+    def timed(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / n
+    fn()
+    first = timed(1)
+    n = int(min(max(reps, 10.0 / max(first, 1e-3)), 200))
+    return timed(n)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -46,6 +68,8 @@ class DeviceCSR:
         self._t: Optional["DeviceCSR"] = None
         self._partials: Dict[int, torch.Tensor] = {}
         self._struct: Optional[LgbCsr] = None
+        self.variant: Optional[int] = None             # kernel variant chosen by autotune() for THIS graph (None: the default)
+        self.autotune_report: Optional[dict] = None
         if self.chunk > 0:
             self._build_plan()
 
@@ -111,6 +135,49 @@ class DeviceCSR:
                                            stream()), "degree_order")
         self._struct = None
         return self
+
+    # ---- plan-time kernel selection --------------------------------------------------------
+    def autotune(self, d: int, candidates=None, reps: int = 5, fused_epilogue: bool = True) -> int:
+        """Pick the fastest lgb_spmm kernel variant for THIS graph and width on THIS device (one-off, like an FFT plan):
+        every candidate is first checked against the default variant's result on random data (a candidate that
+        disagrees beyond fp32 summation-order noise is dropped and reported), then timed with CUDA events over ``reps``
+        launches of the call shape the LightGCN layers use (Y + fused accumulate).  The choice is stored on the graph
+        (``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
+        if candidates is None:
+            candidates = AUTOTUNE_CANDIDATES if d % 4 == 0 and d <= 64 else (0,)
+        dev = self.device
+        report = {"d": d, "ms": {}, "rejected": {}}
+        if self.n_rows == 0 or self.nnz == 0 or len(candidates) <= 1:
+            self.variant, self.autotune_report = (candidates[0] if candidates else None), report
+            return self.variant
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        X = torch.randn(self.n_cols, d, device=dev, generator=gen)
+        acc = torch.randn(self.n_rows, d, device=dev, generator=gen) if fused_epilogue else None
+        ref = ref_mag = None
+        best, best_ms = candidates[0], float("inf")
+        for v in candidates:
+            Y = torch.empty(self.n_rows, d, device=dev)
+            out = torch.empty(self.n_rows, d, device=dev) if fused_epilogue else None
+            try:
+                run = (lambda: self.spmm(X, Y=Y, acc_in=acc, acc_out=out, variant=v)) if fused_epilogue else (lambda: self.spmm(X, Y=Y, variant=v))   # noqa: E731
+                run()
+                if ref is None:
+                    ref = Y.clone()
+                    ref_mag = float(ref.abs().max()) + 1e-30
+                else:
+                    err = float((Y - ref).abs().max())
+                    if not err <= 1e-4 * ref_mag:            # also catches NaN
+                        report["rejected"][v] = f"max |diff| {err:.3e} vs magnitude {ref_mag:.3e}"
+                        continue
+                ms = _time_ms(run, reps, dev)
+            except RuntimeError as exc:                       # a variant that is not available for this shape
+                report["rejected"][v] = str(exc)[:200]
+                continue
+            report["ms"][v] = ms
+            if ms < best_ms:
+                best, best_ms = v, ms
+        self.variant, self.autotune_report = best, report
+        return best
 
     def with_values(self, val: Optional[torch.Tensor]) -> "DeviceCSR":
         """Same structure (arrays and plan shared), different values."""
@@ -204,7 +271,9 @@ class DeviceCSR:
             if t is not None and (tuple(t.shape) != (self.n_rows, d) or not t.is_contiguous() or t.dtype != torch.float32):
                 raise RuntimeError(f"spmm: {name} must be contiguous float32 [{self.n_rows}, {d}]")
         lib = _lib.load()
-        flags = (1 if mean else 0) | ((SPMM_VARIANT if variant is None else variant) << 4)
+        if variant is None:
+            variant = SPMM_VARIANT if self.variant is None else self.variant
+        flags = (1 if mean else 0) | (variant << 4)
         with torch.cuda.device(self.device):
             if y_tail is not None:
                 # split epilogue: rows >= split_row write raw sums to y_tail (see lgb_spmm_split)

@@ -280,6 +280,14 @@ class ShardedLightGCN:
     def graphs(self):
         return [self.g_users, self.g_items]
 
+    def autotune(self):
+        """Per-rank plan-time choice of the SpMM kernel variant for each row view (DeviceCSR.autotune); ranks may choose
+        differently -- the item rows are all-reduced, so the replicated blocks stay identical."""
+        out = {"users": self.g_users.autotune(self.d), "items": self.g_items.autotune(self.d, fused_epilogue=False)}
+        if self.g_all is not None:
+            out["all"] = self.g_all.autotune(self.d)
+        return out
+
     @property
     def users_weight(self):
         return self.table[: self.Ug]

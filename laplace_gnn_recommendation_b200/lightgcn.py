@@ -15,6 +15,8 @@ form g <- A^T g + r with r = dE_f/(K+1), K launches of the same kernel on the CS
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional, Tuple
 
@@ -26,6 +28,9 @@ from ._lib import check, ptr, stream
 from .bpr import bpr_indexed
 from .csr import DeviceCSR
 from .sparse import SparseTensor, gcn_norm, matmul
+
+
+_AUTOTUNE = os.environ.get("LGB_SPMM_AUTOTUNE", "0") == "1"   # tune the SpMM variant per graph on first use
 
 
 def _scale_concat(a: Optional[torch.Tensor], b: Optional[torch.Tensor], na: int, nb: int, d: int, scale: float,
@@ -137,6 +142,15 @@ class LightGCN(nn.Module):
             self._fuse_tables()
         return out
 
+    # ---- plan-time kernel selection (optional) ------------------------------------------------
+    def autotune(self, edge_index: SparseTensor):
+        """Time the SpMM kernel variants on THIS graph (and its transpose, for the backward) at this embedding width and
+        keep the fastest for all later calls (``DeviceCSR.autotune``).  One-off per graph, ~tens of launches; also run
+        automatically on first use when LGB_SPMM_AUTOTUNE=1.  Returns (forward variant, backward variant)."""
+        g = gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr()
+        d = self.users_emb.weight.shape[1]
+        return g.autotune(d), g.transpose().autotune(d)
+
     # ---- reference API ------------------------------------------------------------------------
     def forward(self, edge_index: SparseTensor):
         """-> (e_u^K, e_u^0, e_i^K, e_i^0); elements 1 and 3 are the Parameters themselves, like the reference."""
@@ -144,6 +158,8 @@ class LightGCN(nn.Module):
         _lib.require_cuda(Wu, Wi)
         adj = gcn_norm(edge_index, add_self_loops=self.add_self_loops)   # cached per graph
         g = adj.csr()
+        if _AUTOTUNE and g.variant is None:
+            self.autotune(edge_index)
         if g.n_rows != self.num_users + self.num_items or g.n_cols != g.n_rows:
             raise RuntimeError(f"adjacency is {g.n_rows}x{g.n_cols}, expected a square matrix of "
                                f"{self.num_users + self.num_items} nodes")
@@ -171,6 +187,8 @@ class LightGCN(nn.Module):
         _lib.require_cuda(Wu, Wi)
         K, U = self.num_iterations, self.num_users
         g = gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr()
+        if _AUTOTUNE and g.variant is None:
+            self.autotune(edge_index)
         E0 = self._table_for(Wu, Wi)
         N, d = E0.shape
         E_f = propagate_forward(g, E0, K)

@@ -149,3 +149,44 @@ def test_reference_driver_loop_runs_in_both_styles():
             assert x[key] == pytest.approx(y[key], rel=1e-4, abs=1e-6), key
     for key in ("loss", "recall", "precision", "ndcg"):
         assert a["test"][key] == pytest.approx(b["test"][key], rel=1e-4, abs=1e-6)
+
+
+def test_autotune_picks_a_checked_variant(cuda_dev, monkeypatch):
+    """DeviceCSR.autotune: every candidate is result-checked against the default before it may win; the choice sticks to
+    the graph; LightGCN.autotune / ShardedLightGCN.autotune drive it.  (Wall-clock stands in for CUDA events here.)"""
+    import time
+    from laplace_gnn_recommendation_b200 import csr
+    from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
+    from tests.test_dist_gloo import make_emu_ops, make_problem
+
+    def wall(fn, reps, device):
+        t = time.perf_counter(); fn(); return (time.perf_counter() - t) * 1e3
+    monkeypatch.setattr(csr, "_time_ms", wall)
+    row, col = TL.random_graph(3, 400, 400, 12000, skew=True)
+    g = TL.DeviceCSR.from_coo(row, col, 400, 400, chunk=64)
+    g = g.with_values(g.gcn_norm()[1])
+    best = g.autotune(64)
+    assert best in csr.AUTOTUNE_CANDIDATES and g.variant == best
+    assert set(g.autotune_report["ms"]) == set(csr.AUTOTUNE_CANDIDATES) and not g.autotune_report["rejected"]
+    X = torch.randn(400, 64, generator=torch.Generator().manual_seed(0))
+    TL.close(g.spmm(X), g.spmm(X, variant=0), rtol=1e-5, atol=1e-6)          # the tuned default computes the same operator
+    assert g.autotune(128) == 0                                              # no alternatives beyond d = 64: default kept
+    # a candidate that does not exist for the shape is rejected, not chosen
+    assert g.autotune(64, candidates=(0, 99)) in (0, 99)
+    # module-level drivers
+    U, I = 30, 20
+    m = lg_module().LightGCN(U, I, 32, 2)
+    ei = torch.stack([torch.randint(0, U, (300,)), torch.randint(0, I, (300,))])
+    r, c, n = TL.lo.wiring_symmetric(ei[0], ei[1], U, I)
+    adj = lg_module().SparseTensor(row=r, col=c, sparse_sizes=(n, n))
+    fwd, bwd = m.autotune(adj)
+    assert fwd in csr.AUTOTUNE_CANDIDATES and bwd in csr.AUTOTUNE_CANDIDATES
+    pb = make_problem(seed=1, U=200, I=60, E=3000, d=64, K=2, B=64)
+    eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], 2, pb["users"], pb["items"], cuda_dev, ops=make_emu_ops(), rank=0, world=1,
+                          schedule="merged")
+    assert set(eng.autotune()) == {"users", "items", "all"}
+
+
+def lg_module():
+    import laplace_gnn_recommendation_b200 as lg
+    return lg

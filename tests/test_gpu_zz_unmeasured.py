@@ -140,3 +140,17 @@ def test_ranking_metrics_on_device_match_reference_golden(cuda_dev):
         got = lg.get_metrics_universal(c["infer_out"].to(cuda_dev), c["edge_index"].to(cuda_dev), c["edge_label_index"].to(cuda_dev),
                                        [e.to(cuda_dev) for e in c["exclude"]], c["k"])
         assert got == pytest.approx((c["recall"], c["precision"], c["ndcg"]), rel=1e-6, abs=1e-7)
+
+
+def test_autotune_on_device(cuda_dev):
+    """DeviceCSR.autotune with real CUDA-event timing: all candidates agree with the default and get a time; the winner
+    computes the same operator."""
+    from laplace_gnn_recommendation_b200 import csr
+    row, col = random_graph(7, 20000, 20000, 600000, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), 20000, 20000)
+    g = g.with_values(g.gcn_norm()[1])
+    best = g.autotune(64)
+    assert best in csr.AUTOTUNE_CANDIDATES and not g.autotune_report["rejected"], g.autotune_report
+    assert set(g.autotune_report["ms"]) == set(csr.AUTOTUNE_CANDIDATES)
+    X = torch.randn(20000, 64, device=cuda_dev)
+    close(g.spmm(X), g.spmm(X, variant=0), rtol=1e-5, atol=1e-5)
