@@ -69,7 +69,9 @@ def both_indexes_from_zero(edge_index: torch.Tensor) -> torch.Tensor:
 def split(edge_index: torch.Tensor):
     """80/10/10 edge split, sklearn ``train_test_split`` with random_state=1 twice (data/lightgcn_loader.py:13-31):
     the same index permutation as the reference, hence bit-identical splits."""
-    from sklearn.model_selection import train_test_split
+    state = random.getstate()      # importing sklearn for the first time draws from Python's global `random`: the reference
+    from sklearn.model_selection import train_test_split   # imports it at module load, i.e. BEFORE the caller seeds, so the
+    random.setstate(state)         # lazy import here must not move the stream that sample_mini_batch's random.choices uses
     n = edge_index.shape[1]
     train_idx, rest = train_test_split(list(range(n)), test_size=0.2, random_state=1)
     val_idx, test_idx = train_test_split(rest, test_size=0.5, random_state=1)

@@ -137,25 +137,28 @@ def make_emu_ops(lazy: bool = True):
     return EmuOps(torch.device("cpu"))
 
 
-def _worker(rank, world, port, K, out_dir, schedule="layer", static_batch=False, ops_kind="oracle", d=16):
+def _worker(rank, world, port, cases, out_dir):
+    """One rank of a gloo group: runs every case (K, schedule, static_batch, ops_kind, d) in turn -- one process start-up
+    per world size instead of one per case."""
     import contextlib
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
-        pb = make_problem(K=K, d=d)
-        if ops_kind == "emu":
-            from tests.emu.harness import emulated
-            ctx = emulated()
-        else:
-            ctx = contextlib.nullcontext()
-        with ctx:
-            ops = make_emu_ops() if ops_kind == "emu" else CpuOracleOps()
-            eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=ops,
-                                  init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
-            loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
-        torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(),
-                        bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"rank{rank}.pt"))
+        for ci, (K, schedule, static_batch, ops_kind, d) in enumerate(cases):
+            pb = make_problem(K=K, d=d)
+            if ops_kind == "emu":
+                from tests.emu.harness import emulated
+                ctx = emulated()
+            else:
+                ctx = contextlib.nullcontext()
+            with ctx:
+                ops = make_emu_ops() if ops_kind == "emu" else CpuOracleOps()
+                eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=ops,
+                                      init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
+                loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+            torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(),
+                            bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -166,43 +169,45 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,K,schedule,static_batch", [(2, 3, "layer", False), (3, 2, "layer", False), (2, 1, "layer", True),
-                                                           (2, 3, "pipelined", True), (3, 2, "pipelined", False),
-                                                           (2, 3, "merged", True), (3, 2, "merged", False), (2, 1, "merged", False),
-                                                           (2, 1, "pipelined", True)])
-def test_sharded_step_equals_single_process_oracle(tmp_path, world, K, schedule, static_batch):
-    _run_and_check(tmp_path, world, K, schedule, static_batch, "oracle", 16)
+# (K, schedule, static_batch, ops_kind, d).  "oracle": the kernels are the CPU oracle (host logic only); "emu": dist.CudaOps
+# drives the REAL kernel sources under the CPU emulator (tests/emu/) -- covers lgb_spmm_split, the BPR owned-user filter /
+# B_norm and the row views under every schedule without a GPU, with lazy all-reduce handles (see make_emu_ops).
+CASES = {
+    2: [(3, "layer", False, "oracle", 16), (1, "layer", True, "oracle", 16), (3, "pipelined", True, "oracle", 16),
+        (3, "merged", True, "oracle", 16), (1, "merged", False, "oracle", 16), (1, "pipelined", True, "oracle", 16),
+        (3, "layer", False, "emu", 64), (3, "merged", True, "emu", 64), (2, "merged", False, "emu", 32),
+        (3, "pipelined", False, "emu", 64), (0, "layer", True, "emu", 64)],
+    3: [(2, "layer", False, "oracle", 16), (2, "pipelined", False, "oracle", 16), (2, "merged", False, "oracle", 16),
+        (2, "pipelined", True, "emu", 64), (1, "layer", True, "emu", 128), (2, "merged", True, "emu", 32)],
+}
 
 
-@pytest.mark.parametrize("world,K,schedule,static_batch,d", [(2, 3, "layer", False, 64), (2, 3, "merged", True, 64),
-                                                             (3, 2, "pipelined", True, 64), (2, 2, "merged", False, 32),
-                                                             (3, 1, "layer", True, 128)])
-def test_sharded_step_with_emulated_kernels(tmp_path, world, K, schedule, static_batch, d):
-    """Same check with dist.CudaOps driving the REAL kernel sources (CPU emulation, tests/emu/) instead of the oracle ops:
-    covers lgb_spmm_split, the BPR owned-user filter / B_norm and the row views under every schedule without a GPU."""
-    _run_and_check(tmp_path, world, K, schedule, static_batch, "emu", d)
-
-
-def _run_and_check(tmp_path, world, K, schedule, static_batch, ops_kind, d):
-    if ops_kind == "emu":
-        from tests.emu import build_emu
-        build_emu.build()          # once, in the parent: the spawned ranks only load it
-    mp.spawn(_worker, args=(world, _free_port(), K, str(tmp_path), schedule, static_batch, ops_kind, d), nprocs=world, join=True)
-    pb = make_problem(K=K, d=d)
-    o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
-    outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
-    assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == pb["U"]
-    assert sum(o["local_edges"] for o in outs) == pb["users"].numel()
-    tol = dict(rtol=1e-5, atol=1e-7)
-    for o in outs:
-        Ug = o["hi"] - o["lo"]
-        torch.testing.assert_close(o["loss"], o_loss, **tol)
-        torch.testing.assert_close(o["Ef"][:Ug], o_uf[o["lo"]:o["hi"]], **tol)
-        torch.testing.assert_close(o["Ef"][Ug:], o_if, **tol)                       # replicated item rows
-        torch.testing.assert_close(o["grad"][:Ug], o_gu[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-9)
-        torch.testing.assert_close(o["grad"][Ug:], o_gi, rtol=1e-5, atol=1e-9)      # identical on every rank
-    for a, b in zip(outs[:-1], outs[1:]):
-        assert a["hi"] == b["lo"]
+@pytest.mark.parametrize("world", sorted(CASES))
+def test_sharded_step_equals_single_process_oracle(tmp_path, world):
+    """Every rank's shard of one fused step (loss, E_f, gradients) equals the single-process oracle, for every schedule /
+    static-batch combination, with oracle-backed ops and with the emulated kernels."""
+    from tests.emu import build_emu
+    build_emu.build()          # once, in the parent: the spawned ranks only load it
+    cases = CASES[world]
+    mp.spawn(_worker, args=(world, _free_port(), cases, str(tmp_path)), nprocs=world, join=True)
+    for ci, (K, schedule, static_batch, ops_kind, d) in enumerate(cases):
+        what = f"world={world} K={K} schedule={schedule} static={static_batch} ops={ops_kind} d={d}"
+        pb = make_problem(K=K, d=d)
+        o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
+        outs = [torch.load(tmp_path / f"case{ci}_rank{r}.pt") for r in range(world)]
+        assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == pb["U"], what
+        assert sum(o["local_edges"] for o in outs) == pb["users"].numel(), what
+        tol = dict(rtol=1e-5, atol=1e-7, msg=lambda m: f"{what}: {m}")
+        gtol = dict(rtol=1e-5, atol=1e-9, msg=lambda m: f"{what}: {m}")
+        for o in outs:
+            Ug = o["hi"] - o["lo"]
+            torch.testing.assert_close(o["loss"], o_loss, **tol)
+            torch.testing.assert_close(o["Ef"][:Ug], o_uf[o["lo"]:o["hi"]], **tol)
+            torch.testing.assert_close(o["Ef"][Ug:], o_if, **tol)                       # replicated item rows
+            torch.testing.assert_close(o["grad"][:Ug], o_gu[o["lo"]:o["hi"]], **gtol)
+            torch.testing.assert_close(o["grad"][Ug:], o_gi, **gtol)                    # identical on every rank
+        for a, b in zip(outs[:-1], outs[1:]):
+            assert a["hi"] == b["lo"], what
 
 
 def test_balanced_bounds_and_local_block():
@@ -222,44 +227,50 @@ def test_balanced_bounds_and_local_block():
 
 # ---------------------------------------------------------------------------------------------------------------------
 # generic row-sharded engine (dist_rows.RowShardedLightGCN): arbitrary [N, N] adjacency, all-gather per layer
-def _rows_worker(rank, world, port, K, wiring, d, out_dir):
+def _rows_worker(rank, world, port, cases, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
         from laplace_gnn_recommendation_b200.dist_rows import RowShardedLightGCN
         from tests.emu.harness import emulated
-        pb = make_problem(K=K, d=d, U=70, I=45, E=900, B=128)
-        row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
-        with emulated():
-            eng = RowShardedLightGCN(pb["U"], pb["I"], pb["d"], K, row, col, "cpu", ops=make_emu_ops(),
-                                     init_tables=(pb["Wu"], pb["Wi"]), chunk=64)
-            loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
-        torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(), bounds=eng.bounds,
-                        nnz=eng.local_nnz), os.path.join(out_dir, f"rank{rank}.pt"))
+        for ci, (K, wiring, d) in enumerate(cases):
+            pb = make_problem(K=K, d=d, U=70, I=45, E=900, B=128)
+            row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
+            with emulated():
+                eng = RowShardedLightGCN(pb["U"], pb["I"], pb["d"], K, row, col, "cpu", ops=make_emu_ops(),
+                                         init_tables=(pb["Wu"], pb["Wi"]), chunk=64)
+                loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+            torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(), bounds=eng.bounds,
+                            nnz=eng.local_nnz), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,K,wiring,d", [(2, 3, "R", 64), (3, 2, "S", 32), (2, 1, "S", 128), (3, 0, "R", 16), (1, 3, "R", 64)])
-def test_row_sharded_engine_equals_single_process_oracle(tmp_path, world, K, wiring, d):
+ROWS_CASES = {1: [(3, "R", 64)], 2: [(3, "R", 64), (1, "S", 128)], 3: [(2, "S", 32), (0, "R", 16)]}   # (K, wiring, d)
+
+
+@pytest.mark.parametrize("world", sorted(ROWS_CASES))
+def test_row_sharded_engine_equals_single_process_oracle(tmp_path, world):
     """The generic engine (north_star's layout: rows of A_hat and of the table range-partitioned, all-gather per layer) with
     the real kernel sources under the emulator, against the single-process oracle -- incl. the reference's own wiring (R)."""
     from tests.emu import build_emu
     build_emu.build()
-    mp.spawn(_rows_worker, args=(world, _free_port(), K, wiring, d, str(tmp_path)), nprocs=world, join=True)
-    pb = make_problem(K=K, d=d, U=70, I=45, E=900, B=128)
-    row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
-    rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
-    o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, K, pb["u"], pb["p"], pb["n"], pb["lam"])
-    o_ef, o_g = torch.cat([o_uf, o_if]), torch.cat([o_gu, o_gi])
-    outs = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
-    assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == n
-    assert sum(o["nnz"][0] for o in outs) == row.numel() == sum(o["nnz"][1] for o in outs)
-    for o in outs:
-        torch.testing.assert_close(o["loss"], o_loss, rtol=1e-5, atol=1e-7)
-        assert torch.equal(o["loss"], outs[0]["loss"])                           # bit-identical without a collective
-        torch.testing.assert_close(o["Ef"], o_ef[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-7)
-        torch.testing.assert_close(o["grad"], o_g[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-9)
-    for a, b in zip(outs[:-1], outs[1:]):
-        assert a["hi"] == b["lo"]
+    cases = ROWS_CASES[world]
+    mp.spawn(_rows_worker, args=(world, _free_port(), cases, str(tmp_path)), nprocs=world, join=True)
+    for ci, (K, wiring, d) in enumerate(cases):
+        pb = make_problem(K=K, d=d, U=70, I=45, E=900, B=128)
+        row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(pb["users"], pb["items"], pb["U"], pb["I"])
+        rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
+        o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(pb["Wu"], pb["Wi"], rowptr, c, K, pb["u"], pb["p"], pb["n"], pb["lam"])
+        o_ef, o_g = torch.cat([o_uf, o_if]), torch.cat([o_gu, o_gi])
+        outs = [torch.load(tmp_path / f"case{ci}_rank{r}.pt") for r in range(world)]
+        assert outs[0]["bounds"][0] == 0 and outs[0]["bounds"][-1] == n
+        assert sum(o["nnz"][0] for o in outs) == row.numel() == sum(o["nnz"][1] for o in outs)
+        for o in outs:
+            torch.testing.assert_close(o["loss"], o_loss, rtol=1e-5, atol=1e-7)
+            assert torch.equal(o["loss"], outs[0]["loss"])                           # bit-identical without a collective
+            torch.testing.assert_close(o["Ef"], o_ef[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-7)
+            torch.testing.assert_close(o["grad"], o_g[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-9)
+        for a, b in zip(outs[:-1], outs[1:]):
+            assert a["hi"] == b["lo"]

@@ -92,3 +92,16 @@ def test_ranking_metrics_match_reference_golden():
             users = c["edge_label_index"][0].unique(sorted=True)
             rebatched = lg.hetero.padded_stack([c["scores"][c["edge_label_index"][0] == u] for u in users], value=-(1 << 50))
             assert torch.equal(rebatched, c["infer_out"])
+
+
+def test_split_does_not_disturb_the_python_random_stream():
+    """split() imports sklearn lazily; that import draws from Python's global `random` the first time it happens, which
+    would shift the `random.choices` draws of sample_mini_batch depending on import order.  The reference imports sklearn at
+    module load (before the caller seeds), so the stream must be the same before and after split()."""
+    import random
+    ei = torch.stack([torch.arange(50) % 7, torch.arange(50) % 11])
+    random.seed(123)
+    want = random.random()
+    random.seed(123)
+    lg.split(ei)
+    assert random.random() == want

@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="ml1m", choices=sorted(WORKLOADS))
     ap.add_argument("--iters", type=int, default=200)
-    ap.add_argument("--style", default="reference", choices=["reference", "fused"])
+    ap.add_argument("--style", default="reference", choices=["reference", "fused", "both"])
     ap.add_argument("--batch", type=int, default=128)          # config.py:144
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--layers", type=int, default=3)
@@ -39,6 +39,12 @@ def main():
     ap.add_argument("--eval-every", type=int, default=100)
     ap.add_argument("--lr-decay-every", type=int, default=50)
     a = ap.parse_args()
+    for style in (["reference", "fused"] if a.style == "both" else [a.style]):
+        a.style = style
+        run(a)
+
+
+def run(a):
     dev = _common.device()
     U, I, E = WORKLOADS[a.workload]
     if _common.DRYRUN:
