@@ -204,9 +204,12 @@ def run_ours(args):
         if args.degree_order:
             g.use_degree_order(); g.transpose().use_degree_order()
         if not args.no_autotune:     # plan-time choice of the SpMM kernel variant for this graph (result-checked, see csr.py)
-            tuned = {"forward": g.autotune(d), "backward": g.transpose().autotune(d),
-                     "forward_ms": g.autotune_report["ms"], "backward_ms": g.transpose().autotune_report["ms"],
-                     "rejected": {**g.autotune_report["rejected"], **g.transpose().autotune_report["rejected"]}}
+            gt = g.transpose()
+            g.autotune(d, chunks=(1024, 512), degree_orders=(False, True))
+            gt.autotune(d, chunks=(1024, 512), degree_orders=(False, True))
+            tuned = {"forward": g.autotune_report.get("chosen"), "backward": gt.autotune_report.get("chosen"),
+                     "forward_ms": g.autotune_report["ms"], "backward_ms": gt.autotune_report["ms"],
+                     "rejected": {**g.autotune_report["rejected"], **gt.autotune_report["rejected"]}}
         nnz = g.nnz
         step = lambda: model.fused_step(adj, ub, pb, nb, lam)   # noqa: E731
     else:

@@ -23,8 +23,8 @@ DEFAULT_CHUNK = int(_os.environ.get("LGB_SPMM_CHUNK", "1024"))   # rows with mor
 
 
 # candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
-# and the warp-per-row kernel it replaced
-AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12)
+# the warp-per-row kernel it replaced, and the sub-warp kernel at gather-unroll 4
+AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13)
 
 
 def _time_ms(fn, reps: int, device) -> float:
@@ -137,47 +137,73 @@ class DeviceCSR:
         return self
 
     # ---- plan-time kernel selection --------------------------------------------------------
-    def autotune(self, d: int, candidates=None, reps: int = 5, fused_epilogue: bool = True) -> int:
-        """Pick the fastest lgb_spmm kernel variant for THIS graph and width on THIS device (one-off, like an FFT plan):
-        every candidate is first checked against the default variant's result on random data (a candidate that
-        disagrees beyond fp32 summation-order noise is dropped and reported), then timed with CUDA events over ``reps``
-        launches of the call shape the LightGCN layers use (Y + fused accumulate).  The choice is stored on the graph
-        (``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
+    def autotune(self, d: int, candidates=None, reps: int = 5, fused_epilogue: bool = True, chunks=None,
+                 degree_orders=(False,)) -> int:
+        """Pick the fastest lgb_spmm configuration for THIS graph and width on THIS device (one-off, like an FFT plan):
+        kernel variant x slice size of the long-row plan (``chunks``, default: the current one) x row processing order
+        (``degree_orders``).  Every configuration is first checked against the first one's result on random data (one that
+        disagrees beyond fp32 summation-order noise is dropped and reported), then timed with CUDA events over the call
+        shape the LightGCN layers use (Y + fused accumulate).  The winner is installed on the graph (plan, row order,
+        ``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
         if candidates is None:
             candidates = AUTOTUNE_CANDIDATES if d % 4 == 0 and d <= 64 else (0,)
+        chunks = tuple(chunks) if chunks else (self.chunk,)
+        if self.chunk <= 0:
+            chunks = (self.chunk,)
         dev = self.device
         report = {"d": d, "ms": {}, "rejected": {}}
-        if self.n_rows == 0 or self.nnz == 0 or len(candidates) <= 1:
-            self.variant, self.autotune_report = (candidates[0] if candidates else None), report
+        n_configs = len(candidates) * len(chunks) * len(degree_orders)
+        if self.n_rows == 0 or self.nnz == 0 or n_configs <= 1:
+            self.variant = candidates[0] if candidates else None
+            report["chosen"] = {"variant": self.variant, "chunk": self.chunk, "degree_order": self.row_order is not None}
+            self.autotune_report = report
             return self.variant
         gen = torch.Generator(device=dev).manual_seed(1234)
         X = torch.randn(self.n_cols, d, device=dev, generator=gen)
         acc = torch.randn(self.n_rows, d, device=dev, generator=gen) if fused_epilogue else None
+        Y = torch.empty(self.n_rows, d, device=dev)
+        out = torch.empty(self.n_rows, d, device=dev) if fused_epilogue else None
         ref = ref_mag = None
-        best, best_ms = candidates[0], float("inf")
-        for v in candidates:
-            Y = torch.empty(self.n_rows, d, device=dev)
-            out = torch.empty(self.n_rows, d, device=dev) if fused_epilogue else None
-            try:
-                run = (lambda: self.spmm(X, Y=Y, acc_in=acc, acc_out=out, variant=v)) if fused_epilogue else (lambda: self.spmm(X, Y=Y, variant=v))   # noqa: E731
-                run()
-                if ref is None:
-                    ref = Y.clone()
-                    ref_mag = float(ref.abs().max()) + 1e-30
-                else:
-                    err = float((Y - ref).abs().max())
-                    if not err <= 1e-4 * ref_mag:            # also catches NaN
-                        report["rejected"][v] = f"max |diff| {err:.3e} vs magnitude {ref_mag:.3e}"
+        best, best_ms = (chunks[0], bool(degree_orders[0]), candidates[0]), float("inf")
+        for chunk in chunks:
+            self._set_chunk(chunk)
+            for order in degree_orders:
+                self.use_degree_order(bool(order))
+                for v in candidates:
+                    key = f"v{v}" + (f"/chunk{chunk}" if len(chunks) > 1 else "") + ("/degree-order" if order else "")
+                    try:
+                        run = (lambda: self.spmm(X, Y=Y, acc_in=acc, acc_out=out, variant=v)) if fused_epilogue else (lambda: self.spmm(X, Y=Y, variant=v))   # noqa: E731
+                        run()
+                        if ref is None:
+                            ref = Y.clone()
+                            ref_mag = float(ref.abs().max()) + 1e-30
+                        else:
+                            err = float((Y - ref).abs().max())
+                            if not err <= 1e-4 * ref_mag:            # also catches NaN
+                                report["rejected"][key] = f"max |diff| {err:.3e} vs magnitude {ref_mag:.3e}"
+                                continue
+                        ms = _time_ms(run, reps, dev)
+                    except RuntimeError as exc:                       # a variant that is not available for this shape
+                        report["rejected"][key] = str(exc)[:200]
                         continue
-                ms = _time_ms(run, reps, dev)
-            except RuntimeError as exc:                       # a variant that is not available for this shape
-                report["rejected"][v] = str(exc)[:200]
-                continue
-            report["ms"][v] = ms
-            if ms < best_ms:
-                best, best_ms = v, ms
-        self.variant, self.autotune_report = best, report
-        return best
+                    report["ms"][key] = ms
+                    if ms < best_ms:
+                        best, best_ms = (chunk, bool(order), v), ms
+        self._set_chunk(best[0])
+        self.use_degree_order(best[1])
+        self.variant, self.autotune_report = best[2], report
+        report["chosen"] = {"variant": best[2], "chunk": best[0], "degree_order": best[1]}
+        return self.variant
+
+    def _set_chunk(self, chunk: int) -> None:
+        """Rebuild the long-row plan for another slice size."""
+        if int(chunk) != self.chunk:
+            self.chunk = int(chunk)
+            self.n_long = self.n_tasks = 0
+            self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
+            if self.chunk > 0:
+                self._build_plan()
+            self._struct = None
 
     def with_values(self, val: Optional[torch.Tensor]) -> "DeviceCSR":
         """Same structure (arrays and plan shared), different values."""

@@ -283,9 +283,15 @@ class ShardedLightGCN:
     def autotune(self):
         """Per-rank plan-time choice of the SpMM kernel variant for each row view (DeviceCSR.autotune); ranks may choose
         differently -- the item rows are all-reduced, so the replicated blocks stay identical."""
-        out = {"users": self.g_users.autotune(self.d), "items": self.g_items.autotune(self.d, fused_epilogue=False)}
+        chunks = (DEFAULT_CHUNK, 256)      # a rank's launch is bounded below by one slice's serial chain: try shorter slices
+        views = {"users": (self.g_users, True), "items": (self.g_items, False)}
         if self.g_all is not None:
-            out["all"] = self.g_all.autotune(self.d)
+            views["all"] = (self.g_all, True)
+        out = {}
+        for name, (g, fused) in views.items():
+            g.autotune(self.d, fused_epilogue=fused, chunks=chunks)
+            out[name] = dict(g.autotune_report.get("chosen", {"variant": g.variant}), ms=g.autotune_report["ms"],
+                             rejected=g.autotune_report["rejected"])
         return out
 
     @property

@@ -165,12 +165,17 @@ def test_autotune_picks_a_checked_variant(cuda_dev, monkeypatch):
     g = g.with_values(g.gcn_norm()[1])
     best = g.autotune(64)
     assert best in csr.AUTOTUNE_CANDIDATES and g.variant == best
-    assert set(g.autotune_report["ms"]) == set(csr.AUTOTUNE_CANDIDATES) and not g.autotune_report["rejected"]
+    assert set(g.autotune_report["ms"]) == {f"v{v}" for v in csr.AUTOTUNE_CANDIDATES} and not g.autotune_report["rejected"]
+    # slice size and row order are plan-time dimensions too; the winner's plan is the one left installed
+    g.autotune(64, candidates=(0, 16), chunks=(64, 16), degree_orders=(False, True))
+    ch = g.autotune_report["chosen"]
+    assert len(g.autotune_report["ms"]) == 8 and g.chunk == ch["chunk"] and (g.row_order is not None) == ch["degree_order"]
     X = torch.randn(400, 64, generator=torch.Generator().manual_seed(0))
     TL.close(g.spmm(X), g.spmm(X, variant=0), rtol=1e-5, atol=1e-6)          # the tuned default computes the same operator
     assert g.autotune(128) == 0                                              # no alternatives beyond d = 64: default kept
     # a candidate that does not exist for the shape is rejected, not chosen
     assert g.autotune(64, candidates=(0, 99)) in (0, 99)
+    TL.close(g.spmm(X), g.with_values(g.val).spmm(X, variant=0), rtol=1e-5, atol=1e-6)
     # module-level drivers
     U, I = 30, 20
     m = lg_module().LightGCN(U, I, 32, 2)

@@ -151,6 +151,8 @@ def test_autotune_on_device(cuda_dev):
     g = g.with_values(g.gcn_norm()[1])
     best = g.autotune(64)
     assert best in csr.AUTOTUNE_CANDIDATES and not g.autotune_report["rejected"], g.autotune_report
-    assert set(g.autotune_report["ms"]) == set(csr.AUTOTUNE_CANDIDATES)
+    assert set(g.autotune_report["ms"]) == {f"v{v}" for v in csr.AUTOTUNE_CANDIDATES}
+    g.autotune(64, candidates=(0, 16), chunks=(1024, 256), degree_orders=(False, True))
+    assert len(g.autotune_report["ms"]) == 8 and not g.autotune_report["rejected"], g.autotune_report
     X = torch.randn(20000, 64, device=cuda_dev)
     close(g.spmm(X), g.spmm(X, variant=0), rtol=1e-5, atol=1e-5)
