@@ -205,11 +205,15 @@ def run_ours(args):
             g.use_degree_order(); g.transpose().use_degree_order()
         if not args.no_autotune:     # plan-time choice of the SpMM kernel variant for this graph (result-checked, see csr.py)
             gt = g.transpose()
-            g.autotune(d, chunks=(1024, 512), degree_orders=(False, True))
-            gt.autotune(d, chunks=(1024, 512), degree_orders=(False, True))
-            tuned = {"forward": g.autotune_report.get("chosen"), "backward": gt.autotune_report.get("chosen"),
-                     "forward_ms": g.autotune_report["ms"], "backward_ms": gt.autotune_report["ms"],
-                     "rejected": {**g.autotune_report["rejected"], **gt.autotune_report["rejected"]}}
+            try:
+                g.autotune(d, chunks=(1024, 512), degree_orders=(False, True))
+                gt.autotune(d, chunks=(1024, 512), degree_orders=(False, True))
+                tuned = {"forward": g.autotune_report.get("chosen"), "backward": gt.autotune_report.get("chosen"),
+                         "forward_ms": g.autotune_report["ms"], "backward_ms": gt.autotune_report["ms"],
+                         "rejected": {**g.autotune_report["rejected"], **gt.autotune_report["rejected"]}}
+            except Exception as exc:      # tuning is optional: fall back to the default plan and say so
+                g.variant = gt.variant = None
+                tuned = {"error": repr(exc)[:300]}
         nnz = g.nnz
         step = lambda: model.fused_step(adj, ub, pb, nb, lam)   # noqa: E731
     else:
@@ -217,7 +221,12 @@ def run_ours(args):
         torch.manual_seed(0)
         eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule, exchange=args.exchange)
         if not args.no_autotune:
-            tuned = eng.autotune()                            # per rank; rank 0's choice is reported
+            try:
+                tuned = eng.autotune()                        # per rank; rank 0's choice is reported
+            except Exception as exc:
+                for gv in eng.graphs():
+                    gv.variant = None
+                tuned = {"error": repr(exc)[:300]}
         nnz = 2 * E
         if not args.graph:
             step = lambda: eng.fused_step(ub, pb, nb, lam)      # noqa: E731
