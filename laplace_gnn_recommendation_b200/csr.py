@@ -23,8 +23,9 @@ DEFAULT_CHUNK = int(_os.environ.get("LGB_SPMM_CHUNK", "1024"))   # rows with mor
 
 
 # candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
-# the warp-per-row kernel it replaced, and the sub-warp kernel at gather-unroll 4
-AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13)
+# the warp-per-row kernel it replaced, the sub-warp kernel at gather-unroll 4, and the four-rows-per-warp forms (20, 22:
+# d in 33..64; for d <= 32 those numbers run the default)
+AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13, 20, 22)
 
 
 def _time_ms(fn, reps: int, device) -> float:

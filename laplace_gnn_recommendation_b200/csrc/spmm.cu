@@ -358,10 +358,13 @@ constexpr int SUBW_MAX = 64;
 // PF (variant 18, measurement pending): shortens the dependent chain of a short row by two memory round trips -- the
 // epilogue operands (acc_in / resid rows, streamed from DRAM) are requested into L2 as soon as the row id is known, and the
 // second batch of (col,val) pairs of rows with more than G entries is loaded before the first batch is consumed.
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false>
+// VPL > 1 (variants 20/21, measurement pending): a lane holds VPL float4 of the row, so a row needs only G = d/(4*VPL) lanes
+// and a warp runs 32/G row chains at once (d = 64: G = 8, VPL = 2 -> four rows per warp, half the shuffles and address
+// arithmetic per non-zero).
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
   static_assert(G % UNROLL == 0, "the unrolled gather step must divide the lane-group width");
-  static_assert(D4C == 0 || D4C == G, "a compile-time d/4 must fill the lane group exactly");
+  static_assert(D4C == 0 || D4C == G * VPL, "a compile-time d/4 must fill the lane group exactly");
   constexpr int NG = 32 / G;
   const int lane = threadIdx.x & 31;
   const int grp = lane / G, lig = lane % G;
@@ -370,19 +373,29 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   int64_t w;
   if (WIDE) {
     if ((int64_t)blockIdx.x < p.n_tasks) {   // one CTA per slice
-      __shared__ float4 wsum[SPMM_WARPS][G];
+      __shared__ float4 wsum[SPMM_WARPS][G * VPL];
       const int wi = threadIdx.x >> 5;
       const int64_t t = blockIdx.x;
       const int s = p.task_start[t], e = p.task_end[t];
-      float4 acc[1] = {f4_zero()};
-      accumulate_slice<G, 1, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C>(p, s + 32 * wi, e, lane, acc);
-      if (lane < G) wsum[wi][lane] = acc[0];
-      __syncthreads();
-      if (wi == 0 && lane < G && lane < d4) {
-        float4 sum = wsum[0][lane];
+      float4 acc[VPL];
 #pragma unroll
-        for (int k = 1; k < SPMM_WARPS; ++k) sum = f4_add(sum, wsum[k][lane]);
-        st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)t * d4 + lane, sum);
+      for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
+      accumulate_slice<G, VPL, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C>(p, s + 32 * wi, e, lane, acc);
+      if (lane < G) {
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) wsum[wi][lane + q * G] = acc[q];
+      }
+      __syncthreads();
+      if (wi == 0 && lane < G) {
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+          const int f = lane + q * G;
+          if (f >= d4) continue;
+          float4 sum = wsum[0][f];
+#pragma unroll
+          for (int k = 1; k < SPMM_WARPS; ++k) sum = f4_add(sum, wsum[k][f]);
+          st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)t * d4 + f, sum);
+        }
       }
       return;
     }
@@ -392,12 +405,18 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   }
 
   if (!WIDE && w < p.n_tasks) {   // slices of long rows: whole warp, partial sums
-    float4 acc[1] = {f4_zero()};
-    const int r = p.task_row[w];
-    (void)r;
+    float4 acc[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
     const int s = p.task_start[w], e = p.task_end[w];
-    accumulate_slice<G, 1, UNROLL, 32, uint32_t, D4C>(p, s, e, lane, acc);
-    if (lane < G && lane < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + lane, acc[0]);
+    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C>(p, s, e, lane, acc);
+    if (lane < G) {
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        const int f = lane + q * G;
+        if (f < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + f, acc[q]);
+      }
+    }
     return;
   }
   const int64_t first = (w - p.n_tasks) * NG;
@@ -413,10 +432,16 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   int deg = e - s;
   const bool is_long = p.chunk > 0 && deg > p.chunk;   // handled by its slices + stage 2
   if (is_long) { deg = 0; }
-  if (PF && r >= 0 && (lig & 7) == 0 && lig < d4 && !(p.y_tail && r >= p.split_row)) {   // one request per 128-byte line
-    const size_t o = (size_t)r * d4 + lig;
-    if (p.acc_in) prefetch_l2(reinterpret_cast<const float4*>(p.acc_in) + o);
-    if (p.resid) prefetch_l2(reinterpret_cast<const float4*>(p.resid) + o);
+  if (PF && r >= 0 && !(p.y_tail && r >= p.split_row)) {   // one request per 128-byte line of the epilogue operands
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int f = lig + q * G;
+      if ((f & 7) == 0 && f < d4) {
+        const size_t o = (size_t)r * d4 + f;
+        if (p.acc_in) prefetch_l2(reinterpret_cast<const float4*>(p.acc_in) + o);
+        if (p.resid) prefetch_l2(reinterpret_cast<const float4*>(p.resid) + o);
+      }
+    }
   }
   const bool all_short = __all_sync(FULL_MASK, deg <= SUBW_MAX);
 
@@ -424,9 +449,10 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     int maxdeg = deg;
 #pragma unroll
     for (int off = G; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL_MASK, maxdeg, off));
-    float4 acc = f4_zero();
+    float4 acc[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
     const uint32_t d4u = (uint32_t)d4;
-    const bool col_ok = lig < d4;
     int c = 0, cn = 0;
     float wv = 0.f, wn = 0.f;
     if (PF && lig < deg) {                         // batch 0 of the (col,val) pairs
@@ -447,10 +473,10 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
           wv = p.val ? ld_stream_f32(p.val + s + base + lig) : 1.f;
         }
       }
-      const int cnt = min(G, deg - base);          // may be <= 0 for the shorter row of the pair
+      const int cnt = min(G, deg - base);          // may be <= 0 for the shorter rows of the warp
       const int cntmax = min(G, maxdeg - base);
       for (int j = 0; j < cntmax; j += UNROLL) {    // j + u < G: UNROLL divides G
-        float4 v[UNROLL];
+        float4 v[UNROLL][VPL];
         float ww[UNROLL];
         bool ok[UNROLL];
 #pragma unroll
@@ -458,19 +484,23 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
           const int k = j + u;
           const int cc = __shfl_sync(FULL_MASK, c, k, G);
           ww[u] = __shfl_sync(FULL_MASK, wv, k, G);
-          ok[u] = col_ok && k < cnt;
-          if (ok[u]) v[u] = ld_gather_f4(X4 + ((uint32_t)cc * d4u + (uint32_t)lig));
+          ok[u] = k < cnt;
+          const uint32_t row = (uint32_t)cc * d4u;
+#pragma unroll
+          for (int q = 0; q < VPL; ++q) {
+            const int f = lig + q * G;
+            if (ok[u] && f < d4) v[u][q] = ld_gather_f4(X4 + (row + (uint32_t)f));
+          }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-          if (ok[u]) f4_fma(acc, ww[u], v[u]);
+#pragma unroll
+          for (int q = 0; q < VPL; ++q)
+            if (ok[u] && lig + q * G < d4) f4_fma(acc[q], ww[u], v[u][q]);
       }
       if (PF) { c = cn; wv = wn; }
     }
-    if (r >= 0 && !is_long) {
-      float4 a1[1] = {acc};
-      epilogue_row<G, 1>(p, r, e - s, lig, a1);
-    }
+    if (r >= 0 && !is_long) epilogue_row<G, VPL>(p, r, e - s, lig, acc);
     return;
   }
   // mixed / longer rows: the whole warp walks the NG rows one after the other
@@ -480,26 +510,28 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     const int ss = __shfl_sync(FULL_MASK, s, g2 * G);
     const int ee = __shfl_sync(FULL_MASK, e, g2 * G);
     if (rr < 0 || (p.chunk > 0 && ee - ss > p.chunk)) continue;
-    float4 acc[1] = {f4_zero()};
-    accumulate_slice<G, 1, UNROLL, 32, uint32_t, D4C>(p, ss, ee, lane, acc);
-    if (lane < G) epilogue_row<G, 1>(p, rr, ee - ss, lane, acc);
+    float4 acc[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
+    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C>(p, ss, ee, lane, acc);
+    if (lane < G) epilogue_row<G, VPL>(p, rr, ee - ss, lane, acc);
   }
 }
 
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false>
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream);
 
-// d/4 == G (d = 64 with G = 16, d = 32 with G = 8) gets the kernel specialised on that constant
-template <int G, int UNROLL, int MINB, bool WIDE = false, bool PF = false>
+// d/4 == G*VPL (d = 64 with G = 16, d = 32 with G = 8) gets the kernel specialised on that constant
+template <int G, int UNROLL, int MINB, bool WIDE = false, bool PF = false, int VPL = 1>
 static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
-  return p.d4 == G ? launch_subwarp_impl<G, UNROLL, MINB, WIDE, G, PF>(p, stream)
-                   : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0, PF>(p, stream);
+  return p.d4 == G * VPL ? launch_subwarp_impl<G, UNROLL, MINB, WIDE, G * VPL, PF, VPL>(p, stream)
+                         : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0, PF, VPL>(p, stream);
 }
 
-template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF>
+template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF, int VPL>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   constexpr int NG = 32 / G;
   const int64_t row_warps = (p.n_rows + NG - 1) / NG;
@@ -507,11 +539,11 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   if (warps > 0) {
     const int64_t blocks = WIDE ? p.n_tasks + (row_warps + SPMM_WARPS - 1) / SPMM_WARPS : (warps + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
-    spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   return LGB_OK;
@@ -902,6 +934,9 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
       case 16: return launch_subwarp<16, 2, 16, true>(p, stream);   // sub-warp rows + one CTA per slice (measurement pending)
       case 18: return launch_subwarp<16, 2, 16, false, true>(p, stream);   // sub-warp rows + chain-shortening prefetches
       case 19: return launch_subwarp<16, 2, 16, true, true>(p, stream);    // 16 + 18
+      case 20: return launch_subwarp<8, 1, 16, true, false, 2>(p, stream);  // four rows per warp (8 lanes x 2 float4), unroll 1
+      case 21: return launch_subwarp<8, 2, 12, true, false, 2>(p, stream);  // four rows per warp, unroll 2 (48 warps / SM)
+      case 22: return launch_subwarp<8, 1, 16, true, true, 2>(p, stream);   // 20 + chain-shortening prefetches
       default: return launch_subwarp<16, 2, 16>(p, stream);
     }
   }
