@@ -18,6 +18,7 @@ tracing bakes in) unless ``bake_dropout_training=False``.
 from __future__ import annotations
 
 import copy
+import os
 import ctypes as C
 from collections import defaultdict, deque
 from typing import Dict, List, Optional, Tuple
@@ -113,11 +114,24 @@ class SAGEConv(nn.Module):
         if root_weight:
             self.lin_r = nn.LazyLinear(out_channels, bias=False) if in_channels[1] <= 0 else Linear(in_channels[1], out_channels, bias=False)
 
+    # Opt-in (SAGEConv.project_first = True, or LGB_SAGE_PROJECT_FIRST=1): when the layer narrows (out < in, e.g. the last
+    # encoder layer 128 -> 64) apply lin_l's weight BEFORE the neighbour aggregation -- sum/mean commute with a linear map,
+    # lin_l(agg_j x_j) = agg_j(W x_j) + b -- so the gather/scatter kernel and its backward move out/in of the bytes.
+    # Same function, different fp32 rounding order than the reference's (PyG's) evaluation, hence not the default.
+    project_first = os.environ.get("LGB_SAGE_PROJECT_FIRST", "0") == "1"
+
     def forward(self, x, edge_index, size=None, graph: Optional[DeviceCSR] = None) -> torch.Tensor:
         x_src, x_dst = (x, x) if isinstance(x, torch.Tensor) else x
         if graph is None:
             graph = build_edge_csr(edge_index, x_src.shape[0], x_dst.shape[0])
-        out = self.lin_l(aggregate(x_src, graph, self.aggr))
+        lazy = isinstance(self.lin_l, nn.LazyLinear) and self.lin_l.has_uninitialized_params()
+        if (self.project_first and not lazy and self.aggr in ("add", "sum", "mean")
+                and self.lin_l.out_features < self.lin_l.in_features):
+            out = aggregate(F.linear(x_src, self.lin_l.weight), graph, self.aggr)
+            if self.lin_l.bias is not None:
+                out = out + self.lin_l.bias
+        else:
+            out = self.lin_l(aggregate(x_src, graph, self.aggr))
         if self.root_weight and x_dst is not None:
             out = out + self.lin_r(x_dst)
         if self.normalize:

@@ -193,3 +193,4 @@ def test_autotune_picks_a_checked_variant(cuda_dev, monkeypatch):
 def lg_module():
     import laplace_gnn_recommendation_b200 as lg
     return lg
+test_sageconv_project_first_matches_reference_order = TZ.test_sageconv_project_first_matches_reference_order

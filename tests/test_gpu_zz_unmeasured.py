@@ -159,3 +159,24 @@ def test_autotune_on_device(cuda_dev):
     assert len(g.autotune_report["ms"]) == 8 and not g.autotune_report["rejected"], g.autotune_report
     X = torch.randn(20000, 64, device=cuda_dev)
     close(g.spmm(X), g.spmm(X, variant=0), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("aggr", ["add", "mean"])
+def test_sageconv_project_first_matches_reference_order(cuda_dev, aggr):
+    """Opt-in SAGEConv.project_first (lin_l's weight applied before the neighbour aggregation when the layer narrows) computes
+    the same layer and the same gradients as the reference order lin_l(agg_j x_j), to fp32 rounding."""
+    gen = torch.Generator().manual_seed(3)
+    ns, nd, E, fin, fout = 300, 200, 4000, 128, 64
+    ei = torch.stack([torch.randint(0, ns, (E,), generator=gen), torch.randint(0, nd, (E,), generator=gen)]).to(cuda_dev)
+    xs, xd = torch.randn(ns, fin, generator=gen).to(cuda_dev), torch.randn(nd, fin, generator=gen).to(cuda_dev)
+    conv = lg.SAGEConv((fin, fin), fout, aggr=aggr).to(cuda_dev)
+    outs = []
+    for flag in (False, True):
+        conv.project_first = flag
+        a, b = xs.clone().requires_grad_(True), xd.clone().requires_grad_(True)
+        conv.zero_grad()
+        y = conv((a, b), ei)
+        (y * torch.linspace(-1, 1, fout, device=cuda_dev)).sum().backward()
+        outs.append((y.detach(), a.grad, b.grad, conv.lin_l.weight.grad.clone(), conv.lin_l.bias.grad.clone()))
+    for u, v in zip(*outs):
+        close(u, v, rtol=1e-4, atol=1e-4)

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--sizes", default="S,M,L")
     ap.add_argument("--aggr", default="add")
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--project-first", action="store_true", help="SAGEConv.project_first: narrow layers aggregate after lin_l's weight")
     a = ap.parse_args()
     dev = _common.device()
     if _common.DRYRUN:
@@ -61,6 +62,10 @@ def main():
             encoder_layers=lg.get_SAGEConv_layers(2, HID, OUT, a.aggr), decoder_layers=lg.get_linear_layers(2, 2 * OUT, HID, 1),
             feature_info={}, metadata=metadata, embedding=False, heterogeneous_prop_agg_type="sum", batch_normalize=True,
             p_dropout_edges=None, p_dropout_features=None).to(dev)
+        if a.project_first:
+            for m in model.modules():
+                if isinstance(m, hetero.SAGEConv):
+                    m.project_first = True
         lossf = torch.nn.BCEWithLogitsLoss()
 
         def step():
@@ -90,7 +95,7 @@ def main():
         ms = t0.elapsed_time(t1) / a.steps
         agg_ms = sum(e0.elapsed_time(e1) for e0, e1, *_ in events) / a.steps
         agg_gb = sum(seg_bytes(nnz, F, rows) for _, _, nnz, rows, F in events) / a.steps / 1e9
-        line = {"size": size, "aggr": a.aggr, "E_sub": SIZES[size][0], "ms_per_step": ms, "aggregation_ms": agg_ms,
+        line = {"size": size, "aggr": a.aggr, "project_first": a.project_first, "E_sub": SIZES[size][0], "ms_per_step": ms, "aggregation_ms": agg_ms,
                 "aggregation_share": agg_ms / ms, "aggregation_GBps": agg_gb / (agg_ms * 1e-3), "launches_per_step": len(events) // a.steps,
                 "loss": float(loss)}
         if size == "S":

@@ -20,6 +20,7 @@ case "${1:-single}" in
     T 400 python tools/shard_probe.py --world 8 --ranks 0,7 --variants 0,16,18,19,12 --chunks 1024,256 2>&1 | grep -v Warn
     T 300 python tools/shard_probe.py --world 4 --ranks 0 --variants 0,16 --chunks 1024,512 2>&1 | grep -v Warn
     T 300 python tools/hetero_bench.py 2>&1 | tail -12
+    T 300 python tools/hetero_bench.py --project-first 2>&1 | tail -12
     T 300 python tools/train_lightgcn.py --style reference --iters 100 2>&1 | tail -1 | cut -c1-400
     T 300 python tools/train_lightgcn.py --style fused --iters 100 2>&1 | tail -1 | cut -c1-400
     T 200 python bench.py --steps 20 --warmup 5 --degree-order --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_degree_order.json
