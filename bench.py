@@ -30,6 +30,12 @@ WORKLOADS = {
 }
 CPU_SAMPLE_SCALE = 8  # the CPU arms run the same generator at 1/8 of every dimension (bounded sample)
 
+# BASELINE.json configs[3]: hetero encoder-decoder ranking step on LinkNeighborLoader-sized batches cut to the H&M shape
+# (SURVEY 8d.5): name -> (E_sub per edge type, N_customer, N_article, label edges); widths 84/76 -> hidden 128 -> out 64
+HETERO_SIZES = {"hetero_s": (72_000, 3_000, 40_000, 1_100), "hetero_m": (400_000, 16_000, 90_000, 5_800),
+                "hetero_l": (3_000_000, 130_000, 105_000, 46_000)}
+HET_FC, HET_FA, HET_HID, HET_OUT, HET_LAYERS = 84, 76, 128, 64, 2
+
 
 def zipf_ids(n_ids: int, n_samples: int, alpha: float, gen: torch.Generator, device) -> torch.Tensor:
     """Ids drawn from Zipf(alpha) over a random permutation of [0, n_ids) (SURVEY 8d degree model)."""
@@ -382,13 +388,258 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# hetero encoder-decoder ranking step (BASELINE.json configs[3]); python bench.py --workload hetero_m
+def hetero_batch(size, dev, seed=0):
+    from laplace_gnn_recommendation_b200 import hetero
+    E, Nc, Na, L = HETERO_SIZES[size]
+    gen = torch.Generator().manual_seed(seed)
+    x = {"customer": torch.randn(Nc, HET_FC, generator=gen), "article": torch.randn(Na, HET_FA, generator=gen)}
+    e = torch.stack([torch.randint(0, Nc, (E,), generator=gen), torch.randint(0, Na, (E,), generator=gen)])
+    ei = {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()}
+    eli = torch.stack([torch.randint(0, Nc, (L,), generator=gen), torch.randint(0, Na, (L,), generator=gen)])
+    y = (torch.rand(L, generator=gen) > 0.75).float()
+    to = (lambda t: t.to(dev)) if dev is not None else (lambda t: t)
+    return {k: to(v) for k, v in x.items()}, {k: to(v) for k, v in ei.items()}, to(eli), to(y)
+
+
+def seg_bytes(E, F, n_dst):
+    """Algorithmic bytes of one neighbour aggregation: E*(4 + F*4) + (N_dst+1)*4 + N_dst*F*4."""
+    return E * (4 + F * 4) + (n_dst + 1) * 4 + n_dst * F * 4
+
+
+def hetero_model(aggr, project_first=False):
+    import laplace_gnn_recommendation_b200 as lg
+    from laplace_gnn_recommendation_b200 import hetero
+    metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
+    torch.manual_seed(0)
+    model = lg.Encoder_Decoder_Model(
+        encoder_layers=lg.get_SAGEConv_layers(HET_LAYERS, HET_HID, HET_OUT, aggr),
+        decoder_layers=lg.get_linear_layers(2, 2 * HET_OUT, HET_HID, 1), feature_info={}, metadata=metadata, embedding=False,
+        heterogeneous_prop_agg_type="sum", batch_normalize=True, p_dropout_edges=None, p_dropout_features=None)
+    if project_first:
+        for m in model.modules():
+            if isinstance(m, hetero.SAGEConv):
+                m.project_first = True
+    return model, metadata
+
+
+def hetero_cpu_step_runner(size, aggr, state_dict, metadata):
+    """The CPU arm: the oracle's training step (hetero SAGE encoder, batch norm, concat-MLP decoder, BCE, autograd backward)."""
+    from oracle import hetero_oracle as ho
+    x, ei, eli, y = hetero_batch(size, None)
+    sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point) for k, v in state_dict.items()}
+    layers = [{et: dict(w_l=sd[f"encoder.layers.{li}.{'__'.join(et)}.lin_l.weight"], b_l=sd[f"encoder.layers.{li}.{'__'.join(et)}.lin_l.bias"],
+                        w_r=sd[f"encoder.layers.{li}.{'__'.join(et)}.lin_r.weight"]) for et in metadata[1]} for li in range(HET_LAYERS)]
+    lin = [(sd[f"decoder.layers.{i}.weight"], sd[f"decoder.layers.{i}.bias"]) for i in range(2)]
+
+    def step():
+        z = ho.hetero_encoder(x, ei, layers, aggr, "sum", metadata[1])
+        zu = ho.batch_norm_train(z["customer"], sd["encoder_layer_norm_customer.weight"], sd["encoder_layer_norm_customer.bias"])
+        zi = ho.batch_norm_train(z["article"], sd["encoder_layer_norm_article.weight"], sd["encoder_layer_norm_article.bias"])
+        loss = ho.bce_with_logits(ho.edge_decoder_mlp(zu, zi, eli, lin), y)
+        loss.backward()
+        return loss
+    return step
+
+
+def hetero_line(args, value, ms):
+    E, Nc, Na, L = HETERO_SIZES[args.workload]
+    return {"metric": "hetero_sage_ranking_step_edge_traversals_per_s", "value": value, "unit": "edge-traversals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}_{args.hetero_aggr}", "E_sub_per_edge_type": E, "N_customer": Nc, "N_article": Na,
+                       "label_edges": L, "widths": [HET_FC, HET_FA, HET_HID, HET_OUT], "sage_layers": HET_LAYERS,
+                       "step": "encoder (2 edge types x 2 SAGE layers) + batch norm + concat-MLP decoder + BCE, forward + backward",
+                       "traversals_per_step": "2 edge types x E_sub x layers x (fwd + bwd)",
+                       "l2": "L: features + messages exceed L2; S/M are L2-resident (stated, not flushed: the reference's own batch sizes)",
+                       "project_first": bool(args.project_first),
+                       "parallelism": "single GPU" if args.gpus == 1 else f"independent batches x{args.gpus}, gradient all-reduce of the dense weights"}}
+
+
+def run_hetero(args):
+    import torch.distributed as dist
+    from laplace_gnn_recommendation_b200 import _lib
+    from laplace_gnn_recommendation_b200.csr import DeviceCSR
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    E, Nc, Na, L = HETERO_SIZES[args.workload]
+    x, ei, eli, y = hetero_batch(args.workload, dev, seed=rank)
+    model, metadata = hetero_model(args.hetero_aggr, args.project_first)
+    model = model.to(dev)
+    lossf = torch.nn.BCEWithLogitsLoss()
+    params = None
+
+    def step(xb=x, eib=ei, elib=eli, yb=y):
+        model.zero_grad(set_to_none=True)
+        loss = lossf(model(dict(xb), eib, elib), yb)
+        loss.backward()
+        if world > 1:                      # data-parallel replicas: one all-reduce of the (small, dense) weight gradients
+            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+            dist.all_reduce(flat)
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    events = []
+    orig = DeviceCSR.spmm
+
+    def timed(self, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = orig(self, *a, **k); e1.record()
+        events.append((e0, e1, self.nnz, self.n_rows, a[0].shape[1]))
+        return out
+    for _ in range(args.warmup):
+        step()
+    sync()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    DeviceCSR.spmm = timed
+    launches0 = _lib.LAUNCHES
+    sync()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        loss = step()
+    t1.record()
+    sync()
+    DeviceCSR.spmm = orig
+    launches = _lib.LAUNCHES - launches0
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([t0.elapsed_time(t1) / max(args.steps, 1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    trav = 2 * E * HET_LAYERS * 2
+    value = world * trav / (ms * 1e-3)
+    agg_ms = [a.elapsed_time(b) for a, b, *_ in events]
+    agg_alg = [seg_bytes(z, F_, r) for _, _, z, r, F_ in events]
+    mp = {}
+    try:
+        mp = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(mp.get("hbm_gbs", 6650.0))
+    achieved = (sum(agg_alg) / 1e9) / (sum(agg_ms) * 1e-3) if agg_ms else None
+    roofline = {"bound": "hbm", "kernel": "lgb_spmm with val == NULL (per-edge-type neighbour sum/mean, forward and transposed backward)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in mp else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "algorithmic_bytes_per_step": sum(agg_alg) / max(args.steps, 1), "launches_timed": len(agg_ms),
+                "avg_launch_ms": statistics.mean(agg_ms) if agg_ms else None,
+                "aggregation_share_of_step": sum(agg_ms) / (args.steps * ms) if agg_ms else None}
+
+    # ---- e2e: the batch arrives in pinned host memory (what a DataLoader hands over), copied inside the timed region
+    hx, hei, heli, hy = hetero_batch(args.workload, None, seed=rank)
+    pin = lambda t: t.pin_memory()   # noqa: E731
+    hx, hei, heli, hy = {k: pin(v) for k, v in hx.items()}, {k: pin(v) for k, v in hei.items()}, pin(heli), pin(hy)
+    h2d = sum(t.numel() * t.element_size() for t in list(hx.values()) + list(hei.values()) + [heli, hy])
+
+    def api_step():
+        xb = {k: v.to(dev, non_blocking=True) for k, v in hx.items()}
+        eib = {k: v.to(dev, non_blocking=True) for k, v in hei.items()}
+        return step(xb, eib, heli.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)).item()
+    for _ in range(3):
+        api_step()
+    sync()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        api_step()
+    sync()
+    e_ms = torch.tensor([(time.perf_counter() - w0) * 1e3 / max(args.steps, 1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * trav / (float(e_ms) * 1e-3), "unit": "edge-traversals/s", "ms_per_step": float(e_ms),
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "path": "Encoder_Decoder_Model.forward(x_dict, edge_index_dict, edge_label_index) -> BCEWithLogitsLoss -> backward -> loss.item()"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        csize = "hetero_s"                                   # bounded sample: the S batch whatever size the GPU arm ran
+        cstep = hetero_cpu_step_runner(csize, args.hetero_aggr, model.state_dict(), metadata)
+        cstep()
+        c0, reps = time.perf_counter(), 0
+        while reps < 3 or (time.perf_counter() - c0 < 10 and reps < 50):
+            cstep(); reps += 1
+        cdt = (time.perf_counter() - c0) / reps
+        ctrav = 2 * HETERO_SIZES[csize][0] * HET_LAYERS * 2
+        cpu_baseline = {"value": ctrav / cdt, "unit": "edge-traversals/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "ms_per_step": cdt * 1e3, "sample": f"{csize} batch (E_sub={HETERO_SIZES[csize][0]}), {reps} full training steps after 1 "
+                                                              "warm-up; oracle port (index_add scatter, torch Linear, autograd)"}
+    if rank == 0:
+        line = hetero_line(args, value, ms)
+        line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                     "loss": float(loss)})
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_hetero_reference(args):
+    """--impl reference for the hetero workloads: the oracle's training step on the S batch, all host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    from laplace_gnn_recommendation_b200 import hetero
+    metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
+    sd = materialized_state_dict()
+    step = hetero_cpu_step_runner("hetero_s", args.hetero_aggr, sd, metadata)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = 2 * HETERO_SIZES["hetero_s"][0] * HET_LAYERS * 2 / dt
+    line = hetero_line(args, value, dt * 1e3)
+    line.update({"impl": "reference",
+                 "cpu_baseline": {"value": value, "unit": "edge-traversals/s", "cores": torch.get_num_threads(), "kind": "port",
+                                  "sample": "hetero_s batch, full training step per step; oracle port"},
+                 "e2e": {"value": value, "unit": "edge-traversals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def materialized_state_dict():
+    """Weights of the lazily-sized hetero model without a device: plain tensors of the right shapes, same initialisers."""
+    from laplace_gnn_recommendation_b200 import hetero
+    torch.manual_seed(0)
+    sd = {}
+    widths = {"customer": HET_FC, "article": HET_FA}
+    for li in range(HET_LAYERS):
+        out = HET_HID if li < HET_LAYERS - 1 else HET_OUT
+        for et in (hetero.EDGE_KEY, hetero.REV_EDGE_KEY):
+            name = f"encoder.layers.{li}.{'__'.join(et)}"
+            lin_l, lin_r = torch.nn.Linear(widths[et[0]], out), torch.nn.Linear(widths[et[2]], out, bias=False)
+            sd[f"{name}.lin_l.weight"], sd[f"{name}.lin_l.bias"], sd[f"{name}.lin_r.weight"] = lin_l.weight, lin_l.bias, lin_r.weight
+        widths = {"customer": out, "article": out}
+    for t in ("customer", "article"):
+        sd[f"encoder_layer_norm_{t}.weight"], sd[f"encoder_layer_norm_{t}.bias"] = torch.ones(HET_OUT), torch.zeros(HET_OUT)
+    dec = [torch.nn.Linear(2 * HET_OUT, HET_HID), torch.nn.Linear(HET_HID, 1)]
+    for i, l in enumerate(dec):
+        sd[f"decoder.layers.{i}.weight"], sd[f"decoder.layers.{i}.bias"] = l.weight, l.bias
+    return sd
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hm", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="hm", choices=sorted(WORKLOADS) + sorted(HETERO_SIZES),
+                    help="hm / ml1m: LightGCN epoch (BASELINE.json configs[2] / [1]); hetero_s|m|l: ranking encoder-decoder step (configs[3])")
+    ap.add_argument("--hetero-aggr", default="add", choices=["add", "mean"], help="SAGEConv aggregation of the hetero workloads")
+    ap.add_argument("--project-first", action="store_true", help="hetero workloads: SAGEConv.project_first (opt-in evaluation order)")
     ap.add_argument("--degree", default="powerlaw", choices=["powerlaw", "uniform"])
     ap.add_argument("--dim", type=int, default=64)
     ap.add_argument("--layers", type=int, default=3)
@@ -404,7 +655,9 @@ def main():
                     help="multi-GPU overlap schedule (dist.ShardedLightGCN); 'layer' is the measured default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload in HETERO_SIZES:
+        (run_hetero_reference if args.impl == "reference" else run_hetero)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

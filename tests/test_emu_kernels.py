@@ -194,3 +194,20 @@ def lg_module():
     import laplace_gnn_recommendation_b200 as lg
     return lg
 test_sageconv_project_first_matches_reference_order = TZ.test_sageconv_project_first_matches_reference_order
+
+
+def test_bench_hetero_workload_pieces(cuda_dev, monkeypatch):
+    """bench.py --workload hetero_*: the synthetic batch, the model, one training step on the (emulated) kernels and the
+    CPU-oracle arm built from the model's state_dict must describe the same computation (same loss)."""
+    import bench
+    monkeypatch.setitem(bench.HETERO_SIZES, "hetero_s", (600, 40, 90, 30))
+    x, ei, eli, y = bench.hetero_batch("hetero_s", cuda_dev)
+    for project_first in (False, True):
+        model, metadata = bench.hetero_model("add", project_first)
+        loss = torch.nn.BCEWithLogitsLoss()(model(dict(x), ei, eli), y)
+        loss.backward()
+        cpu = bench.hetero_cpu_step_runner("hetero_s", "add", model.state_dict(), metadata)()
+        assert float(loss) == pytest.approx(float(cpu), rel=1e-5)
+    sd = bench.materialized_state_dict()
+    assert set(sd) == {k for k in model.state_dict() if "num_batches_tracked" not in k and "running_" not in k}
+    assert bench.seg_bytes(10, 4, 3) == 10 * (4 + 16) + 4 * 4 + 3 * 16

@@ -19,8 +19,10 @@ case "${1:-single}" in
     # one GPU standing in for rank r of an 8- / 4-way sharded run: per-launch latency floor, slice size, CTA-wide slices
     T 400 python tools/shard_probe.py --world 8 --ranks 0,7 --variants 0,16,18,19,12 --chunks 1024,256 2>&1 | grep -v Warn
     T 300 python tools/shard_probe.py --world 4 --ranks 0 --variants 0,16 --chunks 1024,512 2>&1 | grep -v Warn
-    T 300 python tools/hetero_bench.py 2>&1 | tail -12
-    T 300 python tools/hetero_bench.py --project-first 2>&1 | tail -12
+    for hs in hetero_s hetero_m hetero_l; do
+      T 200 python bench.py --workload $hs --steps 20 --warmup 5 | tail -1 > gpurun_out/bench_$hs.json
+      T 200 python bench.py --workload $hs --steps 20 --warmup 5 --project-first --no-cpu-baseline | tail -1 > gpurun_out/bench_${hs}_project_first.json
+    done
     T 300 python tools/train_lightgcn.py --style reference --iters 100 2>&1 | tail -1 | cut -c1-400
     T 300 python tools/train_lightgcn.py --style fused --iters 100 2>&1 | tail -1 | cut -c1-400
     T 200 python bench.py --steps 20 --warmup 5 --degree-order --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_degree_order.json
