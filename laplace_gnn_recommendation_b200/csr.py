@@ -2,12 +2,13 @@
 
 HBM layout per graph (int32 indices, fp32 values):
     rowptr[n_rows+1] | colidx[nnz] | val[nnz] (optional) | split plan (long_rows, long_ptr, task_row,
-    task_start) | optional degree-bucketed row_order[n_rows] | per-d partial-sum scratch [n_tasks, d]
+    task_start, task_end) | optional degree-bucketed row_order[n_rows] | per-d partial-sum scratch [n_tasks, d]
 The transposed graph (CSC arrays, used by every backward) is a second DeviceCSR built lazily and cached.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -15,11 +16,11 @@ import torch
 from . import _lib
 from ._lib import LgbCsr, check, ptr, stream
 
-import os as _os
-
-SPMM_VARIANT = int(_os.environ.get("LGB_SPMM_VARIANT", "0"))  # 0 = tuned default; see LGB_SPMM_VARIANT_SHIFT in the header
-DEFAULT_CHUNK = int(_os.environ.get("LGB_SPMM_CHUNK", "1024"))   # rows with more non-zeros are split into chunk-sized tasks (csrc/spmm.cu): bounds the length of
-                      # any sequential fp32 accumulation chain (accuracy) and the work of one warp (load balance)
+# kernel variant used when neither the call nor autotune() names one (0 = the default; see LGB_SPMM_VARIANT_SHIFT in the header)
+SPMM_VARIANT = int(os.environ.get("LGB_SPMM_VARIANT", "0"))
+# rows with more non-zeros are split into chunk-sized slices (csrc/spmm.cu): bounds the length of any sequential fp32
+# accumulation chain (accuracy) and the work of one warp (load balance)
+DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
 
 
 # candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
