@@ -176,6 +176,39 @@ class LightGCN(nn.Module):
     def message_and_aggregate(self, adj_t: SparseTensor, x: torch.Tensor) -> torch.Tensor:
         return matmul(adj_t, x)
 
+    # ---- CUDA-graph replay of the fused step (launch-bound graphs: ML-1M-sized and smaller) -------------------
+    def capture_step(self, edge_index: SparseTensor, batch_size: int, lambda_val: float):
+        """Capture ``fused_step`` for a fixed batch size into ONE CUDA graph and return ``step(u, p, n) -> loss`` that copies
+        the three index vectors into static buffers and replays it: the 2K + 3 kernel launches (+ memset) of an iteration
+        become a single graph launch, which is what bounds an iteration on graphs whose SpMM takes tens of microseconds.
+        The gradients land in ``users_emb.weight.grad`` / ``items_emb.weight.grad`` (same buffers on every replay), the loss
+        in the returned 0-dim tensor.  The embedding tables are read in place, so optimizer steps between replays are seen."""
+        Wu = self.users_emb.weight
+        _lib.require_cuda(Wu)
+        dev = Wu.device
+        gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr().transpose()      # build everything outside the capture
+        su, sp, sn = (torch.zeros(int(batch_size), dtype=torch.int64, device=dev) for _ in range(3))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up on a side stream, as torch.cuda.graph requires
+            for _ in range(2):
+                self.fused_step(edge_index, su, sp, sn, lambda_val)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.fused_step(edge_index, su, sp, sn, lambda_val)
+        grads = (self.users_emb.weight.grad, self.items_emb.weight.grad)
+
+        def step(user_indices, pos_item_indices, neg_item_indices):
+            su.copy_(user_indices, non_blocking=True)
+            sp.copy_(pos_item_indices, non_blocking=True)
+            sn.copy_(neg_item_indices, non_blocking=True)
+            graph.replay()
+            self.users_emb.weight.grad, self.items_emb.weight.grad = grads      # zero_grad(set_to_none) may have dropped them
+            return loss
+        step.graph = graph
+        return step
+
     # ---- fused training step (no autograd graph, no gathered copies) ------------------------------
     @torch.no_grad()
     def fused_step(self, edge_index: SparseTensor, user_indices: torch.Tensor, pos_item_indices: torch.Tensor,

@@ -180,3 +180,26 @@ def test_sageconv_project_first_matches_reference_order(cuda_dev, aggr):
         outs.append((y.detach(), a.grad, b.grad, conv.lin_l.weight.grad.clone(), conv.lin_l.bias.grad.clone()))
     for u, v in zip(*outs):
         close(u, v, rtol=1e-4, atol=1e-4)
+
+
+def test_captured_step_replays_the_fused_step(cuda_dev):
+    """LightGCN.capture_step: the CUDA-graph replay gives the same loss and gradients as fused_step for new batches, and sees
+    parameter updates made between replays."""
+    gen = torch.Generator().manual_seed(4)
+    U, I, E, d, K, B, lam = 300, 200, 5000, 64, 3, 128, 1e-4
+    users, items = torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)
+    row, col, n = lo.wiring_symmetric(users, items, U, I)
+    torch.manual_seed(2)
+    model = lg.LightGCN(U, I, d, K).to(cuda_dev)
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(n, n)).to(cuda_dev)
+    step = model.capture_step(adj, B, lam)
+    opt = lg.FusedAdam(model.parameters(), lr=1e-2)
+    for it in range(3):
+        pick = torch.randint(0, E, (B,), generator=gen)
+        u, p, nn_ = users[pick].to(cuda_dev), items[pick].to(cuda_dev), torch.randint(0, I, (B,), generator=gen).to(cuda_dev)
+        loss = step(u, p, nn_).clone()
+        gu, gi = model.users_emb.weight.grad.clone(), model.items_emb.weight.grad.clone()
+        want = model.fused_step(adj, u, p, nn_, lam)
+        close(loss, want)
+        close(gu, model.users_emb.weight.grad, atol=1e-9); close(gi, model.items_emb.weight.grad, atol=1e-9)
+        opt.step()                                   # the next replay must see the updated tables

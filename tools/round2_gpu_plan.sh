@@ -14,6 +14,7 @@ case "${1:-single}" in
     T 200 python bench.py --steps 20 --warmup 5 | tail -1 > gpurun_out/bench_hm.json
     T 200 python bench.py --steps 20 --warmup 5 --degree uniform --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_uniform.json
     T 200 python bench.py --steps 50 --warmup 5 --workload ml1m --no-cpu-baseline | tail -1 > gpurun_out/bench_ml1m.json
+    T 200 python bench.py --steps 50 --warmup 5 --workload ml1m --no-cpu-baseline --graph | tail -1 > gpurun_out/bench_ml1m_graph.json
     LGB_SPMM_VARIANT=16 T 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_v16.json
     T 200 python tools/spmm_probe.py --variants 0,16,18,19,12,13 2>&1 | grep -v Warn
     # one GPU standing in for rank r of an 8- / 4-way sharded run: per-launch latency floor, slice size, CTA-wide slices
