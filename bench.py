@@ -270,6 +270,8 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     DeviceCSR.spmm = timed_spmm
+    if world > 1 and hasattr(eng.ops, "exchange_events") and not args.graph:
+        eng.ops.exchange_events = []           # CUDA events on the comm stream around every item-block all-reduce
     launches0 = _lib.LAUNCHES
     sync()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,6 +281,19 @@ def run_ours(args):
     t1.record()
     sync()
     launches = _lib.LAUNCHES - launches0
+    exchange = None
+    if world > 1 and getattr(eng.ops, "exchange_events", None):
+        ev, eng.ops.exchange_events = eng.ops.exchange_events, None
+        x_ms = [a.elapsed_time(b) for a, b, _ in ev]
+        x_bytes = [n for _, _, n in ev]
+        # an all-reduce of M bytes over G ranks moves 2*M*(G-1)/G bytes through each GPU's links (reduce-scatter + all-gather)
+        bus = [2.0 * n * (world - 1) / world for n in x_bytes]
+        exchange = {"collective": f"NCCL all-reduce of the replicated item block ({args.exchange})", "per_step": len(ev) // max(args.steps, 1),
+                    "mean_ms": statistics.mean(x_ms), "mean_bytes": statistics.mean(x_bytes),
+                    "bus_GBps": sum(bus) / 1e9 / (sum(x_ms) * 1e-3), "nvlink_peak_GBps_per_direction": 900.0,
+                    "frac_of_nominal": sum(bus) / 1e9 / (sum(x_ms) * 1e-3) / 900.0,
+                    "share_of_step_if_exposed": sum(x_ms) / (args.steps * float(t0.elapsed_time(t1)) / max(args.steps, 1)),
+                    "note": "timed on the comm stream; in the default schedule it overlaps with the users SpMM"}
     clk = clocks.stop() if rank == 0 else None
     graphed = bool(args.graph)
     if graphed:
@@ -384,6 +399,8 @@ def run_ours(args):
     if rank == 0:
         line = base_line(args, value, ms, nnz)
         line["config"]["spmm_variant"] = tuned if tuned is not None else "default (autotune off)"
+        if exchange is not None:
+            line["exchange"] = exchange
         line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                      "cpu_baseline": cpu_baseline, "loss": float(loss),
                      "interactions_per_s": E / (ms * 1e-3)})

@@ -70,6 +70,7 @@ class CudaOps:
         self.device, self.group = device, group
         self.comm = torch.cuda.Stream(device=device)
         self._bpr_ws = None
+        self.exchange_events = None     # set to a list to record (start, end, bytes) CUDA events of every item-block exchange
 
     # graph ----------------------------------------------------------------------------------
     def build_graph(self, row, col, n, dinv):
@@ -144,7 +145,13 @@ class CudaOps:
         cur = torch.cuda.current_stream(self.device)
         self.comm.wait_stream(cur)
         with torch.cuda.stream(self.comm):
+            if self.exchange_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.comm)
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            if self.exchange_events is not None:
+                e1.record(self.comm)
+                self.exchange_events.append((e0, e1, t.numel() * t.element_size()))
         return _StreamWait(self.comm, cur)
 
     def all_reduce(self, t: torch.Tensor):
