@@ -23,6 +23,23 @@ sys.path.insert(0, REPO)
 
 import torch  # noqa: E402
 
+
+class CUDA:
+    """The CUDA-runtime touch points of this script in one place.  On the GPU box these are the plain torch.cuda calls;
+    tests/test_emu_kernels.py swaps the class for wall-clock / CPU stand-ins to dry-run the script's own logic (workload
+    set-up, plan-time tuning, JSON assembly) on the emulated kernels -- the product path itself has no such switch."""
+    available = staticmethod(lambda: torch.cuda.is_available())
+    event = staticmethod(lambda: torch.cuda.Event(enable_timing=True))
+    synchronize = staticmethod(lambda: torch.cuda.synchronize())
+    empty_cache = staticmethod(lambda: torch.cuda.empty_cache())
+    pin = staticmethod(lambda t: t.pin_memory())
+
+    @staticmethod
+    def device(local: int) -> torch.device:
+        torch.cuda.set_device(local)
+        return torch.device("cuda", local)
+
+
 WORKLOADS = {
     # name: (U, I, E)  -- BASELINE.json configs[2] (H&M-shaped) and configs[1] (MovieLens-1M-shaped)
     "hm": (1_371_980, 105_542, 31_788_324),
@@ -181,10 +198,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
+    if not CUDA.available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dev = CUDA.device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus:
@@ -244,14 +260,14 @@ def run_ours(args):
             gstep = eng.capture(B, lam)
             step = lambda: gstep(ub, pb, nb)                    # noqa: E731
     del users, items
-    torch.cuda.empty_cache()
+    CUDA.empty_cache()
 
     # per-launch CUDA-event timing of the dominant kernel (lgb_spmm) inside the timed region
     spmm_events = []
     orig_spmm = DeviceCSR.spmm
 
     def timed_spmm(self, *a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = CUDA.event(), CUDA.event()
         e0.record()
         out = orig_spmm(self, *a, **k)
         e1.record()
@@ -261,7 +277,7 @@ def run_ours(args):
     def sync():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        CUDA.synchronize()
 
     for _ in range(args.warmup):
         step()
@@ -274,7 +290,7 @@ def run_ours(args):
         eng.ops.exchange_events = []           # CUDA events on the comm stream around every item-block all-reduce
     launches0 = _lib.LAUNCHES
     sync()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0, t1 = CUDA.event(), CUDA.event()
     t0.record()
     for _ in range(args.steps):
         loss = step()
@@ -340,7 +356,7 @@ def run_ours(args):
     # ---- e2e: the reference-style call sequence through the public API, host buffers in the timed region
     e2e = None
     if world == 1:
-        hu, hp, hn = (t.cpu().pin_memory() for t in (ub, pb, nb))
+        hu, hp, hn = (CUDA.pin(t.cpu()) for t in (ub, pb, nb))
 
         def api_step():
             u_ = hu.to(dev, non_blocking=True); p_ = hp.to(dev, non_blocking=True); n_ = hn.to(dev, non_blocking=True)
@@ -355,13 +371,13 @@ def run_ours(args):
         w0 = time.perf_counter()
         for _ in range(args.steps):
             api_step()
-        torch.cuda.synchronize()
+        CUDA.synchronize()
         e_ms = (time.perf_counter() - w0) * 1e3 / max(args.steps, 1)
         e2e = {"value": 2 * K * nnz / (e_ms * 1e-3), "unit": "edge-traversals/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": 3 * B * 8, "d2h_bytes_per_step": 4,
                "path": "LightGCN.forward(SparseTensor) -> 6 gathers -> bpr_loss -> loss.backward() -> loss.item()"}
     else:
-        hu, hp, hn = (t.cpu().pin_memory() for t in (ub, pb, nb))
+        hu, hp, hn = (CUDA.pin(t.cpu()) for t in (ub, pb, nb))
 
         def api_step():
             if not args.graph:
@@ -483,10 +499,9 @@ def run_hetero(args):
     from laplace_gnn_recommendation_b200 import _lib
     from laplace_gnn_recommendation_b200.csr import DeviceCSR
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
+    if not CUDA.available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    dev = CUDA.device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus:
@@ -510,12 +525,12 @@ def run_hetero(args):
     def sync():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        CUDA.synchronize()
     events = []
     orig = DeviceCSR.spmm
 
     def timed(self, *a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = CUDA.event(), CUDA.event()
         e0.record(); out = orig(self, *a, **k); e1.record()
         events.append((e0, e1, self.nnz, self.n_rows, a[0].shape[1]))
         return out
@@ -528,7 +543,7 @@ def run_hetero(args):
     DeviceCSR.spmm = timed
     launches0 = _lib.LAUNCHES
     sync()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0, t1 = CUDA.event(), CUDA.event()
     t0.record()
     for _ in range(args.steps):
         loss = step()
@@ -561,7 +576,7 @@ def run_hetero(args):
 
     # ---- e2e: the batch arrives in pinned host memory (what a DataLoader hands over), copied inside the timed region
     hx, hei, heli, hy = hetero_batch(args.workload, None, seed=rank)
-    pin = lambda t: t.pin_memory()   # noqa: E731
+    pin = CUDA.pin
     hx, hei, heli, hy = {k: pin(v) for k, v in hx.items()}, {k: pin(v) for k, v in hei.items()}, pin(heli), pin(hy)
     h2d = sum(t.numel() * t.element_size() for t in list(hx.values()) + list(hei.values()) + [heli, hy])
 
@@ -600,7 +615,7 @@ def run_hetero(args):
     if rank == 0:
         line = hetero_line(args, value, ms)
         line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                     "loss": float(loss)})
+                     "loss": float(loss.detach())})
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

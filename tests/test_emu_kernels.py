@@ -211,3 +211,62 @@ def test_bench_hetero_workload_pieces(cuda_dev, monkeypatch):
     sd = bench.materialized_state_dict()
     assert set(sd) == {k for k in model.state_dict() if "num_batches_tracked" not in k and "running_" not in k}
     assert bench.seg_bytes(10, 4, 3) == 10 * (4 + 16) + 4 * 4 + 3 * 16
+
+
+class _WallEvent:
+    def __init__(self):
+        self.t = 0.0
+
+    def record(self, stream=None):
+        import time
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+    def synchronize(self):
+        pass
+
+
+@pytest.mark.parametrize("workload", ["hm", "hetero_s"])
+def test_bench_script_logic_dry_run(cuda_dev, monkeypatch, capsys, workload):
+    """bench.py's own logic (workload set-up, plan-time tuning, timed loop, roofline / e2e / cpu_baseline assembly, the JSON
+    contract) executed end to end at N=1 on a tiny workload: kernels = the emulated library, CUDA events = wall clock.  The
+    numbers mean nothing; every key the driver reads must be there and be finite."""
+    import argparse
+    import json
+    import math
+    import bench
+    from laplace_gnn_recommendation_b200 import csr
+
+    class FakeCuda:
+        available = staticmethod(lambda: True)
+        event = staticmethod(_WallEvent)
+        synchronize = staticmethod(lambda: None)
+        empty_cache = staticmethod(lambda: None)
+        pin = staticmethod(lambda t: t)
+        device = staticmethod(lambda local: cuda_dev)
+    monkeypatch.setattr(bench, "CUDA", FakeCuda)
+    monkeypatch.setattr(csr, "_time_ms", lambda fn, reps, device: (fn(), 1.0)[1])
+    monkeypatch.setattr(torch, "Generator", lambda device=None: torch._C.Generator())     # make_graph asks for a device generator
+    monkeypatch.setitem(bench.WORKLOADS, "hm", (300, 120, 4000))
+    monkeypatch.setitem(bench.HETERO_SIZES, "hetero_s", (600, 40, 90, 30))
+    monkeypatch.setattr(bench, "CPU_SAMPLE_SCALE", 2)
+    for k in ("WORLD_SIZE", "RANK", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    args = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="ours", workload=workload, degree="powerlaw", dim=64, layers=3, batch=64,
+                              degree_order=False, no_cpu_baseline=False, no_autotune=False, graph=False, exchange="nccl",
+                              schedule="layer", hetero_aggr="add", project_first=False)
+    (bench.run_hetero if workload.startswith("hetero") else bench.run_ours)(args)
+    line = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 2 and line["gpu_launches"] > 0 and math.isfinite(line["value"]) and line["value"] > 0
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["achieved"] > 0
+    assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["kind"] == "port"
+    assert "workload" in line["config"] and math.isfinite(line["loss"])
+    if workload == "hm":
+        tuned = line["config"]["spmm_variant"]
+        assert "error" not in tuned and tuned["forward"]["variant"] in csr.AUTOTUNE_CANDIDATES and not tuned["rejected"], tuned
