@@ -33,6 +33,8 @@ class CUDA:
     synchronize = staticmethod(lambda: torch.cuda.synchronize())
     empty_cache = staticmethod(lambda: torch.cuda.empty_cache())
     pin = staticmethod(lambda t: t.pin_memory())
+    backend = "nccl"            # torch.distributed backend of the multi-GPU runs
+    sharded_ops = None          # None: dist.ShardedLightGCN builds its own CudaOps
 
     @staticmethod
     def device(local: int) -> torch.device:
@@ -202,7 +204,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     dev = CUDA.device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group(CUDA.backend, **({"device_id": dev} if CUDA.backend == "nccl" else {}))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
 
@@ -245,7 +247,8 @@ def run_ours(args):
     else:
         from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
         torch.manual_seed(0)
-        eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule, exchange=args.exchange)
+        eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule, exchange=args.exchange,
+                              ops=CUDA.sharded_ops() if CUDA.sharded_ops else None)
         if not args.no_autotune:
             try:
                 tuned = eng.autotune()                        # per rank; rank 0's choice is reported

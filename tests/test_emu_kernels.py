@@ -270,3 +270,54 @@ def test_bench_script_logic_dry_run(cuda_dev, monkeypatch, capsys, workload):
     if workload == "hm":
         tuned = line["config"]["spmm_variant"]
         assert "error" not in tuned and tuned["forward"]["variant"] in csr.AUTOTUNE_CANDIDATES and not tuned["rejected"], tuned
+
+
+def _bench_rank(rank, world, port, out_dir):
+    import argparse
+    import contextlib
+    import io
+    import os
+    import time
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    import bench
+    from laplace_gnn_recommendation_b200 import csr
+    from tests.test_dist_gloo import make_emu_ops
+
+    class FakeCuda:
+        available = staticmethod(lambda: True)
+        event = staticmethod(_WallEvent)
+        synchronize = staticmethod(lambda: None)
+        empty_cache = staticmethod(lambda: None)
+        pin = staticmethod(lambda t: t)
+        device = staticmethod(lambda local: torch.device("cpu"))
+        backend = "gloo"
+        sharded_ops = staticmethod(make_emu_ops)
+    bench.CUDA = FakeCuda
+    csr._time_ms = lambda fn, reps, device: (fn(), 1.0)[1]
+    torch.Generator = lambda device=None: torch._C.Generator()
+    bench.WORKLOADS["hm"] = (300, 120, 4000)
+    args = argparse.Namespace(gpus=world, steps=2, warmup=3, impl="ours", workload="hm", degree="powerlaw", dim=64, layers=3, batch=64,
+                              degree_order=False, no_cpu_baseline=True, no_autotune=False, graph=False, exchange="nccl",
+                              schedule="layer", hetero_aggr="add", project_first=False)
+    buf = io.StringIO()
+    with emulated(), contextlib.redirect_stdout(buf):
+        bench.run_ours(args)
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write(buf.getvalue())
+
+
+def test_bench_script_logic_dry_run_two_ranks(tmp_path):
+    """The multi-GPU branch of bench.py (sharded engine, per-rank plan-time tuning, max-over-ranks timing, rank-0 JSON line) on
+    two gloo ranks with the emulated kernels."""
+    import json
+    import torch.multiprocessing as mp
+    from tests.emu import build_emu
+    from tests.test_dist_gloo import _free_port
+    build_emu.build()
+    mp.spawn(_bench_rank, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    out0, out1 = (open(tmp_path / f"rank{r}.txt").read() for r in range(2))
+    assert not [ln for ln in out1.splitlines() if ln.startswith("{")]                  # only rank 0 prints
+    line = json.loads([ln for ln in out0.splitlines() if ln.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0 and line["cpu_baseline"] is None
+    assert "users" in line["config"]["spmm_variant"] and "items" in line["config"]["spmm_variant"], line["config"]
+    assert line["e2e"]["value"] > 0 and line["roofline"]["launches_timed"] > 0 and line["gpu_launches"] > 0
