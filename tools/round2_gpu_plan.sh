@@ -28,6 +28,7 @@ case "${1:-single}" in
     T 300 python tools/train_lightgcn.py --style fused --iters 100 2>&1 | tail -1 | cut -c1-400
     T 200 python bench.py --steps 20 --warmup 5 --degree-order --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_degree_order.json
     T 600 python tools/sweep.py 2>&1 | tail -12
+    T 300 python tools/next_rows_bench.py 2>&1 | grep -v Warn > gpurun_out/next_rows.jsonl
     ;;
   dist2|dist4|dist8)
     n=${1#dist}
