@@ -33,6 +33,7 @@ class CUDA:
     synchronize = staticmethod(lambda: torch.cuda.synchronize())
     empty_cache = staticmethod(lambda: torch.cuda.empty_cache())
     pin = staticmethod(lambda t: t.pin_memory())
+    step_timer = None           # None: ShardedLightGCN.autotune_step times with CUDA events
     backend = "nccl"            # torch.distributed backend of the multi-GPU runs
     sharded_ops = None          # None: dist.ShardedLightGCN builds its own CudaOps
 
@@ -256,6 +257,14 @@ def run_ours(args):
                 for gv in eng.graphs():
                     gv.variant = None
                 tuned = {"error": repr(exc)[:300]}
+            if not args.graph:
+                # step form (host-filtered vs static-shape BPR section): result-checked on every rank, timed max-over-ranks;
+                # all ranks run the same candidates in the same order (ShardedLightGCN.autotune_step)
+                try:
+                    tuned["step_form"] = eng.autotune_step(ub, pb, nb, lam, timer=CUDA.step_timer)
+                except Exception as exc:
+                    eng.schedule, eng.static_batch = args.schedule, False
+                    tuned["step_form"] = {"error": repr(exc)[:300]}
         nnz = 2 * E
         if not args.graph:
             step = lambda: eng.fused_step(ub, pb, nb, lam)      # noqa: E731

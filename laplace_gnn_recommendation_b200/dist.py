@@ -301,6 +301,60 @@ class ShardedLightGCN:
                              rejected=g.autotune_report["rejected"])
         return out
 
+    def autotune_step(self, user_indices, pos_item_indices, neg_item_indices, lambda_val: float, reps: int = 5,
+                      candidates=((None, False), (None, True)), timer=None) -> dict:
+        """Plan-time choice of the step form on THIS machine: every candidate (schedule, static_batch) -- by default the
+        measured host-filtered step and the static-shape step (kernel-side owned-user filter, loss riding on the gradient
+        all-reduce, that all-reduce hidden behind the first backward SpMM) under the current schedule -- must reproduce the
+        first candidate's loss and gradients on the given batch on EVERY rank, and is then timed (barrier, CUDA events, max
+        over ranks); the fastest is kept.  Every rank runs the same candidates in the same order, so the collective sequence
+        stays matched.  Returns a report."""
+        inited = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.ops.group) > 1
+
+        def agree(value: float, op) -> float:
+            t = torch.tensor([value], dtype=torch.float64, device=self.device)
+            if inited:
+                dist.all_reduce(t, op=op, group=self.ops.group)
+            return float(t)
+
+        def default_timer(fn):
+            if inited:
+                dist.barrier(group=self.ops.group)
+            torch.cuda.synchronize(self.device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / reps
+        timer = timer or default_timer
+        keep = (self.schedule, self.static_batch)
+        report, ref, best, best_ms = {"ms": {}, "rejected": {}}, None, keep, float("inf")
+        for schedule, static in candidates:
+            schedule = schedule or keep[0]
+            if schedule == "merged" and self.g_all is None:
+                continue
+            key = f"{schedule}/{'static' if static else 'host-filtered'}"
+            self.schedule, self.static_batch = schedule, bool(static)
+            loss = self.fused_step(user_indices, pos_item_indices, neg_item_indices, lambda_val).clone()
+            grad = self.grad.clone()
+            if ref is None:
+                ref = (loss, grad)
+            else:
+                same = bool(torch.allclose(loss, ref[0], rtol=1e-5, atol=1e-7)) and \
+                    bool(torch.allclose(grad, ref[1], rtol=1e-4, atol=1e-6 * float(ref[1].abs().max()) + 1e-12))
+                if agree(1.0 if same else 0.0, dist.ReduceOp.MIN) < 0.5:
+                    report["rejected"][key] = "loss / gradients differ from the first candidate on at least one rank"
+                    continue
+            ms = agree(timer(lambda: self.fused_step(user_indices, pos_item_indices, neg_item_indices, lambda_val)), dist.ReduceOp.MAX)
+            report["ms"][key] = ms
+            if ms < best_ms:
+                best, best_ms = (schedule, bool(static)), ms
+        self.schedule, self.static_batch = best
+        report["chosen"] = {"schedule": best[0], "static_batch": best[1]}
+        return report
+
     @property
     def users_weight(self):
         return self.table[: self.Ug]

@@ -157,7 +157,13 @@ def _worker(rank, world, port, cases, out_dir):
                 eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=ops,
                                       init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
                 loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
-            torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(),
+                tuned = None
+                if ops_kind == "emu" and ci == len(cases) - 1:      # plan-time choice of the step form, once per world size
+                    import time
+                    tuned = eng.autotune_step(pb["u"], pb["p"], pb["n"], pb["lam"], candidates=((None, False), (None, True), ("pipelined", True)),
+                                              timer=lambda fn: (time.perf_counter(), fn(), time.perf_counter())[2] * 0 + 1.0 + rank)
+                    loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])      # the installed winner still computes the step
+            torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(), tuned=tuned,
                             bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -208,6 +214,10 @@ def test_sharded_step_equals_single_process_oracle(tmp_path, world):
             torch.testing.assert_close(o["grad"][Ug:], o_gi, **gtol)                    # identical on every rank
         for a, b in zip(outs[:-1], outs[1:]):
             assert a["hi"] == b["lo"], what
+        if outs[0]["tuned"] is not None:             # autotune_step: every rank reports the same, complete, rejection-free table
+            t0 = outs[0]["tuned"]
+            assert len(t0["ms"]) == 3 and not t0["rejected"] and all(o["tuned"] == t0 for o in outs), t0
+            assert all(v == float(world) for v in t0["ms"].values())          # max over ranks of the (1 + rank) the fake timer returns
 
 
 def test_balanced_bounds_and_local_block():

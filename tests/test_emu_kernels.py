@@ -293,6 +293,7 @@ def _bench_rank(rank, world, port, out_dir):
         device = staticmethod(lambda local: torch.device("cpu"))
         backend = "gloo"
         sharded_ops = staticmethod(make_emu_ops)
+        step_timer = staticmethod(lambda fn: (fn(), 1.0)[1])
     bench.CUDA = FakeCuda
     csr._time_ms = lambda fn, reps, device: (fn(), 1.0)[1]
     torch.Generator = lambda device=None: torch._C.Generator()
@@ -320,4 +321,6 @@ def test_bench_script_logic_dry_run_two_ranks(tmp_path):
     line = json.loads([ln for ln in out0.splitlines() if ln.startswith("{")][-1])
     assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0 and line["cpu_baseline"] is None
     assert "users" in line["config"]["spmm_variant"] and "items" in line["config"]["spmm_variant"], line["config"]
+    form = line["config"]["spmm_variant"]["step_form"]
+    assert len(form["ms"]) == 2 and not form["rejected"] and form["chosen"]["schedule"] == "layer", form
     assert line["e2e"]["value"] > 0 and line["roofline"]["launches_timed"] > 0 and line["gpu_launches"] > 0
