@@ -333,8 +333,10 @@ class ShardedLightGCN:
         report, ref, best, best_ms = {"ms": {}, "rejected": {}}, None, keep, float("inf")
         for schedule, static in candidates:
             schedule = schedule or keep[0]
-            if schedule == "merged" and self.g_all is None:
-                continue
+            if schedule == "merged" and self.g_all is None:      # the all-rows view (+ its plan and kernel choice) is built on demand
+                self.g_all = self.ops.row_view(self.g_full, 0, self.n)
+                if self.g_users.variant is not None:
+                    self.g_all.autotune(self.d, chunks=(DEFAULT_CHUNK, 256))
             key = f"{schedule}/{'static' if static else 'host-filtered'}"
             self.schedule, self.static_batch = schedule, bool(static)
             loss = self.fused_step(user_indices, pos_item_indices, neg_item_indices, lambda_val).clone()
