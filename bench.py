@@ -258,10 +258,10 @@ def run_ours(args):
                     gv.variant = None
                 tuned = {"error": repr(exc)[:300]}
             if not args.graph:
-                # step form (host-filtered vs static-shape BPR section, one merged launch per layer): result-checked on every rank, timed max-over-ranks;
+                # step form (host-filtered vs static-shape BPR section, pipelined exchange, one merged launch per layer): result-checked on every rank, timed max-over-ranks;
                 # all ranks run the same candidates in the same order (ShardedLightGCN.autotune_step)
                 try:
-                    forms = ((None, False), (None, True), ("merged", True)) if args.schedule == "layer" else ((None, False), (None, True))
+                    forms = ((None, False), (None, True), ("pipelined", True), ("merged", True)) if args.schedule == "layer" else ((None, False), (None, True))
                     tuned["step_form"] = eng.autotune_step(ub, pb, nb, lam, candidates=forms, timer=CUDA.step_timer)
                 except Exception as exc:
                     eng.schedule, eng.static_batch = args.schedule, False

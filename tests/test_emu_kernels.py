@@ -322,5 +322,5 @@ def test_bench_script_logic_dry_run_two_ranks(tmp_path):
     assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0 and line["cpu_baseline"] is None
     assert "users" in line["config"]["spmm_variant"] and "items" in line["config"]["spmm_variant"], line["config"]
     form = line["config"]["spmm_variant"]["step_form"]
-    assert len(form["ms"]) == 3 and not form["rejected"] and form["chosen"]["schedule"] in ("layer", "merged"), form
+    assert len(form["ms"]) == 4 and not form["rejected"] and form["chosen"]["schedule"] in ("layer", "pipelined", "merged"), form
     assert line["e2e"]["value"] > 0 and line["roofline"]["launches_timed"] > 0 and line["gpu_launches"] > 0
