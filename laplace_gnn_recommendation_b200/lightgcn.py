@@ -186,7 +186,10 @@ class LightGCN(nn.Module):
         Wu = self.users_emb.weight
         _lib.require_cuda(Wu)
         dev = Wu.device
-        gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr().transpose()      # build everything outside the capture
+        g = gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr()
+        g.transpose()                                                                   # build everything outside the capture
+        if _AUTOTUNE and g.variant is None:
+            self.autotune(edge_index)                                                   # ... including the plan-time tuning
         su, sp, sn = (torch.zeros(int(batch_size), dtype=torch.int64, device=dev) for _ in range(3))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
