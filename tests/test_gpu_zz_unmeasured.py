@@ -240,3 +240,54 @@ def test_acceptance_lightgcn_learns(cuda_dev):
     loss1, recall1, precision1, ndcg1 = lg.evaluation(model, test_ei, test_sp, [train_ei], 12, lam)
     assert loss1 < loss0 - 0.05, (loss0, loss1)                  # bpr_loss of the reference decreases (towards -inf) as ranking improves
     assert recall1 > max(2.0 * recall0, 0.5) and precision1 > precision0, (recall0, recall1, precision0, precision1)
+
+
+def test_acceptance_ranking_model_learns(cuda_dev):
+    """Acceptance test in the shape of tests/test_acceptance_movielens.py:16-60 for the ranking encoder-decoder: training.py's
+    step (forward on x_dict / edge_index_dict / edge_label_index, BCEWithLogitsLoss, backward, Adam) on a planted-community
+    batch must bring the loss under the reference's own threshold (loss < 0.5) and rank held-out positives above negatives."""
+    from laplace_gnn_recommendation_b200 import hetero
+    torch.manual_seed(42)
+    gen = torch.Generator().manual_seed(42)
+    Nc, Na, C, per_user, Fc, Fa = 160, 80, 4, 6, 12, 10
+    ccomm, acomm = torch.arange(Nc) % C, torch.arange(Na) % C
+    x = {"customer": torch.randn(Nc, Fc, generator=gen) * 0.3, "article": torch.randn(Na, Fa, generator=gen) * 0.3}
+    x["customer"][torch.arange(Nc), ccomm] += 1.0                       # the community is visible in the features
+    x["article"][torch.arange(Na), acomm] += 1.0
+    pos_u, pos_a = [], []
+    for u in range(Nc):
+        pool = torch.arange(Na)[acomm == ccomm[u]]
+        pick = pool[torch.randperm(pool.numel(), generator=gen)[:per_user]]
+        pos_u += [u] * per_user; pos_a += pick.tolist()
+    pos = torch.stack([torch.tensor(pos_u), torch.tensor(pos_a)])
+    hold = torch.rand(pos.shape[1], generator=gen) < 0.25                 # message edges vs label edges (LinkNeighborLoader split)
+    msg, lab_pos = pos[:, ~hold], pos[:, hold]
+    neg = torch.stack([torch.randint(0, Nc, (3 * lab_pos.shape[1],), generator=gen), torch.randint(0, Na, (3 * lab_pos.shape[1],), generator=gen)])
+    neg = neg[:, ccomm[neg[0]] != acomm[neg[1]]]                          # negatives: outside the customer's community
+    eli = torch.cat([lab_pos, neg], dim=1)
+    y = torch.cat([torch.ones(lab_pos.shape[1]), torch.zeros(neg.shape[1])])
+    ei = {hetero.EDGE_KEY: msg, hetero.REV_EDGE_KEY: msg.flip(0).contiguous()}
+    metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
+    model = lg.Encoder_Decoder_Model(
+        encoder_layers=lg.get_SAGEConv_layers(2, 32, 16, "mean"), decoder_layers=lg.get_linear_layers(2, 32, 32, 1), feature_info={},
+        metadata=metadata, embedding=False, heterogeneous_prop_agg_type="sum", batch_normalize=True, p_dropout_edges=None,
+        p_dropout_features=None).to(cuda_dev)
+    x = {k: v.to(cuda_dev) for k, v in x.items()}
+    ei = {k: v.to(cuda_dev) for k, v in ei.items()}
+    eli, y = eli.to(cuda_dev), y.to(cuda_dev)
+    crit = torch.nn.BCEWithLogitsLoss()
+    model.train()
+    first = float(crit(model(dict(x), ei, eli).view(-1), y).detach())     # also materialises the lazy input widths
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    for _ in range(60):                                                   # training.py:19-34
+        opt.zero_grad()
+        loss = crit(model(dict(x), ei, eli).view(-1), y)
+        loss.backward()
+        opt.step()
+    final = float(loss.detach())
+    assert final < 0.5 and final < 0.7 * first, (first, final)            # the reference's acceptance threshold: loss < 0.5
+    scores = model.infer(dict(x), ei, eli)                                # [users, max candidates], padded with -2^50
+    assert scores.dim() == 2 and scores.shape[0] == eli[0].unique().numel()
+    with torch.no_grad():
+        logits = model(dict(x), ei, eli).view(-1)
+    assert float(logits[y > 0.5].mean()) > float(logits[y < 0.5].mean()) + 1.0
