@@ -27,8 +27,9 @@ BUILD = os.path.join(HERE, "_build")
 GEN = os.path.join(BUILD, "gen")
 # LGB_EMU_ASAN=1: AddressSanitizer build (own output directory) for the memcheck run described in tests/emu/README.md
 ASAN = os.environ.get("LGB_EMU_ASAN") == "1"
-if ASAN:
-    BUILD = os.path.join(HERE, "_build", "asan")
+UBSAN = os.environ.get("LGB_EMU_UBSAN") == "1"      # -fsanitize=undefined build (signed overflow, misaligned vector access, bad shifts)
+if ASAN or UBSAN:
+    BUILD = os.path.join(HERE, "_build", "asan" if ASAN else "ubsan")
     GEN = os.path.join(BUILD, "gen")
 LIB_PATH = os.path.join(BUILD, "liblaplace_b200_emu.so")
 SKIP = set()
@@ -199,6 +200,8 @@ def build(force: bool = False) -> str:
              "-Wno-unused-variable", "-I", os.path.join(HERE, "include"), "-I", GEN]
     if ASAN:
         flags += ["-O1", "-fsanitize=address", "-fno-omit-frame-pointer"]
+    if UBSAN:
+        flags += ["-O1", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
 
     def compile_one(src):
         obj = os.path.join(BUILD, os.path.basename(src).rsplit(".", 1)[0] + ".o")
@@ -210,7 +213,7 @@ def build(force: bool = False) -> str:
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(8, len(units))) as ex:
         objs = list(ex.map(compile_one, units))
-    r = subprocess.run(["g++", "-shared", "-o", LIB_PATH + ".tmp"] + (["-fsanitize=address"] if ASAN else []) + objs + ["-lpthread"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared", "-o", LIB_PATH + ".tmp"] + (["-fsanitize=address"] if ASAN else []) + (["-fsanitize=undefined"] if UBSAN else []) + objs + ["-lpthread"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulator link failed:\n" + r.stdout + r.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)   # atomic: concurrent test workers never see a half-written library
