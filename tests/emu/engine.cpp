@@ -8,6 +8,7 @@
 //   * a shuffle that reads a lane which did not take part,
 //   * a block in which nobody can make progress (deadlock).
 // The error is sticky and surfaces through cudaGetLastError(), i.e. through the library's own LGB_LAUNCH_CHECK.
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -51,7 +52,7 @@ dim3 g_blockDim, g_gridDim;
 
 namespace {
 
-constexpr size_t STACK_BYTES = 128 * 1024;
+constexpr size_t STACK_BYTES = 256 * 1024;   // + one guard page below: an overflow faults instead of corrupting a neighbour
 constexpr int MAX_THREADS = 1024;
 
 enum Wait { RUNNABLE = 0, WAIT_WARP = 1, WAIT_BLOCK = 2, DONE = 3 };
@@ -134,9 +135,11 @@ void trampoline() {
 
 void prepare(Fiber& f) {
   if (!f.stack) {
-    void* m = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    const size_t guard = 4096;
+    void* m = mmap(nullptr, STACK_BYTES + guard, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (m == MAP_FAILED) { perror("cuda-emu: mmap"); abort(); }
-    f.stack = (char*)m;
+    mprotect(m, guard, PROT_NONE);
+    f.stack = (char*)m + guard;
   }
   uint64_t* sp = (uint64_t*)(((uintptr_t)f.stack + STACK_BYTES) & ~(uintptr_t)15);
   *--sp = 0;                        // return address slot of trampoline()'s imaginary caller (keeps rsp % 16 == 8 at entry)
@@ -144,6 +147,17 @@ void prepare(Fiber& f) {
   for (int i = 0; i < 6; ++i) *--sp = 0;   // rbp rbx r12 r13 r14 r15
   f.sp = sp;
   f.wait = RUNNABLE;
+}
+
+uint64_t g_rng = 0x9e3779b97f4a7c15ull;
+int order_mode_and_seed() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LGB_EMU_ORDER");
+    mode = (!e || !strncmp(e, "forward", 7)) ? 0 : (!strncmp(e, "reverse", 7) ? 1 : 2);
+    if (mode == 2 && e && strchr(e, ':')) g_rng ^= strtoull(strchr(e, ':') + 1, nullptr, 10) * 0xbf58476d1ce4e5b9ull;
+  }
+  return mode;
 }
 
 void run_block(int nthreads) {
@@ -167,9 +181,23 @@ void run_block(int nthreads) {
     f.tidx.z = t / (g_blockDim.x * g_blockDim.y);
     prepare(f);
   }
+  // Visiting order of the runnable threads (LGB_EMU_ORDER = forward | reverse | shuffle[:seed]).  Correct kernels cannot
+  // tell the difference: anything that communicates through shared or global memory without the barrier / collective it
+  // needs computes something else under another order -- a cheap race fuzzer for code the lockstep order would let pass.
+  const int order_mode = order_mode_and_seed();
+  uint64_t& rng = g_rng;
+  static std::vector<int> order;
+  order.resize(nthreads);
+  for (int t = 0; t < nthreads; ++t) order[t] = order_mode == 1 ? nthreads - 1 - t : t;
   while (g_block_alive > 0 && !g_abort) {
     bool ran = false;
-    for (int t = 0; t < nthreads && !g_abort; ++t) {
+    if (order_mode == 2)
+      for (int t = nthreads - 1; t > 0; --t) {          // Fisher-Yates with an xorshift generator, new order every pass
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[t], order[(int)(rng % (uint64_t)(t + 1))]);
+      }
+    for (int oi = 0; oi < nthreads && !g_abort; ++oi) {
+      const int t = order[oi];
       Fiber& f = g_fibers[t];
       if (f.wait == DONE) continue;
       if (f.wait == WAIT_WARP && g_warps[t >> 5].gen == f.wait_gen) continue;
@@ -206,9 +234,19 @@ void launch(dim3 grid, dim3 block, body_fn fn, void* arg) {
   g_blockDim = block;
   g_gridDim = grid;
   g_abort = false;
+  // blocks of a grid run in LGB_EMU_ORDER too (forward / reverse / a random cyclic stride): hardware promises no order
+  const int mode = order_mode_and_seed();
+  uint64_t stride = 1, offset = 0;
+  if (mode == 2 && grid.x > 2) {
+    g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17;
+    offset = g_rng % grid.x;
+    stride = 1 + (g_rng >> 20) % (grid.x - 1);
+    while (std::__gcd<uint64_t>(stride, grid.x) != 1) ++stride;      // coprime stride = a permutation of 0..grid.x-1
+  }
   for (unsigned bz = 0; bz < grid.z && !g_abort; ++bz)
     for (unsigned by = 0; by < grid.y && !g_abort; ++by)
-      for (unsigned bx = 0; bx < grid.x && !g_abort; ++bx) {
+      for (unsigned i = 0; i < grid.x && !g_abort; ++i) {
+        const unsigned bx = mode == 0 ? i : (mode == 1 ? grid.x - 1 - i : (unsigned)((offset + (uint64_t)i * stride) % grid.x));
         g_blockIdx.x = bx; g_blockIdx.y = by; g_blockIdx.z = bz;
         run_block((int)nthreads);
       }
