@@ -71,6 +71,21 @@ def emulated():
     patch(_lib, "_lib", lib)
     patch(loader, "_device_for", lambda t: t.device)
     patch(torch.cuda, "device", _NullDeviceGuard)
+    # initcheck: every torch.empty* allocation made while emulating is poisoned (NaN / a large bit pattern), so a kernel or
+    # host path that reads memory nobody wrote yields NaNs or wild indices and fails its parity test
+    real_empty, real_empty_like = torch.empty, torch.empty_like
+
+    def poison(t):
+        if t.numel():
+            if t.dtype.is_floating_point:
+                t.fill_(float("nan"))
+            elif t.dtype in (torch.int32, torch.int64):
+                t.fill_(0x7A7A7A7A)
+            elif t.dtype == torch.uint8:
+                t.fill_(0xAB)
+        return t
+    patch(torch, "empty", lambda *a, **k: poison(real_empty(*a, **k)))
+    patch(torch, "empty_like", lambda *a, **k: poison(real_empty_like(*a, **k)))
     try:
         yield torch.device("cpu")
     finally:

@@ -232,7 +232,7 @@ def test_acceptance_lightgcn_learns(cuda_dev):
     model.eval()
     loss0, recall0, precision0, _ = lg.evaluation(model, test_ei, test_sp, [train_ei], 12, lam)
     model.train()
-    for it in range(150):
+    for it in range(100):
         u, p, n = (t.to(cuda_dev) for t in lg.sample_mini_batch(128, train_ei))
         model.fused_step(train_sp, u, p, n, lam)
         opt.step()
