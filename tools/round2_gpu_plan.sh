@@ -4,6 +4,8 @@
 #   gpurun --timeout 900 -- 'bash tools/round2_gpu_plan.sh single'
 #   gpurun --gpus 2 --timeout 600 -- 'bash tools/round2_gpu_plan.sh dist2'
 #   gpurun --gpus 8 --timeout 600 -- 'bash tools/round2_gpu_plan.sh dist8'
+#   gpurun --timeout 1800 -- 'bash tools/round2_gpu_plan.sh ncu'        (then: python tools/ncu_summary.py gpurun_out/spmm_r2.ncu-rep)
+#   gpurun --timeout 1000 -- 'bash tools/round2_gpu_plan.sh sanitize'
 set -u
 mkdir -p gpurun_out
 T() { timeout "$@"; echo "[rc=$?] ${*:2}" | cut -c1-160; }
@@ -29,6 +31,22 @@ case "${1:-single}" in
     T 200 python bench.py --steps 20 --warmup 5 --degree-order --no-cpu-baseline | tail -1 > gpurun_out/bench_hm_degree_order.json
     T 600 python tools/sweep.py 2>&1 | tail -12
     T 300 python tools/next_rows_bench.py 2>&1 | grep -v Warn > gpurun_out/next_rows.jsonl
+    ;;
+  ncu)
+    # the top kernel, once: launch list + full capture (B200_PROFILING.md: plain run first, one ncu tool per call)
+    # (no T wrapper here: ncu may only run if the plain run of the same command line exited 0)
+    B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-autotune"
+    timeout 200 $B > gpurun_out/plain_r2.log 2>&1 &&
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv \
+        $B > gpurun_out/ncu_launches_r2.log 2>&1 &&
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:spmm_ -s 6 -c 4 -o gpurun_out/spmm_r2 \
+        $B > gpurun_out/ncu_full_r2.log 2>&1
+    echo "[rc=$?] ncu captures"
+    ;;
+  sanitize)
+    # memcheck of the small parity cases (one compute-sanitizer tool per call)
+    T 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_lightgcn.py -q -x \
+        -k "csr_build or spmm_vs_oracle or lightgcn_against_oracle or bpr_against or topk_against_reference" 2>&1 | tail -15
     ;;
   dist2|dist4|dist8)
     n=${1#dist}
