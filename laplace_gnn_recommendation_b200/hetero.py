@@ -197,6 +197,11 @@ def _fan_in(outs: List[torch.Tensor], aggr: str) -> torch.Tensor:
     return torch.div(out, n) if (aggr == "mean" and n > 1) else out
 
 
+def _is_flip_of(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """a == b.flip(0), entry for entry (one fused comparison; the bool read-back is the only host sync of the batch set-up)."""
+    return bool(torch.equal(a[0], b[1]) and torch.equal(a[1], b[0]))
+
+
 class HeteroEncoder(nn.Module):
     """``to_hetero(GNNEncoder(...), metadata, aggr)``: one copy of every conv layer per edge type
     (sub-module names ``layers.<i>.<src>__<rel>__<dst>`` as PyG generates them), fan-in per destination."""
@@ -214,8 +219,16 @@ class HeteroEncoder(nn.Module):
 
     def forward(self, x_dict: Dict[str, torch.Tensor], edge_index_dict) -> Dict[str, torch.Tensor]:
         x = dict(x_dict)
-        # one CSR (+ lazily its transpose) per edge type per batch, shared by all layers and the backward
-        graphs = {et: build_edge_csr(edge_index_dict[et], x[et[0]].shape[0], x[et[2]].shape[0]) for et in self.edge_types}
+        # one CSR (+ lazily its transpose) per edge type per batch, shared by all layers and the backward; an edge type
+        # that is the exact flip of another one (``rev_buys`` of ``buys``, what ToUndirected produces) IS that one's
+        # transpose, so the pair costs two sorts instead of four
+        graphs: Dict[tuple, DeviceCSR] = {}
+        for et in self.edge_types:
+            ei = edge_index_dict[et]
+            mate = next((o for o in graphs if o[0] == et[2] and o[2] == et[0]
+                         and edge_index_dict[o].shape == ei.shape and _is_flip_of(ei, edge_index_dict[o])), None)
+            graphs[et] = graphs[mate].transpose() if mate is not None else \
+                build_edge_csr(ei, x[et[0]].shape[0], x[et[2]].shape[0])
         for li, convs in enumerate(self.layers):
             last = li == len(self.layers) - 1
             if not last and self.p_dropout_features is not None:

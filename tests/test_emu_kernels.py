@@ -326,3 +326,4 @@ def test_bench_script_logic_dry_run_two_ranks(tmp_path):
     assert line["e2e"]["value"] > 0 and line["roofline"]["launches_timed"] > 0 and line["gpu_launches"] > 0
 test_acceptance_lightgcn_learns = TZ.test_acceptance_lightgcn_learns
 test_acceptance_ranking_model_learns = TZ.test_acceptance_ranking_model_learns
+test_reverse_edge_type_shares_the_transposed_csr = TZ.test_reverse_edge_type_shares_the_transposed_csr

@@ -291,3 +291,32 @@ def test_acceptance_ranking_model_learns(cuda_dev):
     with torch.no_grad():
         logits = model(dict(x), ei, eli).view(-1)
     assert float(logits[y > 0.5].mean()) > float(logits[y < 0.5].mean()) + 1.0
+
+
+def test_reverse_edge_type_shares_the_transposed_csr(cuda_dev, monkeypatch):
+    """An edge type that is the exact flip of another (rev_buys of buys) reuses that graph's transpose: one COO->CSR build
+    instead of two per batch, identical encoder output; a reverse type with different edges is built on its own."""
+    from laplace_gnn_recommendation_b200 import hetero
+    gen = torch.Generator().manual_seed(6)
+    Nc, Na, E = 50, 70, 600
+    e = torch.stack([torch.randint(0, Nc, (E,), generator=gen), torch.randint(0, Na, (E,), generator=gen)]).to(cuda_dev)
+    other = torch.stack([torch.randint(0, Na, (E,), generator=gen), torch.randint(0, Nc, (E,), generator=gen)]).to(cuda_dev)
+    x = {"customer": torch.randn(Nc, 12, generator=gen).to(cuda_dev), "article": torch.randn(Na, 9, generator=gen).to(cuda_dev)}
+    metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
+    torch.manual_seed(0)
+    enc = lg.to_hetero(hetero.GNNEncoder(lg.get_SAGEConv_layers(2, 16, 8, "mean"), None, None), metadata, aggr="sum").to(cuda_dev)
+    calls = []
+    real = hetero.build_edge_csr
+    monkeypatch.setattr(hetero, "build_edge_csr", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    z_shared = enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()})
+    assert len(calls) == 1
+    monkeypatch.setattr(hetero, "_is_flip_of", lambda a, b: False)           # force two independent builds of the same edges
+    z_own = enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()})
+    assert len(calls) == 3
+    for k in z_shared:
+        assert torch.equal(z_shared[k], z_own[k])                            # same arrays, same summation order: same bits
+    monkeypatch.undo()
+    calls.clear()
+    monkeypatch.setattr(hetero, "build_edge_csr", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: other})
+    assert len(calls) == 2
