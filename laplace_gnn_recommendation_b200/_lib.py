@@ -75,6 +75,7 @@ PROTOTYPES = {
     "lgb_edge_dot_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_edge_dot_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "lgb_topk_exclude": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "lgb_topk_exclude_tiled": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "lgb_neg_reject_mask": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_sort_keys_ws_bytes": (C.c_int, [c_i64, C.POINTER(c_sz)]),
     "lgb_edge_keys_sorted": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),

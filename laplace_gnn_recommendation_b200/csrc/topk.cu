@@ -43,6 +43,8 @@ __device__ __forceinline__ int block_excl_scan(int flag, int* warp_tot, int& tot
   return before + within;
 }
 
+// SCORED = true: score_ws already holds the scores of this block of users (topk_score_tile_kernel); only mask + select run.
+template <bool SCORED>
 __global__ void __launch_bounds__(TOPK_THREADS)
 topk_exclude_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi, const int64_t* __restrict__ users,
                     int64_t n_items, int d, const int32_t* __restrict__ seen_ptr, const int32_t* __restrict__ seen_idx,
@@ -62,22 +64,24 @@ topk_exclude_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi, 
   const int I = (int)n_items;
   const int keff = min(k, I);
 
-  for (int j = tid; j < d; j += TOPK_THREADS) su[j] = Wu[u * d + j];
-  __syncthreads();
-  for (int i = tid; i < I; i += TOPK_THREADS) {
-    const float* w = Wi + (size_t)i * d;
-    float s = 0.f;
-    if ((d & 3) == 0) {
-      for (int j = 0; j < d; j += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(w + j);
-        s = fmaf(su[j], v.x, s); s = fmaf(su[j + 1], v.y, s); s = fmaf(su[j + 2], v.z, s); s = fmaf(su[j + 3], v.w, s);
+  if (!SCORED) {
+    for (int j = tid; j < d; j += TOPK_THREADS) su[j] = Wu[u * d + j];
+    __syncthreads();
+    for (int i = tid; i < I; i += TOPK_THREADS) {
+      const float* w = Wi + (size_t)i * d;
+      float s = 0.f;
+      if ((d & 3) == 0) {
+        for (int j = 0; j < d; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(w + j);
+          s = fmaf(su[j], v.x, s); s = fmaf(su[j + 1], v.y, s); s = fmaf(su[j + 2], v.z, s); s = fmaf(su[j + 3], v.w, s);
+        }
+      } else {
+        for (int j = 0; j < d; ++j) s = fmaf(su[j], w[j], s);
       }
-    } else {
-      for (int j = 0; j < d; ++j) s = fmaf(su[j], w[j], s);
+      ws[i] = s;
     }
-    ws[i] = s;
+    __syncthreads();
   }
-  __syncthreads();
   if (seen_ptr) {
     const int s0 = seen_ptr[u], s1 = seen_ptr[u + 1];
     for (int t = s0 + tid; t < s1; t += TOPK_THREADS) {
@@ -162,6 +166,54 @@ topk_exclude_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi, 
   }
 }
 
+// ---- user-tiled scoring ---------------------------------------------------------------------------------------
+// The one-CTA-per-user kernel re-reads the whole item table (27 MB at the H&M shape) from L2 for every user: 4 FMAs per
+// 16 bytes loaded.  Here a CTA scores TOPK_UT users at once: every item row is loaded ONCE per CTA and multiplied against
+// TOPK_UT user rows held in shared memory (broadcast reads), 4*TOPK_UT FMAs per 16 bytes -- the contraction becomes
+// FMA-bound on the CUDA cores instead of L2-bound.  Each score is the same fp32 FMA chain in ascending-d order as in the
+// per-user kernel (bit-identical scores, hence bit-identical ids); selection then runs per user on the score rows.
+constexpr int TOPK_UT = 8;
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_score_tile_kernel(const float* __restrict__ Wu, const float* __restrict__ Wi, const int64_t* __restrict__ users,
+                       int64_t n_users, int64_t n_items, int d, float* __restrict__ score_ws) {
+  __shared__ __align__(16) float su[TOPK_UT][TOPK_MAXD];
+  const int tid = threadIdx.x;
+  const int64_t u0 = (int64_t)blockIdx.x * TOPK_UT;
+  const int nu = (int)min((int64_t)TOPK_UT, n_users - u0);
+  for (int t = tid; t < TOPK_UT * d; t += TOPK_THREADS) {
+    const int uu = t / d, j = t - uu * d;
+    su[uu][j] = uu < nu ? Wu[users[u0 + uu] * d + j] : 0.f;
+  }
+  __syncthreads();
+  const int I = (int)n_items;
+  for (int i = tid; i < I; i += TOPK_THREADS) {
+    const float* w = Wi + (size_t)i * d;
+    float s[TOPK_UT];
+#pragma unroll
+    for (int uu = 0; uu < TOPK_UT; ++uu) s[uu] = 0.f;
+    if ((d & 3) == 0) {
+      for (int j = 0; j < d; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(w + j);
+#pragma unroll
+        for (int uu = 0; uu < TOPK_UT; ++uu) {
+          const float4 a = *reinterpret_cast<const float4*>(&su[uu][j]);
+          s[uu] = fmaf(a.x, v.x, s[uu]); s[uu] = fmaf(a.y, v.y, s[uu]); s[uu] = fmaf(a.z, v.z, s[uu]); s[uu] = fmaf(a.w, v.w, s[uu]);
+        }
+      }
+    } else {
+      for (int j = 0; j < d; ++j) {
+        const float wj = w[j];
+#pragma unroll
+        for (int uu = 0; uu < TOPK_UT; ++uu) s[uu] = fmaf(su[uu][j], wj, s[uu]);
+      }
+    }
+#pragma unroll
+    for (int uu = 0; uu < TOPK_UT; ++uu)
+      if (uu < nu) score_ws[(size_t)(u0 + uu) * n_items + i] = s[uu];
+  }
+}
+
 // ---- negative sampling support --------------------------------------------------------------
 __global__ void edge_keys_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t n,
                                  int64_t num_nodes, int64_t* __restrict__ keys) {
@@ -206,7 +258,28 @@ int lgb_topk_exclude(const float* Wu, const float* Wi, const int64_t* users, int
   LGB_REQUIRE(Wu && Wi && users && out_ids && score_ws, LGB_EINVAL, "lgb_topk_exclude: null pointer");
   int kp = 2;
   while (kp < k) kp <<= 1;
-  topk_exclude_kernel<<<(unsigned)n_users, TOPK_THREADS, 0, (cudaStream_t)stream>>>(
+  topk_exclude_kernel<false><<<(unsigned)n_users, TOPK_THREADS, 0, (cudaStream_t)stream>>>(
+      Wu, Wi, users, n_items, d, seen_ptr, seen_idx, k, kp, out_ids, out_scores, score_ws);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_topk_exclude_tiled(const float* Wu, const float* Wi, const int64_t* users, int64_t n_users, int64_t n_items,
+                           int32_t d, const int32_t* seen_ptr, const int32_t* seen_idx, int32_t k, int64_t* out_ids,
+                           float* out_scores, float* score_ws, void* stream) {
+  LGB_REQUIRE(n_users >= 0 && n_items > 0 && d > 0 && k > 0, LGB_EINVAL, "lgb_topk_exclude_tiled: bad size");
+  LGB_REQUIRE(k <= TOPK_MAXK, LGB_EINVAL, "lgb_topk_exclude_tiled: k=%d > %d", k, TOPK_MAXK);
+  LGB_REQUIRE(d <= TOPK_MAXD, LGB_EINVAL, "lgb_topk_exclude_tiled: d=%d > %d", d, TOPK_MAXD);
+  LGB_REQUIRE(n_items < (1ll << 31) - 1 && n_users < (1ll << 31) - 1, LGB_ERANGE, "lgb_topk_exclude_tiled: size exceeds int32");
+  if (n_users == 0) return LGB_OK;
+  LGB_REQUIRE(Wu && Wi && users && out_ids && score_ws, LGB_EINVAL, "lgb_topk_exclude_tiled: null pointer");
+  LGB_REQUIRE((((uintptr_t)Wi) & 15) == 0 || (d & 3) != 0, LGB_EINVAL, "lgb_topk_exclude_tiled: item table must be 16-byte aligned");
+  int kp = 2;
+  while (kp < k) kp <<= 1;
+  topk_score_tile_kernel<<<(unsigned)((n_users + TOPK_UT - 1) / TOPK_UT), TOPK_THREADS, 0, (cudaStream_t)stream>>>(
+      Wu, Wi, users, n_users, n_items, d, score_ws);
+  LGB_LAUNCH_CHECK();
+  topk_exclude_kernel<true><<<(unsigned)n_users, TOPK_THREADS, 0, (cudaStream_t)stream>>>(
       Wu, Wi, users, n_items, d, seen_ptr, seen_idx, k, kp, out_ids, out_scores, score_ws);
   LGB_LAUNCH_CHECK();
   return LGB_OK;

@@ -11,9 +11,18 @@ from typing import Dict, Iterable, List, Optional
 
 import torch
 
-from . import _lib
+import os
+
+from . import _lib, csr as _csr
 from ._lib import check, ptr, stream
 from .csr import DeviceCSR
+
+# scoring kernel of recommend_topk: "cta" = one CTA per user (measured in round 1), "tiled" = 8 users per CTA share every
+# item row (FMA-bound instead of L2-bound), "auto" = the first call with enough users runs BOTH on its first block, requires
+# bit-identical ids and scores, times them with CUDA events and keeps the faster for that (items, d, k) shape.
+TOPK_MODE = os.environ.get("LGB_TOPK_MODE", "auto")
+_TOPK_CHOICE: Dict[tuple, str] = {}
+_TOPK_AUTO_MIN_USERS = 64
 
 
 class SeenItems:
@@ -26,8 +35,9 @@ class SeenItems:
 
 
 def recommend_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, users: torch.Tensor, k: int,
-                   seen: Optional[SeenItems] = None, block: int = 2048, return_scores: bool = False):
-    """ids[len(users), k] (int64, -1 padded when fewer than k unseen items exist)."""
+                   seen: Optional[SeenItems] = None, block: int = 2048, return_scores: bool = False,
+                   mode: Optional[str] = None):
+    """ids[len(users), k] (int64, -1 padded when fewer than k unseen items exist).  ``mode``: see TOPK_MODE."""
     _lib.require_cuda(user_emb, item_emb, users)
     user_emb, item_emb = _lib.f32c(user_emb.detach()), _lib.f32c(item_emb.detach())
     users = _lib.i64c(users)
@@ -40,14 +50,38 @@ def recommend_topk(user_emb: torch.Tensor, item_emb: torch.Tensor, users: torch.
     block = max(1, min(block, (1 << 28) // max(I, 1)))
     ws = torch.empty(min(block, max(nu, 1)) * I, dtype=torch.float32, device=dev)
     lib = _lib.load()
-    with torch.cuda.device(dev):
-        for s in range(0, nu, block):
-            e = min(s + block, nu)
-            check(lib.lgb_topk_exclude(ptr(user_emb), ptr(item_emb), users[s:e].data_ptr(), e - s, I, d,
-                                       ptr(seen.csr.rowptr) if seen else None, ptr(seen.csr.colidx) if seen else None,
-                                       k, out[s:e].data_ptr(), scores[s:e].data_ptr() if scores is not None else None,
-                                       ptr(ws), stream()), "topk_exclude")
-            _lib.count_launch()
+    sp, si = (ptr(seen.csr.rowptr), ptr(seen.csr.colidx)) if seen else (None, None)
+
+    def run(fn, s, e, ids, sc):
+        with torch.cuda.device(dev):
+            check(fn(ptr(user_emb), ptr(item_emb), users[s:e].data_ptr(), e - s, I, d, sp, si, k, ids.data_ptr(),
+                     sc.data_ptr() if sc is not None else None, ptr(ws), stream()), "topk_exclude")
+
+    mode = mode or TOPK_MODE
+    if mode == "auto":
+        key = (I, d, k, str(dev))
+        if key not in _TOPK_CHOICE and nu >= _TOPK_AUTO_MIN_USERS:
+            e = min(block, nu)
+            ref_i, ref_s = torch.empty(e, k, dtype=torch.int64, device=dev), torch.empty(e, k, dtype=torch.float32, device=dev)
+            got_i, got_s = torch.empty_like(ref_i), torch.empty_like(ref_s)
+            run(lib.lgb_topk_exclude, 0, e, ref_i, ref_s)
+            try:
+                run(lib.lgb_topk_exclude_tiled, 0, e, got_i, got_s)
+                same = torch.equal(ref_i, got_i) and torch.equal(ref_s, got_s)
+            except RuntimeError:                       # e.g. an item table that is not 16-byte aligned
+                same = False
+            if same:
+                t_cta = _csr._time_ms(lambda: run(lib.lgb_topk_exclude, 0, e, ref_i, ref_s), 2, dev)
+                t_tiled = _csr._time_ms(lambda: run(lib.lgb_topk_exclude_tiled, 0, e, got_i, got_s), 2, dev)
+                _TOPK_CHOICE[key] = "tiled" if t_tiled < t_cta else "cta"
+            else:                                      # never expected: same FMA chains; keep the measured kernel
+                _TOPK_CHOICE[key] = "cta"
+        mode = _TOPK_CHOICE.get(key, "cta")
+    fn = lib.lgb_topk_exclude_tiled if mode == "tiled" else lib.lgb_topk_exclude
+    for s in range(0, nu, block):
+        e = min(s + block, nu)
+        run(fn, s, e, out[s:e], scores[s:e] if scores is not None else None)
+        _lib.count_launch(2 if mode == "tiled" else 1)
     return (out, scores) if return_scores else out
 
 

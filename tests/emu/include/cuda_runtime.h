@@ -26,6 +26,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 // ---- vector types ---------------------------------------------------------------------------------------
 struct alignas(16) float4 { float x, y, z, w; };

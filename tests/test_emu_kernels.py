@@ -327,3 +327,4 @@ def test_bench_script_logic_dry_run_two_ranks(tmp_path):
 test_acceptance_lightgcn_learns = TZ.test_acceptance_lightgcn_learns
 test_acceptance_ranking_model_learns = TZ.test_acceptance_ranking_model_learns
 test_reverse_edge_type_shares_the_transposed_csr = TZ.test_reverse_edge_type_shares_the_transposed_csr
+test_topk_tiled_scoring_is_bit_identical = TZ.test_topk_tiled_scoring_is_bit_identical

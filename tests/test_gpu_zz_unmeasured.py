@@ -320,3 +320,25 @@ def test_reverse_edge_type_shares_the_transposed_csr(cuda_dev, monkeypatch):
     monkeypatch.setattr(hetero, "build_edge_csr", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
     enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: other})
     assert len(calls) == 2
+
+
+@pytest.mark.parametrize("k,I,d,U", [(12, 3706, 64, 70), (256, 3706, 64, 33), (12, 500, 32, 64), (1000, 1200, 16, 9), (5, 3, 8, 17),
+                                     (12, 300, 6, 20)])
+def test_topk_tiled_scoring_is_bit_identical(cuda_dev, k, I, d, U):
+    """lgb_topk_exclude_tiled (8 users per CTA share every item row) returns exactly the ids AND scores of the one-CTA-per-user
+    kernel: the same fp32 FMA chains in the same order, only the loop nest differs."""
+    gen = torch.Generator().manual_seed(k * 7 + I)
+    Wu, Wi = torch.randn(U, d, generator=gen).to(cuda_dev), torch.randn(I, d, generator=gen).to(cuda_dev)
+    excl = torch.stack([torch.randint(0, U, (U * 15,), generator=gen), torch.randint(0, I, (U * 15,), generator=gen)]).to(cuda_dev)
+    seen = lg.SeenItems(excl, U, I)
+    users = torch.randperm(U, generator=gen).to(cuda_dev)
+    a_i, a_s = lg.recommend_topk(Wu, Wi, users, k, seen, return_scores=True, mode="cta")
+    b_i, b_s = lg.recommend_topk(Wu, Wi, users, k, seen, return_scores=True, mode="tiled")
+    assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s)
+    c_i = lg.recommend_topk(Wu, Wi, users, k, None, mode="tiled", block=16)            # several blocks, no exclusion list
+    assert torch.equal(c_i, lg.recommend_topk(Wu, Wi, users, k, None, mode="cta"))
+    if U >= 64:                                                                        # "auto" settles on one of the two
+        from laplace_gnn_recommendation_b200 import topk
+        topk._TOPK_CHOICE.clear()
+        assert torch.equal(lg.recommend_topk(Wu, Wi, users, k, seen, mode="auto"), a_i)
+        assert list(topk._TOPK_CHOICE.values())[0] in ("cta", "tiled")
