@@ -59,10 +59,11 @@ def main():
         users, items = make_graph(U, I, E, "powerlaw", 1234, dev)
         seen = lg.SeenItems(torch.stack([users, items]), U, I)
         who = torch.randint(0, U, (topk_users,), device=dev)
-        for k in (12, 256):
+        for k, mode in ((12, "cta"), (12, "tiled"), (256, "cta"), (256, "tiled")):
             kk = min(k, I)
-            ms = timeit(lambda: lg.recommend_topk(Wu, Wi, who, kk, seen), reps=5, warmup=2)
-            print(json.dumps({"row": "f2 score + top-k with exclusion", "k": kk, "users": topk_users, "ms": ms,
+            ms = timeit(lambda: lg.recommend_topk(Wu, Wi, who, kk, seen, mode=mode), reps=5, warmup=2)
+            print(json.dumps({"row": "f2 score + top-k with exclusion", "scoring": mode, "k": kk, "users": topk_users, "ms": ms,
+                              "fp32_TFLOPs": 2.0 * topk_users * I * d / 1e9 / ms,
                               "users_per_s": topk_users / (ms * 1e-3), "item_table_GBps": topk_users * I * d * 4 / 1e6 / ms,
                               "all_users_estimate_s": U / (topk_users / (ms * 1e-3))}), flush=True)
 
