@@ -22,7 +22,7 @@ from .csr import DeviceCSR
 # bit-identical ids and scores, times them with CUDA events and keeps the faster for that (items, d, k) shape.
 TOPK_MODE = os.environ.get("LGB_TOPK_MODE", "auto")
 _TOPK_CHOICE: Dict[tuple, str] = {}
-_TOPK_AUTO_MIN_USERS = 64
+_TOPK_AUTO_MIN_USERS = 256      # smaller calls stay on the per-user kernel (nothing to gain, and no probing cost)
 
 
 class SeenItems:

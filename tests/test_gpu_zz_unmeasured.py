@@ -340,5 +340,10 @@ def test_topk_tiled_scoring_is_bit_identical(cuda_dev, k, I, d, U):
     if U >= 64:                                                                        # "auto" settles on one of the two
         from laplace_gnn_recommendation_b200 import topk
         topk._TOPK_CHOICE.clear()
-        assert torch.equal(lg.recommend_topk(Wu, Wi, users, k, seen, mode="auto"), a_i)
-        assert list(topk._TOPK_CHOICE.values())[0] in ("cta", "tiled")
+        keep, topk._TOPK_AUTO_MIN_USERS = topk._TOPK_AUTO_MIN_USERS, 32
+        try:
+            assert torch.equal(lg.recommend_topk(Wu, Wi, users, k, seen, mode="auto"), a_i)
+            assert list(topk._TOPK_CHOICE.values())[0] in ("cta", "tiled")
+        finally:
+            topk._TOPK_AUTO_MIN_USERS = keep
+            topk._TOPK_CHOICE.clear()
