@@ -129,7 +129,8 @@ typedef struct lgb_csr {
  * row, unroll 8), 2/3 = software-pipelined persistent warps, 4..6, 12 = warp per row at other unroll / occupancy points,
  * 7..11 = cp.async rings, 13..15 = sub-warp rows at other unroll depths, 16 = sub-warp rows + one CTA per slice of a long
  * row, 17 = the 64-bit-index family that tables with n_cols*d/4 >= 2^31 elements get automatically,
- * 18 = sub-warp rows + L2 prefetch of the epilogue operands and double-buffered (col,val) batches, 19 = 16 + 18,
+ * 18 = sub-warp rows + L2 prefetch of the epilogue operands, double-buffered (col,val) batches and an L2 evict_first
+ * policy on those streamed loads, 19 = 16 + 18,
  * 20..22 (d in 33..64) = four rows per warp: 8 lanes x 2 float4 per row, with CTA-wide slices (22: + the prefetches of 18).  Every variant computes the same operator (rtol 1e-5); summation order inside a row differs between families. */
 #define LGB_SPMM_VARIANT_SHIFT 4
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid,

@@ -61,6 +61,30 @@ __device__ __forceinline__ float4 ld_gather_f4(const float4* p) {
                : "l"(p));
   return v;
 }
+// The same streamed loads with an L2 eviction policy (createpolicy descriptor, folded into the load's memory descriptor):
+// read-once CSR arrays / epilogue operands marked evict_first leave the L2 to the gathered embedding rows.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int ld_stream_i32_hint(const int32_t* p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f32_hint(const float* p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
 // Ask L2 for a line that will be read later in this thread's dependent chain (no register, no scoreboard entry).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Streaming 128-bit store (written once, read by a later kernel).

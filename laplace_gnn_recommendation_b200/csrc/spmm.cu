@@ -108,8 +108,10 @@ __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int
     for (int q = 0; q < VPL; ++q) acc[q] = f4_add(acc[q], f4_shfl_xor(acc[q], off));
 }
 
-template <int G, int VPL>
+// EF: the epilogue operands (read once per launch) are loaded with the L2 evict_first policy.
+template <int G, int VPL, bool EF = false>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg, int lig, float4 (&acc)[VPL]) {
+  const uint64_t pol = EF ? l2_policy_evict_first() : 0;
   if (p.y_tail && r >= p.split_row) {   // multi-GPU item rows: partial sums go to the exchange buffer untouched
     float4* out = reinterpret_cast<float4*>(p.y_tail) + (size_t)(r - p.split_row) * p.d4;
 #pragma unroll
@@ -129,11 +131,17 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
       const float c = (float)max(deg, 1);
       y.x = __fdiv_rn(y.x, c); y.y = __fdiv_rn(y.y, c); y.z = __fdiv_rn(y.z, c); y.w = __fdiv_rn(y.w, c);
     }
-    if (p.resid) y = f4_add(y, ld_stream_f4(reinterpret_cast<const float4*>(p.resid) + rowoff + f));
+    if (p.resid) {
+      const float4* src = reinterpret_cast<const float4*>(p.resid) + rowoff + f;
+      y = f4_add(y, EF ? ld_stream_f4_hint(src, pol) : ld_stream_f4(src));
+    }
     if (p.Y) st_f4(reinterpret_cast<float4*>(p.Y) + rowoff + f, y);
     if (p.acc_out) {
       float4 a = y;
-      if (p.acc_in) a = f4_add(ld_stream_f4(reinterpret_cast<const float4*>(p.acc_in) + rowoff + f), y);
+      if (p.acc_in) {
+        const float4* src = reinterpret_cast<const float4*>(p.acc_in) + rowoff + f;
+        a = f4_add(EF ? ld_stream_f4_hint(src, pol) : ld_stream_f4(src), y);
+      }
       if (p.acc_div != 1.0f) {
         a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
         a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
@@ -455,16 +463,17 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     const uint32_t d4u = (uint32_t)d4;
     int c = 0, cn = 0;
     float wv = 0.f, wn = 0.f;
+    const uint64_t pol = PF ? l2_policy_evict_first() : 0;      // PF variants: streamed operands leave L2 to the gathered rows
     if (PF && lig < deg) {                         // batch 0 of the (col,val) pairs
-      c = ld_stream_i32(p.colidx + s + lig);
-      wv = p.val ? ld_stream_f32(p.val + s + lig) : 1.f;
+      c = ld_stream_i32_hint(p.colidx + s + lig, pol);
+      wv = p.val ? ld_stream_f32_hint(p.val + s + lig, pol) : 1.f;
     }
     for (int base = 0; base < maxdeg; base += G) {
       if (PF) {                                    // the NEXT batch is requested before this one is consumed
         cn = 0; wn = 0.f;
         if (base + G + lig < deg) {
-          cn = ld_stream_i32(p.colidx + s + base + G + lig);
-          wn = p.val ? ld_stream_f32(p.val + s + base + G + lig) : 1.f;
+          cn = ld_stream_i32_hint(p.colidx + s + base + G + lig, pol);
+          wn = p.val ? ld_stream_f32_hint(p.val + s + base + G + lig, pol) : 1.f;
         }
       } else {
         c = 0; wv = 0.f;
@@ -500,7 +509,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
       }
       if (PF) { c = cn; wv = wn; }
     }
-    if (r >= 0 && !is_long) epilogue_row<G, VPL>(p, r, e - s, lig, acc);
+    if (r >= 0 && !is_long) epilogue_row<G, VPL, PF>(p, r, e - s, lig, acc);
     return;
   }
   // mixed / longer rows: the whole warp walks the NG rows one after the other

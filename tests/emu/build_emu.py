@@ -44,6 +44,10 @@ ASM_BODIES = {
     "red_add_f4": "p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w;",
     "cp_async_16": "*reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);",
     "prefetch_l2": "",
+    "l2_policy_evict_first": "return 0;",
+    "ld_stream_i32_hint": "return *p;",
+    "ld_stream_f32_hint": "return *p;",
+    "ld_stream_f4_hint": "return *p;",
     "cp_async_commit": "",
     "cp_async_wait": "",
     # NVSwitch multicast (csrc/peer.cu): the "multicast address" is a key registered with emu_multicast_bind(); a load-reduce
