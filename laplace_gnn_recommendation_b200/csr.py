@@ -24,9 +24,9 @@ DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
 
 
 # candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
-# the warp-per-row kernel it replaced, the sub-warp kernel at gather-unroll 4, and the four-rows-per-warp forms (20, 22:
-# d in 33..64; for d <= 32 those numbers run the default)
-AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13, 20, 22)
+# the warp-per-row kernel it replaced, the sub-warp kernel at gather-unroll 4, and the four-rows-per-warp forms (20, 22: d in 33..64;
+# 23, 25: with 256-bit loads, d = 64; other widths run the default under those numbers)
+AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13, 20, 22, 23, 25)
 
 
 def _time_ms(fn, reps: int, device) -> float:

@@ -87,6 +87,16 @@ __device__ __forceinline__ float4 ld_stream_f4_hint(const float4* p, uint64_t po
 }
 // Ask L2 for a line that will be read later in this thread's dependent chain (no register, no scoreboard entry).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 256-bit per-lane global accesses (new on sm_100: SASS LDG.E.256 / STG.E.256): 32 contiguous bytes of an embedding row in
+// ONE instruction, i.e. a 256-byte row with 8 lanes.  The address must be 32-byte aligned.
+struct f4x2 { float4 a, b; };
+__device__ __forceinline__ f4x2 ld_gather_f8(const float4* p) {
+  f4x2 v;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+               : "l"(p));
+  return v;
+}
 // Streaming 128-bit store (written once, read by a later kernel).
 __device__ __forceinline__ void st_f4(float4* p, const float4& v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

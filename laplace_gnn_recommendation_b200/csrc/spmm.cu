@@ -109,14 +109,16 @@ __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int
 }
 
 // EF: the epilogue operands (read once per launch) are loaded with the L2 evict_first policy.
-template <int G, int VPL, bool EF = false>
+// CONTIG: lane `lig` holds the VPL ADJACENT float4 lig*VPL .. lig*VPL+VPL-1 of the row (the 256-bit-load layout) instead of
+// the strided lig, lig+G, ...
+template <int G, int VPL, bool EF = false, bool CONTIG = false>
 __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg, int lig, float4 (&acc)[VPL]) {
   const uint64_t pol = EF ? l2_policy_evict_first() : 0;
   if (p.y_tail && r >= p.split_row) {   // multi-GPU item rows: partial sums go to the exchange buffer untouched
     float4* out = reinterpret_cast<float4*>(p.y_tail) + (size_t)(r - p.split_row) * p.d4;
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
-      const int f = lig + q * G;
+      const int f = CONTIG ? lig * VPL + q : lig + q * G;
       if (f < p.d4) st_f4(out + f, acc[q]);
     }
     return;
@@ -124,7 +126,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
   const size_t rowoff = (size_t)r * p.d4;
 #pragma unroll
   for (int q = 0; q < VPL; ++q) {
-    const int f = lig + q * G;
+    const int f = CONTIG ? lig * VPL + q : lig + q * G;
     if (f >= p.d4) continue;
     float4 y = acc[q];
     if (p.mean) {
@@ -369,10 +371,13 @@ constexpr int SUBW_MAX = 64;
 // VPL > 1 (variants 20/21, measurement pending): a lane holds VPL float4 of the row, so a row needs only G = d/(4*VPL) lanes
 // and a warp runs 32/G row chains at once (d = 64: G = 8, VPL = 2 -> four rows per warp, half the shuffles and address
 // arithmetic per non-zero).
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1>
+// W256 (variants 23-25, d = 64 only, measurement pending): the short-row path fetches a lane's two float4 with ONE 256-bit
+// load (sm_100's LDG.E.256) -- a 256-byte row = one load instruction of 8 lanes, four rows per warp-level load.
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
   static_assert(G % UNROLL == 0, "the unrolled gather step must divide the lane-group width");
   static_assert(D4C == 0 || D4C == G * VPL, "a compile-time d/4 must fill the lane group exactly");
+  static_assert(!W256 || (VPL == 2 && D4C == 2 * G), "256-bit gathers need two adjacent float4 per lane and an exact fit");
   constexpr int NG = 32 / G;
   const int lane = threadIdx.x & 31;
   const int grp = lane / G, lig = lane % G;
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   if (PF && r >= 0 && !(p.y_tail && r >= p.split_row)) {   // one request per 128-byte line of the epilogue operands
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
-      const int f = lig + q * G;
+      const int f = W256 ? lig * VPL + q : lig + q * G;
       if ((f & 7) == 0 && f < d4) {
         const size_t o = (size_t)r * d4 + f;
         if (p.acc_in) prefetch_l2(reinterpret_cast<const float4*>(p.acc_in) + o);
@@ -495,21 +500,29 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
           ww[u] = __shfl_sync(FULL_MASK, wv, k, G);
           ok[u] = k < cnt;
           const uint32_t row = (uint32_t)cc * d4u;
+          if (W256) {
+            if (ok[u]) {
+              const f4x2 t = ld_gather_f8(X4 + (row + (uint32_t)(lig * 2)));
+              v[u][0] = t.a;
+              v[u][VPL - 1] = t.b;
+            }
+          } else {
 #pragma unroll
-          for (int q = 0; q < VPL; ++q) {
-            const int f = lig + q * G;
-            if (ok[u] && f < d4) v[u][q] = ld_gather_f4(X4 + (row + (uint32_t)f));
+            for (int q = 0; q < VPL; ++q) {
+              const int f = lig + q * G;
+              if (ok[u] && f < d4) v[u][q] = ld_gather_f4(X4 + (row + (uint32_t)f));
+            }
           }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
           for (int q = 0; q < VPL; ++q)
-            if (ok[u] && lig + q * G < d4) f4_fma(acc[q], ww[u], v[u][q]);
+            if (ok[u] && (W256 || lig + q * G < d4)) f4_fma(acc[q], ww[u], v[u][q]);
       }
       if (PF) { c = cn; wv = wn; }
     }
-    if (r >= 0 && !is_long) epilogue_row<G, VPL, PF>(p, r, e - s, lig, acc);
+    if (r >= 0 && !is_long) epilogue_row<G, VPL, PF, W256>(p, r, e - s, lig, acc);
     return;
   }
   // mixed / longer rows: the whole warp walks the NG rows one after the other
@@ -530,7 +543,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1>
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream);
 
 // d/4 == G*VPL (d = 64 with G = 16, d = 32 with G = 8) gets the kernel specialised on that constant
@@ -540,7 +553,7 @@ static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
                          : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0, PF, VPL>(p, stream);
 }
 
-template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF, int VPL>
+template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF, int VPL, bool W256>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   constexpr int NG = 32 / G;
   const int64_t row_warps = (p.n_rows + NG - 1) / NG;
@@ -548,7 +561,7 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   if (warps > 0) {
     const int64_t blocks = WIDE ? p.n_tasks + (row_warps + SPMM_WARPS - 1) / SPMM_WARPS : (warps + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL, W256><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
@@ -946,6 +959,10 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
       case 20: return launch_subwarp<8, 1, 16, true, false, 2>(p, stream);  // four rows per warp (8 lanes x 2 float4), unroll 1
       case 21: return launch_subwarp<8, 2, 12, true, false, 2>(p, stream);  // four rows per warp, unroll 2 (48 warps / SM)
       case 22: return launch_subwarp<8, 1, 16, true, true, 2>(p, stream);   // 20 + chain-shortening prefetches
+      // 23-25: the same with ONE 256-bit load per lane and non-zero (LDG.E.256, new on sm_100); d = 64 exactly
+      case 23: return d4 == 16 ? launch_subwarp_impl<8, 1, 16, true, 16, false, 2, true>(p, stream) : launch_subwarp<16, 2, 16>(p, stream);
+      case 24: return d4 == 16 ? launch_subwarp_impl<8, 2, 12, true, 16, false, 2, true>(p, stream) : launch_subwarp<16, 2, 16>(p, stream);
+      case 25: return d4 == 16 ? launch_subwarp_impl<8, 1, 16, true, 16, true, 2, true>(p, stream) : launch_subwarp<16, 2, 16>(p, stream);
       default: return launch_subwarp<16, 2, 16>(p, stream);
     }
   }

@@ -59,7 +59,7 @@ test_batch_sized_aggregation_properties = TH.test_batch_sized_aggregation_proper
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d):
-    TZ.test_spmm_kernel_variants_agree(cuda_dev, d, n=700, nnz=14000)   # smaller than on the GPU: 23 variants x 4 launches
+    TZ.test_spmm_kernel_variants_agree(cuda_dev, d, n=700, nnz=14000)   # smaller than on the GPU: 26 variants x 4 launches
 
 
 def test_spmm_empty_and_single_heavy_row(cuda_dev):

@@ -27,6 +27,8 @@ def test_spmm_wide_slice_variant_vs_oracle(cuda_dev, d, chunk):
     if d > 32:                       # four rows per warp (8 lanes x 2 float4): d in 33..64 only
         _spmm_vs_oracle(cuda_dev, d, chunk, variant=20)
         _spmm_vs_oracle(cuda_dev, d, chunk, variant=22)
+        _spmm_vs_oracle(cuda_dev, d, chunk, variant=23)     # ... with one 256-bit load per lane (d = 64; other widths: default)
+        _spmm_vs_oracle(cuda_dev, d, chunk, variant=25)
 
 
 @pytest.mark.parametrize("d", [8, 64, 84, 128, 256])
@@ -36,7 +38,7 @@ def test_spmm_64bit_index_family_vs_oracle(cuda_dev, d):
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
-    """All 23 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    """All 26 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
     cp.async rings, sub-warp rows, CTA-wide slices, 64-bit element indexing) compute the same operator with the same fused
     epilogue: rtol 1e-5 against the default."""
     row, col = random_graph(d + 1, n, n, nnz, skew=True)
@@ -46,11 +48,11 @@ def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
     gen = torch.Generator().manual_seed(d)
     X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
     outs = {}
-    for variant in range(23):
+    for variant in range(26):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
-    for v in range(1, 23):
+    for v in range(1, 26):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
