@@ -132,7 +132,8 @@ typedef struct lgb_csr {
  * 18 = sub-warp rows + L2 prefetch of the epilogue operands, double-buffered (col,val) batches and an L2 evict_first
  * policy on those streamed loads, 19 = 16 + 18,
  * 20..22 (d in 33..64) = four rows per warp: 8 lanes x 2 float4 per row, with CTA-wide slices (22: + the prefetches of 18),
- * 23..25 (d = 64) = the same with one 256-bit load per lane and non-zero (LDG.E.256).  Every variant computes the same operator (rtol 1e-5); summation order inside a row differs between families. */
+ * 23..25 (d = 64) = the same with one 256-bit load per lane and non-zero (LDG.E.256), 26/27 (d = 128) = warp per row with
+ * 256-bit gathers (16 lanes x 32 bytes per row; unroll 1 at 64 warps/SM, unroll 2 at 40).  Every variant computes the same operator (rtol 1e-5); summation order inside a row differs between families. */
 #define LGB_SPMM_VARIANT_SHIFT 4
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid,
              const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws,

@@ -148,7 +148,7 @@ class DeviceCSR:
         shape the LightGCN layers use (Y + fused accumulate).  The winner is installed on the graph (plan, row order,
         ``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
         if candidates is None:
-            candidates = AUTOTUNE_CANDIDATES if d % 4 == 0 and d <= 64 else (0,)
+            candidates = AUTOTUNE_CANDIDATES if d % 4 == 0 and d <= 64 else ((0, 26, 27) if d == 128 else (0,))
         chunks = tuple(chunks) if chunks else (self.chunk,)
         if self.chunk <= 0:
             chunks = (self.chunk,)

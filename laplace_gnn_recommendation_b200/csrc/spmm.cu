@@ -58,11 +58,13 @@ struct SpmmParams {
 // Loads and FMAs of the entries past the end of a row are predicated off (no zero-filled registers, no weight select).
 // D4C = d/4 when it is known at compile time (the row is exactly one float4 per lane of the group: d = 4*G*VPL, e.g. d = 64
 // with G = 16): the column-bound predicates disappear and the row offset becomes a shift; 0 = read it from the parameters.
-template <int G, int VPL, int UNROLL, int STEP = 32, typename IT = uint32_t, int D4C = 0>
+// W256: a lane holds two ADJACENT float4 of the row (2*lig, 2*lig+1) and fetches them with one 256-bit load (LDG.E.256).
+template <int G, int VPL, int UNROLL, int STEP = 32, typename IT = uint32_t, int D4C = 0, bool W256 = false>
 __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int e, int lane, float4 (&acc)[VPL]) {
   constexpr int NG = 32 / G;
   static_assert(32 % (NG * UNROLL) == 0, "a batch of 32 entries must be a whole number of unrolled steps");
   static_assert(D4C == 0 || D4C == G * VPL, "a compile-time d/4 must fill the lane group exactly");
+  static_assert(!W256 || (VPL == 2 && D4C == 2 * G), "256-bit gathers need two adjacent float4 per lane and an exact fit");
   const int grp = lane / G;
   const int lig = lane % G;
   const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
@@ -88,17 +90,25 @@ __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int
         ww[u] = __shfl_sync(FULL_MASK, w, k);
         ok[u] = k < cnt;
         const IT row = (IT)cc * d4i;
+        if (W256) {
+          if (ok[u]) {
+            const f4x2 t = ld_gather_f8(X4 + (row + (IT)(lig * 2)));
+            v[u][0] = t.a;
+            v[u][VPL - 1] = t.b;
+          }
+        } else {
 #pragma unroll
-        for (int q = 0; q < VPL; ++q) {
-          const int f = lig + q * G;
-          if (ok[u] && f < d4) v[u][q] = ld_gather_f4(X4 + (row + (IT)f));
+          for (int q = 0; q < VPL; ++q) {
+            const int f = lig + q * G;
+            if (ok[u] && f < d4) v[u][q] = ld_gather_f4(X4 + (row + (IT)f));
+          }
         }
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
         for (int q = 0; q < VPL; ++q)
-          if (ok[u] && lig + q * G < d4) f4_fma(acc[q], ww[u], v[u][q]);
+          if (ok[u] && (W256 || lig + q * G < d4)) f4_fma(acc[q], ww[u], v[u][q]);
     }
   }
   // combine the groups (fixed butterfly order)
@@ -154,7 +164,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
 }
 
 // Stage 1: slices of long rows first (heaviest work is scheduled first), then one warp per ordinary row.
-template <int G, int VPL, int UNROLL, int MINB, typename IT = uint32_t>
+template <int G, int VPL, int UNROLL, int MINB, typename IT = uint32_t, int D4C = 0, bool W256 = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const SpmmParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * SPMM_WARPS + (threadIdx.x >> 5);
@@ -166,12 +176,12 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const 
     const int r = p.task_row[w];
     const int s = p.task_start[w];
     const int e = min(s + p.chunk, p.rowptr[r + 1]);
-    accumulate_slice<G, VPL, UNROLL, 32, IT>(p, s, e, lane, acc);
+    accumulate_slice<G, VPL, UNROLL, 32, IT, D4C, W256>(p, s, e, lane, acc);
     if (lane < G) {
       float4* out = reinterpret_cast<float4*>(p.partial) + (size_t)w * p.d4;
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
-        const int f = lane + q * G;
+        const int f = W256 ? lane * VPL + q : lane + q * G;
         if (f < p.d4) st_f4(out + f, acc[q]);
       }
     }
@@ -183,8 +193,8 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_rows_kernel(const 
   const int s = p.rowptr[r];
   const int e = p.rowptr[r + 1];
   if (p.chunk > 0 && e - s > p.chunk) return;  // long row: handled by its slices + stage 2
-  accumulate_slice<G, VPL, UNROLL, 32, IT>(p, s, e, lane, acc);
-  if (lane < G) epilogue_row<G, VPL>(p, r, e - s, lane, acc);
+  accumulate_slice<G, VPL, UNROLL, 32, IT, D4C, W256>(p, s, e, lane, acc);
+  if (lane < G) epilogue_row<G, VPL, false, W256>(p, r, e - s, lane, acc);
 }
 
 
@@ -393,10 +403,10 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
       float4 acc[VPL];
 #pragma unroll
       for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
-      accumulate_slice<G, VPL, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C>(p, s + 32 * wi, e, lane, acc);
+      accumulate_slice<G, VPL, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C, W256>(p, s + 32 * wi, e, lane, acc);
       if (lane < G) {
 #pragma unroll
-        for (int q = 0; q < VPL; ++q) wsum[wi][lane + q * G] = acc[q];
+        for (int q = 0; q < VPL; ++q) wsum[wi][W256 ? lane * VPL + q : lane + q * G] = acc[q];   // indexed by float4 of the row
       }
       __syncthreads();
       if (wi == 0 && lane < G) {
@@ -422,11 +432,11 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
 #pragma unroll
     for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
     const int s = p.task_start[w], e = p.task_end[w];
-    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C>(p, s, e, lane, acc);
+    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256>(p, s, e, lane, acc);
     if (lane < G) {
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
-        const int f = lane + q * G;
+        const int f = W256 ? lane * VPL + q : lane + q * G;
         if (f < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + f, acc[q]);
       }
     }
@@ -535,8 +545,8 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     float4 acc[VPL];
 #pragma unroll
     for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
-    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C>(p, ss, ee, lane, acc);
-    if (lane < G) epilogue_row<G, VPL>(p, rr, ee - ss, lane, acc);
+    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256>(p, ss, ee, lane, acc);
+    if (lane < G) epilogue_row<G, VPL, false, W256>(p, rr, ee - ss, lane, acc);
   }
 }
 
@@ -757,14 +767,14 @@ static int sm_count() {
   return g_sm_count;
 }
 
-template <int G, int VPL, int UNROLL, int MINB = 1, typename IT = uint32_t>
+template <int G, int VPL, int UNROLL, int MINB = 1, typename IT = uint32_t, int D4C = 0, bool W256 = false>
 static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
   const int64_t items = p.n_tasks + p.n_rows;
   if (items > 0) {
     const int64_t blocks = (items + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
     if (variant == 1 || (p.n_tasks > 0 && !p.task_end)) {
-      spmm_rows_kernel<G, VPL, UNROLL, MINB, IT><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+      spmm_rows_kernel<G, VPL, UNROLL, MINB, IT, D4C, W256><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     } else {
       // persistent grid: every SM filled to the occupancy limit, each warp walks items w, w+W, ...
       static int occ = 0;
@@ -966,7 +976,13 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
       default: return launch_subwarp<16, 2, 16>(p, stream);
     }
   }
-  if (d4 <= 32) return (variant == 1) ? launch_vec<32, 1, 8>(p, 1, stream) : launch_vec<32, 1, 2, 16>(p, 1, stream);
+  if (d4 <= 32) {
+    if (variant == 1) return launch_vec<32, 1, 8>(p, 1, stream);
+    // 26: d = 128 with 256-bit gathers -- 16 lanes x 32 bytes per row, two rows per warp-level load (measurement pending)
+    if (variant == 26 && d4 == 32) return launch_vec<16, 2, 1, 16, uint32_t, 32, true>(p, 1, stream);
+    if (variant == 27 && d4 == 32) return launch_vec<16, 2, 2, 10, uint32_t, 32, true>(p, 1, stream);
+    return launch_vec<32, 1, 2, 16>(p, 1, stream);
+  }
   if (d4 <= 64) return launch_vec<32, 2, 2, 12>(p, 1, stream);
   if (d4 <= 128) return launch_vec<32, 4, 1, 8>(p, 1, stream);
   set_error("lgb_spmm: d=%d > 512 not supported", d);

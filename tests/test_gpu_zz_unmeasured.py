@@ -31,6 +31,13 @@ def test_spmm_wide_slice_variant_vs_oracle(cuda_dev, d, chunk):
         _spmm_vs_oracle(cuda_dev, d, chunk, variant=25)
 
 
+@pytest.mark.parametrize("chunk", [256, 8, 0])
+@pytest.mark.parametrize("variant", [26, 27])
+def test_spmm_256bit_gathers_d128_vs_oracle(cuda_dev, variant, chunk):
+    """d = 128 with 256-bit per-lane gathers (16 lanes x 32 bytes per row, LDG.E.256): rows, slices of long rows, epilogue."""
+    _spmm_vs_oracle(cuda_dev, 128, chunk, variant=variant)
+
+
 @pytest.mark.parametrize("d", [8, 64, 84, 128, 256])
 def test_spmm_64bit_index_family_vs_oracle(cuda_dev, d):
     """Variant 17 = the kernels a table with n_cols*d/4 >= 2^31 elements is routed to (64-bit element index)."""
@@ -38,7 +45,7 @@ def test_spmm_64bit_index_family_vs_oracle(cuda_dev, d):
 
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
-    """All 26 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
+    """All 28 kernel variants (warp-per-row at several unroll depths / occupancies, software-pipelined persistent warps,
     cp.async rings, sub-warp rows, CTA-wide slices, 64-bit element indexing) compute the same operator with the same fused
     epilogue: rtol 1e-5 against the default."""
     row, col = random_graph(d + 1, n, n, nnz, skew=True)
@@ -48,11 +55,11 @@ def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
     gen = torch.Generator().manual_seed(d)
     X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
     outs = {}
-    for variant in range(26):
+    for variant in range(28):
         Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
         g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
         outs[variant] = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
-    for v in range(1, 26):
+    for v in range(1, 28):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
 
