@@ -348,12 +348,17 @@ const char* error_string() { return g_last_error_text.c_str(); }
 
 }  // namespace emu
 
+extern "C" void emu_multicast_clear() { emu::g_mc.clear(); }
+
 extern "C" void emu_multicast_bind(void* mc_base, size_t bytes, int world, void** peer_bases) {
   emu::Multicast m;
   m.base = (char*)mc_base;
   m.bytes = bytes;
   for (int r = 0; r < world; ++r) m.peers.push_back((char*)peer_bases[r]);
-  for (auto& old : emu::g_mc)
-    if (old.base == m.base) { old = m; return; }
-  emu::g_mc.push_back(m);
+  // a registration is only as alive as the tensors behind it: drop every older one whose key range overlaps the new key
+  // (the allocator reuses addresses -- a stale range that still matched would redirect loads/stores into freed peers)
+  auto& v = emu::g_mc;
+  v.erase(std::remove_if(v.begin(), v.end(), [&](const emu::Multicast& o) { return o.base < m.base + m.bytes && m.base < o.base + o.bytes; }),
+          v.end());
+  v.push_back(m);
 }
