@@ -136,6 +136,12 @@ class CudaOps:
             return
         _bpr_launch(a, Ef.device)
 
+    def adam(self, p, g, m, v, lr, beta1, beta2, eps, step):
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, beta1, beta2, eps, int(step), stream()),
+                  "adam_step")
+        _lib.count_launch()
+
     # collectives -------------------------------------------------------------------------------
     def all_reduce_async(self, t: torch.Tensor):
         """Sum-all-reduce of ``t`` on the comm stream, ordered after the work already queued on the
@@ -300,6 +306,18 @@ class ShardedLightGCN:
             out[name] = dict(g.autotune_report.get("chosen", {"variant": g.variant}), ms=g.autotune_report["ms"],
                              rejected=g.autotune_report["rejected"])
         return out
+
+    # ---- optimizer step on the local shard (run_pipeline_lightgcn.py:103,159 -- optim.Adam over both tables) ------------
+    def adam_step(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        """One fused Adam step (lgb_adam_step, same arithmetic as torch.optim.Adam) on the local table with the gradients the
+        last ``fused_step`` left in ``self.grad``: the owned user rows are updated by their owner only; the item rows carry
+        identical gradients on every rank (they were all-reduced), so the replicated item block stays bit-identical without
+        a broadcast.  State (exp_avg, exp_avg_sq, step) lives on the engine."""
+        if not hasattr(self, "_adam"):
+            self._adam = dict(step=0, m=torch.zeros_like(self.table), v=torch.zeros_like(self.table))
+        st = self._adam
+        st["step"] += 1
+        self.ops.adam(self.table, self.grad, st["m"], st["v"], float(lr), float(betas[0]), float(betas[1]), float(eps), st["step"])
 
     def autotune_step(self, user_indices, pos_item_indices, neg_item_indices, lambda_val: float, reps: int = 5,
                       candidates=((None, False), (None, True)), timer=None) -> dict:

@@ -76,6 +76,12 @@ class CpuOracleOps:
             dE0_items.index_add_(0, p, 2 * lam * p0)
             dE0_items.index_add_(0, n, 2 * lam * n0)
 
+    def adam(self, p, g, m, v, lr, beta1, beta2, eps, step):
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr / bc1)
+
     class _Done:
         def wait(self):
             pass
@@ -163,7 +169,11 @@ def _worker(rank, world, port, cases, out_dir):
                     tuned = eng.autotune_step(pb["u"], pb["p"], pb["n"], pb["lam"], candidates=((None, False), (None, True), ("pipelined", True)),
                                               timer=lambda fn: (time.perf_counter(), fn(), time.perf_counter())[2] * 0 + 1.0 + rank)
                     loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])      # the installed winner still computes the step
-            torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(), tuned=tuned,
+                snap = dict(loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone())
+                eng.adam_step(lr=1e-2)                                               # optimizer step on the shard, then a second iteration
+                eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+                eng.adam_step(lr=1e-2)
+            torch.save(dict(lo=eng.lo, hi=eng.hi, tuned=tuned, table=eng.table.clone(), **snap,
                             bounds=eng.bounds, local_edges=eng.local_edges), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -214,6 +224,21 @@ def test_sharded_step_equals_single_process_oracle(tmp_path, world):
             torch.testing.assert_close(o["grad"][Ug:], o_gi, **gtol)                    # identical on every rank
         for a, b in zip(outs[:-1], outs[1:]):
             assert a["hi"] == b["lo"], what
+        # two iterations with ShardedLightGCN.adam_step == two iterations of the oracle with torch.optim.Adam
+        Wu, Wi = pb["Wu"].clone().requires_grad_(True), pb["Wi"].clone().requires_grad_(True)
+        opt = torch.optim.Adam([Wu, Wi], lr=1e-2)
+        rowptr, cc, _ = lo.csr_from_coo(*lo.wiring_symmetric(pb["users"], pb["items"], pb["U"], pb["I"])[:2], pb["U"] + pb["I"], pb["U"] + pb["I"])
+        for _ in range(2):
+            _, gu, gi, _, _ = lo.train_iteration(Wu.detach(), Wi.detach(), rowptr, cc, K, pb["u"], pb["p"], pb["n"], pb["lam"])
+            Wu.grad, Wi.grad = gu, gi
+            opt.step()
+        for o in outs:
+            Ug = o["hi"] - o["lo"]
+            atol = dict(rtol=1e-4, atol=5e-6, msg=lambda m: f"{what} (after 2 Adam steps): {m}")
+            torch.testing.assert_close(o["table"][:Ug], Wu.detach()[o["lo"]:o["hi"]], **atol)
+            torch.testing.assert_close(o["table"][Ug:], Wi.detach(), **atol)
+            Ug0 = outs[0]["hi"] - outs[0]["lo"]
+            assert torch.equal(o["table"][Ug:], outs[0]["table"][Ug0:]), what            # replicated item block: same bits on every rank
         if outs[0]["tuned"] is not None:             # autotune_step: every rank reports the same, complete, rejection-free table
             t0 = outs[0]["tuned"]
             assert len(t0["ms"]) == 3 and not t0["rejected"] and all(o["tuned"] == t0 for o in outs), t0
