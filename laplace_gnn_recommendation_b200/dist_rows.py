@@ -144,6 +144,14 @@ class RowShardedLightGCN:
             g_pad = dst
         return self.grad
 
+    def adam_step(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        """Fused Adam (lgb_adam_step, torch.optim.Adam arithmetic) on the owned rows with the gradients of the last fused_step."""
+        if not hasattr(self, "_adam"):
+            self._adam = dict(step=0, m=torch.zeros_like(self.table), v=torch.zeros_like(self.table))
+        st = self._adam
+        st["step"] += 1
+        self.ops.adam(self.table, self.grad, st["m"], st["v"], float(lr), float(betas[0]), float(betas[1]), float(eps), st["step"])
+
     def _bpr(self, iu, ip, in_, lam: float, B: int, loss=None, dEf=None, dE0=None, gscale: float = 1.0) -> None:
         a = LgbBprArgs()
         ef, e0 = self._efg.data_ptr(), self._e0g.data_ptr()

@@ -276,8 +276,12 @@ def _rows_worker(rank, world, port, cases, out_dir):
                 eng = RowShardedLightGCN(pb["U"], pb["I"], pb["d"], K, row, col, "cpu", ops=make_emu_ops(),
                                          init_tables=(pb["Wu"], pb["Wi"]), chunk=64)
                 loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
-            torch.save(dict(lo=eng.lo, hi=eng.hi, loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone(), bounds=eng.bounds,
-                            nnz=eng.local_nnz), os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
+                snap = dict(loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone())
+                eng.adam_step(lr=1e-2)
+                eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+                eng.adam_step(lr=1e-2)
+            torch.save(dict(lo=eng.lo, hi=eng.hi, bounds=eng.bounds, table=eng.table.clone(), nnz=eng.local_nnz, **snap),
+                       os.path.join(out_dir, f"case{ci}_rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -309,3 +313,12 @@ def test_row_sharded_engine_equals_single_process_oracle(tmp_path, world):
             torch.testing.assert_close(o["grad"], o_g[o["lo"]:o["hi"]], rtol=1e-5, atol=1e-9)
         for a, b in zip(outs[:-1], outs[1:]):
             assert a["hi"] == b["lo"]
+        Wu, Wi = pb["Wu"].clone().requires_grad_(True), pb["Wi"].clone().requires_grad_(True)      # two iterations incl. Adam
+        opt = torch.optim.Adam([Wu, Wi], lr=1e-2)
+        for _ in range(2):
+            _, gu, gi, _, _ = lo.train_iteration(Wu.detach(), Wi.detach(), rowptr, c, K, pb["u"], pb["p"], pb["n"], pb["lam"])
+            Wu.grad, Wi.grad = gu, gi
+            opt.step()
+        full = torch.cat([Wu.detach(), Wi.detach()])
+        for o in outs:
+            torch.testing.assert_close(o["table"], full[o["lo"]:o["hi"]], rtol=1e-4, atol=5e-6)
