@@ -97,6 +97,18 @@ __device__ __forceinline__ f4x2 ld_gather_f8(const float4* p) {
                : "l"(p));
   return v;
 }
+__device__ __forceinline__ f4x2 ld_stream_f8(const float4* p) {   // read-once 32 bytes: no L1 allocation
+  f4x2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_f8(float4* p, const float4& a, const float4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x),
+               "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
 // Streaming 128-bit store (written once, read by a later kernel).
 __device__ __forceinline__ void st_f4(float4* p, const float4& v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)

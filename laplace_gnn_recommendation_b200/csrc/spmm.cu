@@ -134,6 +134,34 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
     return;
   }
   const size_t rowoff = (size_t)r * p.d4;
+  if (CONTIG && VPL == 2) {
+    // the 256-bit layout (callers guarantee d/4 == 2*G): both float4 of the lane move with ONE load / store each
+    const size_t o = rowoff + (size_t)lig * 2;
+    float4 y0 = acc[0], y1 = acc[VPL - 1];
+    if (p.mean) {
+      const float c = (float)max(deg, 1);
+      y0.x = __fdiv_rn(y0.x, c); y0.y = __fdiv_rn(y0.y, c); y0.z = __fdiv_rn(y0.z, c); y0.w = __fdiv_rn(y0.w, c);
+      y1.x = __fdiv_rn(y1.x, c); y1.y = __fdiv_rn(y1.y, c); y1.z = __fdiv_rn(y1.z, c); y1.w = __fdiv_rn(y1.w, c);
+    }
+    if (p.resid) {
+      const f4x2 t = ld_stream_f8(reinterpret_cast<const float4*>(p.resid) + o);
+      y0 = f4_add(y0, t.a); y1 = f4_add(y1, t.b);
+    }
+    if (p.Y) st_f8(reinterpret_cast<float4*>(p.Y) + o, y0, y1);
+    if (p.acc_out) {
+      float4 a0 = y0, a1 = y1;
+      if (p.acc_in) {
+        const f4x2 t = ld_stream_f8(reinterpret_cast<const float4*>(p.acc_in) + o);
+        a0 = f4_add(t.a, y0); a1 = f4_add(t.b, y1);
+      }
+      if (p.acc_div != 1.0f) {
+        a0.x = __fdiv_rn(a0.x, p.acc_div); a0.y = __fdiv_rn(a0.y, p.acc_div); a0.z = __fdiv_rn(a0.z, p.acc_div); a0.w = __fdiv_rn(a0.w, p.acc_div);
+        a1.x = __fdiv_rn(a1.x, p.acc_div); a1.y = __fdiv_rn(a1.y, p.acc_div); a1.z = __fdiv_rn(a1.z, p.acc_div); a1.w = __fdiv_rn(a1.w, p.acc_div);
+      }
+      st_f8(reinterpret_cast<float4*>(p.acc_out) + o, a0, a1);
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < VPL; ++q) {
     const int f = CONTIG ? lig * VPL + q : lig + q * G;

@@ -45,6 +45,8 @@ ASM_BODIES = {
     "cp_async_16": "*reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);",
     "prefetch_l2": "",
     "ld_gather_f8": "f4x2 v; v.a = p[0]; v.b = p[1]; return v;",
+    "ld_stream_f8": "f4x2 v; v.a = p[0]; v.b = p[1]; return v;",
+    "st_f8": "p[0] = a; p[1] = b;",
     "l2_policy_evict_first": "return 0;",
     "ld_stream_i32_hint": "return *p;",
     "ld_stream_f32_hint": "return *p;",
