@@ -48,7 +48,7 @@ WORKLOADS = {
     "hm": (1_371_980, 105_542, 31_788_324),
     "ml1m": (6_040, 3_706, 1_000_209),
 }
-CPU_SAMPLE_SCALE = 8  # the CPU arms run the same generator at 1/8 of every dimension (bounded sample)
+CPU_SAMPLE_SCALE = 1  # the CPU arms run the SAME graph as the GPU arm (full config: ~3-5 s per epoch on the box's host cores)
 
 # BASELINE.json configs[3]: hetero encoder-decoder ranking step on LinkNeighborLoader-sized batches cut to the H&M shape
 # (SURVEY 8d.5): name -> (E_sub per edge type, N_customer, N_article, label edges); widths 84/76 -> hidden 128 -> out 64
@@ -82,6 +82,25 @@ def make_graph(U: int, I: int, E: int, degree: str, seed: int, device):
 def spmm_bytes(nnz: int, rows: int, d: int) -> float:
     """Algorithmic bytes of one SpMM launch, cache-oblivious row-gather model."""
     return nnz * 8 + (rows + 1) * 4 + nnz * d * 4 + rows * d * 4
+
+
+def spmm_floor_bytes(nnz: int, rows: int, d: int) -> float:
+    """Compulsory DRAM bytes of one SpMM launch: CSR arrays once, operand table once, output once."""
+    return nnz * 8 + (rows + 1) * 4 + 2 * rows * d * 4
+
+
+def lookup_traffic(workload, degree, d, n_gpus, plan):
+    """ncu-measured DRAM bytes per lgb_spmm call for EXACTLY the configuration that ran (profiles/roofline_traffic.json),
+    or None: a capture of another kernel / plan / shard size never stands in."""
+    try:
+        caps = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))["captures"]
+    except Exception:
+        return None
+    for c in caps:
+        if (c["workload"], c["degree"], c["d"], c["n_gpus"]) == (workload, degree, d, n_gpus) and plan is not None and \
+                (c["variant"], c["chunk"], bool(c["degree_order"])) == (plan.get("variant"), plan.get("chunk"), bool(plan.get("degree_order"))):
+            return c
+    return None
 
 
 def epoch_bytes(nnz: int, N: int, d: int, K: int, B: int) -> float:
@@ -167,9 +186,9 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = 2 * args.layers * nnz / dt
-    sample = (f"{args.workload}-shaped graph at 1/{CPU_SAMPLE_SCALE} scale (U={U}, I={I}, E={E}, nnz={nnz}, {args.degree}), "
-              f"full epoch per step, torch CSR (MKL) SpMM + autograd")
-    line = base_line(args, value, dt * 1e3, nnz_full=None)
+    sample = (f"the full {args.workload}-shaped graph (U={U}, I={I}, E={E}, nnz={nnz}, {args.degree}; same generator and seed as the GPU arm), "
+              f"one full epoch per step, torch CSR (MKL) SpMM + autograd")
+    line = base_line(args, value, dt * 1e3, nnz_full=None, sizes=(U, I, E))
     line.update({"impl": "reference", "n_gpus": args.gpus, "dtype": "f32",
                  "cpu_baseline": {"value": value, "unit": "edge-traversals/s", "cores": torch.get_num_threads(),
                                   "kind": "port", "sample": sample},
@@ -177,8 +196,8 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def base_line(args, value, ms, nnz_full):
-    U, I, E = WORKLOADS[args.workload]
+def base_line(args, value, ms, nnz_full, sizes=None):
+    U, I, E = sizes or WORKLOADS[args.workload]     # the sizes that actually ran
     return {
         "metric": "lightgcn_fwd_bwd_bpr_edge_traversals_per_s", "value": value, "unit": "edge-traversals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -187,8 +206,83 @@ def base_line(args, value, ms, nnz_full):
                    "d": args.dim, "K": args.layers, "B": args.batch,
                    "epoch": "K SpMM fwd + layer mean + BPR(B) + K SpMM^T bwd; sampler and Adam excluded",
                    "l2": "working set (tables 378 MB + CSR 1 GB per direction at hm) exceeds the 126 MB L2; no flush",
-                   "parallelism": "single GPU" if args.gpus == 1 else f"users range-sharded x{args.gpus}, items replicated, NCCL all-reduce"},
+                   "parallelism": "single GPU" if args.gpus == 1 else f"users range-sharded x{args.gpus}, items replicated, one item-block exchange per layer"},
     }
+
+
+def time_step(fn, dev, world, dist, reps=10):
+    """ms per call, barrier + CUDA events, max over ranks (set-up-time comparisons of step forms)."""
+    for _ in range(2):
+        fn()
+    if world > 1:
+        dist.barrier()
+    CUDA.synchronize()
+    e0, e1 = CUDA.event(), CUDA.event()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    CUDA.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def want_graph(args, eng) -> bool:
+    """N > 1: 'auto' captures the step only when the exchange is the package's own kernel (no NCCL call inside the capture)."""
+    return args.graph == "on" or (args.graph == "auto" and getattr(eng.ops, "kind", "") == "symm")
+
+
+def sharded_parity_check(args, dev, rank, world):
+    """N > 1: a small fixed problem (skewed degrees, K = 3, d = 64, B = 512) through the SAME engine configuration the bench
+    is about to time (schedule, exchange, CUDA-graph replay when requested), every rank's shard against the single-process
+    CPU oracle (the bench may call oracle/ as a checker).  Returns the worst relative errors over all ranks."""
+    import torch.distributed as dist
+    from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
+    from oracle import lightgcn_oracle as lo
+    gen = torch.Generator().manual_seed(7)
+    U, I, E, d, K, B, lam = 4000, 600, 90000, 64, 3, 512, 1e-3
+    users = (torch.rand(E, generator=gen) ** 2 * U).long().clamp(max=U - 1)
+    items = (torch.rand(E, generator=gen) ** 3 * I).long().clamp(max=I - 1)
+    Wu, Wi = torch.randn(U, d, generator=gen) * 0.1, torch.randn(I, d, generator=gen) * 0.1
+    pick = torch.randint(0, E, (B,), generator=gen)
+    u, p, n = users[pick], items[pick], torch.randint(0, I, (B,), generator=gen)
+    ops = CUDA.sharded_ops() if CUDA.sharded_ops else None
+    eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule="chains" if args.schedule == "auto" else args.schedule,
+                          exchange=args.exchange, ops=ops, init_tables=(Wu, Wi), max_batch=B)
+    ud, pd, nd = u.to(dev), p.to(dev), n.to(dev)
+    out = {"exchange": getattr(eng.ops, "kind", "?"), "multicast": bool(getattr(eng.ops, "multicast", False)), "schedule": eng.schedule}
+    forms = {"eager": lambda: eng.fused_step(ud, pd, nd, lam)}
+    if want_graph(args, eng):
+        try:
+            gstep = eng.capture(B, lam)
+            forms["graph"] = lambda: gstep(ud, pd, nd)
+        except Exception as exc:
+            out["graph_error"] = repr(exc)[:200]
+    row, col, nn = lo.wiring_symmetric(users, items, U, I)
+    rowptr, c, _ = lo.csr_from_coo(row, col, nn, nn)
+    o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(Wu, Wi, rowptr, c, K, u, p, n, lam)
+
+    def rel(got, want):
+        got, want = got.detach().cpu().double(), want.double()
+        return float((got - want).abs().max() / (want.abs().max() + 1e-30))
+    for name, fn in forms.items():
+        for _ in range(2):                                   # twice: the second pass re-uses every buffer and signal slot
+            loss = fn()
+        CUDA.synchronize()
+        errs = torch.tensor([abs(float(loss) - float(o_loss)) / abs(float(o_loss)),
+                             max(rel(eng.E_f_users, o_uf[eng.lo:eng.hi]) if eng.Ug else 0.0, rel(eng.E_f_items, o_if)),
+                             max(rel(eng.grad_users, o_gu[eng.lo:eng.hi]) if eng.Ug else 0.0, rel(eng.grad_items, o_gi))],
+                            dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        out[name] = {"loss_rel_err": float(errs[0]), "emb_max_rel_err": float(errs[1]), "grad_max_rel_err": float(errs[2]),
+                     "ok": bool((errs <= 1e-5).all())}
+    out["problem"] = f"U={U} I={I} E={E} d={d} K={K} B={B}, skewed degrees, vs oracle/lightgcn_oracle.train_iteration; errors = max |got-want| / max |want| over all ranks"
+    del eng
+    CUDA.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -211,7 +305,7 @@ def run_ours(args):
 
     U, I, E = WORKLOADS[args.workload]
     d, K, B, lam = args.dim, args.layers, args.batch, 1e-6
-    tuned = None
+    tuned, shard_parity, graph_report = None, None, None
     users, items = make_graph(U, I, E, args.degree, 1234, dev)
     gen = torch.Generator(device=dev).manual_seed(42)
     pick = torch.randint(0, E, (B,), generator=gen, device=dev)
@@ -240,16 +334,23 @@ def run_ours(args):
                 g.variant = gt.variant = None
                 tuned = {"error": repr(exc)[:300]}
         nnz = g.nnz
-        if args.graph:                                           # one CUDA-graph launch per iteration (launch-bound small graphs)
+        if args.graph == "on":                                   # one CUDA-graph launch per iteration (launch-bound small graphs)
             gstep1 = model.capture_step(adj, B, lam)
             step = lambda: gstep1(ub, pb, nb)                    # noqa: E731
         else:
             step = lambda: model.fused_step(adj, ub, pb, nb, lam)   # noqa: E731
     else:
         from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
+        # the SAME embedding tables as the single-GPU model (same generator, same order): the loss printed at N = 1, 2, 4, 8
+        # is then one number to rtol 1e-5, which the scaling record can be checked against
         torch.manual_seed(0)
-        eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule=args.schedule, exchange=args.exchange,
-                              ops=CUDA.sharded_ops() if CUDA.sharded_ops else None)
+        cpu_model = lg.LightGCN(U, I, d, K)
+        tables = (cpu_model.users_emb.weight.detach(), cpu_model.items_emb.weight.detach())
+        ops = CUDA.sharded_ops() if CUDA.sharded_ops else None
+        eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule="chains" if args.schedule == "auto" else args.schedule,
+                              exchange=args.exchange, ops=ops, init_tables=tables, max_batch=max(B, 128))
+        del cpu_model, tables
+        shard_parity = sharded_parity_check(args, dev, rank, world)      # small fixed problem through the SAME step form vs the oracle
         if not args.no_autotune:
             try:
                 tuned = eng.autotune()                        # per rank; rank 0's choice is reported
@@ -257,21 +358,34 @@ def run_ours(args):
                 for gv in eng.graphs():
                     gv.variant = None
                 tuned = {"error": repr(exc)[:300]}
-            if not args.graph:
-                # step form (host-filtered vs static-shape BPR section, pipelined exchange, one merged launch per layer): result-checked on every rank, timed max-over-ranks;
+            if args.schedule == "auto":
+                # schedule (two layer chains on two streams vs one stream): result-checked on every rank, timed max-over-ranks;
                 # all ranks run the same candidates in the same order (ShardedLightGCN.autotune_step)
                 try:
-                    forms = ((None, False), (None, True), ("pipelined", True), ("merged", True)) if args.schedule == "layer" else ((None, False), (None, True))
-                    tuned["step_form"] = eng.autotune_step(ub, pb, nb, lam, candidates=forms, timer=CUDA.step_timer)
+                    tuned["step_form"] = eng.autotune_step(ub, pb, nb, lam, candidates=("chains", "layer"), timer=CUDA.step_timer)
                 except Exception as exc:
-                    eng.schedule, eng.static_batch = args.schedule, False
+                    eng.schedule = "chains"
                     tuned["step_form"] = {"error": repr(exc)[:300]}
+        elif args.schedule == "auto":
+            eng.schedule = "chains"
         nnz = 2 * E
-        if not args.graph:
-            step = lambda: eng.fused_step(ub, pb, nb, lam)      # noqa: E731
-        else:                                                   # whole step (kernels + NCCL) replayed from one CUDA graph
-            gstep = eng.capture(B, lam)
-            step = lambda: gstep(ub, pb, nb)                    # noqa: E731
+        eager = lambda: eng.fused_step(ub, pb, nb, lam)          # noqa: E731
+        step = eager
+        if want_graph(args, eng):                                # whole step (kernels on three streams + exchanges) replayed from one CUDA graph
+            try:
+                ref_loss = float(eager())
+                gstep = eng.capture(B, lam)
+                g_loss = float(gstep(ub, pb, nb))
+                same = abs(g_loss - ref_loss) <= 1e-5 * abs(ref_loss) + 1e-7
+                t_e, t_g = (time_step(f, dev, world, dist) for f in (eager, lambda: gstep(ub, pb, nb)))
+                use = same and (args.graph == "on" or t_g < t_e)
+                graph_report = {"replay_matches_eager": same, "eager_ms": t_e, "graph_ms": t_g, "used": bool(use)}
+                if use:
+                    step = lambda: gstep(ub, pb, nb)             # noqa: E731
+            except Exception as exc:
+                graph_report = {"error": repr(exc)[:300], "used": False}
+            if tuned is not None:
+                tuned["cuda_graph"] = graph_report
     del users, items
     CUDA.empty_cache()
 
@@ -299,8 +413,9 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     DeviceCSR.spmm = timed_spmm
-    if world > 1 and hasattr(eng.ops, "exchange_events") and not args.graph:
-        eng.ops.exchange_events = []           # CUDA events on the comm stream around every item-block all-reduce
+    graphed = bool(graph_report and graph_report.get("used")) or (world == 1 and args.graph == "on")
+    if world > 1 and hasattr(eng.ops, "exchange_events") and not graphed:
+        eng.ops.exchange_events = []           # CUDA events on the comm streams around every exchange
     launches0 = _lib.LAUNCHES
     sync()
     t0, t1 = CUDA.event(), CUDA.event()
@@ -313,24 +428,28 @@ def run_ours(args):
     exchange = None
     if world > 1 and getattr(eng.ops, "exchange_events", None):
         ev, eng.ops.exchange_events = eng.ops.exchange_events, None
+        ev = [e for e in ev if e[2] >= I * d * 4]                    # the item-block exchanges (not the 2*B*d batch rows)
         x_ms = [a.elapsed_time(b) for a, b, _ in ev]
         x_bytes = [n for _, _, n in ev]
         # an all-reduce of M bytes over G ranks moves 2*M*(G-1)/G bytes through each GPU's links (reduce-scatter + all-gather)
         bus = [2.0 * n * (world - 1) / world for n in x_bytes]
-        exchange = {"collective": f"NCCL all-reduce of the replicated item block ({args.exchange})", "per_step": len(ev) // max(args.steps, 1),
+        exchange = {"collective": ("own kernel over symmetric memory (lgb_exchange_allreduce_f32: barrier + multimem.ld_reduce / multimem.st + barrier)"
+                                   if getattr(eng.ops, "kind", "") == "symm" else "NCCL all-reduce") + " of the replicated item block",
+                    "multicast": bool(getattr(eng.ops, "multicast", False)), "per_step": len(ev) // max(args.steps, 1),
                     "mean_ms": statistics.mean(x_ms), "mean_bytes": statistics.mean(x_bytes),
                     "bus_GBps": sum(bus) / 1e9 / (sum(x_ms) * 1e-3), "nvlink_peak_GBps_per_direction": 900.0,
                     "frac_of_nominal": sum(bus) / 1e9 / (sum(x_ms) * 1e-3) / 900.0,
                     "share_of_step_if_exposed": sum(x_ms) / (args.steps * float(t0.elapsed_time(t1)) / max(args.steps, 1)),
-                    "note": "timed on the comm stream; in the default schedule it overlaps with the users SpMM"}
+                    "measured_reference_GBps": 770.0,
+                    "note": "timed on the high-priority comm streams (the time includes waiting for the slowest rank at the entry barrier); "
+                            "it overlaps with the other chain's SpMM launches"}
     clk = clocks.stop() if rank == 0 else None
-    graphed = bool(args.graph)
     if graphed:
         # the timed region replayed a CUDA graph (no per-launch host hooks); per-launch SpMM durations for the
         # roofline and the launch count come from an instrumented kernel-by-kernel pass of the SAME step
         launches0 = _lib.LAUNCHES
         for _ in range(3):
-            (eng.fused_step(ub, pb, nb, lam) if world > 1 else model.fused_step(adj, ub, pb, nb, lam))
+            (eager() if world > 1 else model.fused_step(adj, ub, pb, nb, lam))
         launches = (_lib.LAUNCHES - launches0) // 3 * args.steps
         sync()
     DeviceCSR.spmm = orig_spmm
@@ -350,16 +469,28 @@ def run_ours(args):
     peak = float(mp.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in mp else "fallback 6650 GB/s (B200_PROFILING.md)"
     achieved = (sum(spmm_alg) / 1e9) / (sum(spmm_ms) * 1e-3) if spmm_ms else None
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get(args.workload)
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": "lgb_spmm (lgb::spmm_subwarp_kernel / spmm_rows_kernel, variant per config.spmm_variant)",
+    avg_ms = statistics.mean(spmm_ms) if spmm_ms else None
+    plan = None
+    if world == 1:        # the plan the forward launches ran with (autotune's choice, or the env / flag defaults)
+        plan = {"variant": g.variant if g.variant is not None else int(os.environ.get("LGB_SPMM_VARIANT", "0")),
+                "chunk": g.chunk, "degree_order": g.row_order is not None}
+    cap = lookup_traffic(args.workload, args.degree, d, world, plan)
+    traffic = cap["dram_bytes_per_call"] if cap else None
+    floor = spmm_floor_bytes(spmm_events[0][2], spmm_events[0][3], d) if spmm_events else None
+    roofline = {"bound": "hbm", "kernel": "lgb_spmm (lgb::spmm_subwarp_kernel / spmm_rows_kernel + spmm_long_reduce_kernel, plan per config.spmm_variant)",
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "frac_note": "algorithmic row-gather model (SURVEY 8d): every gathered row counted as DRAM traffic, so > 1 when rows are served "
+                             "by L1/L2; dram_frac is the physical figure",
+                # physical DRAM bandwidth of the dominant kernel: ncu dram bytes of the SAME plan / live CUDA-event launch time / peak
+                "dram_frac": (traffic / 1e9) / (avg_ms * 1e-3) / peak if (traffic and avg_ms) else None,
+                "traffic_source": cap["source"] if cap else "no ncu capture of this exact configuration (workload, degree, d, n_gpus, plan)",
+                "l2_hit_pct": cap.get("lts_hit_pct") if cap else None, "l1_hit_pct": cap.get("l1_hit_pct") if cap else None,
+                "compulsory_floor_bytes_per_launch": floor,
+                "traffic_over_floor": traffic / floor if (traffic and floor) else None,
+                "plan": plan,
                 "algorithmic_bytes_per_launch": spmm_alg[0] if spmm_alg else None,
-                "avg_launch_ms": statistics.mean(spmm_ms) if spmm_ms else None,
+                "avg_launch_ms": avg_ms,
                 "launches_timed": len(spmm_ms),
                 "timed_in": "separate kernel-by-kernel pass (timed region replays a CUDA graph)" if graphed else "timed region",
                 "spmm_share_of_step": (sum(spmm_ms) / ((3 if graphed else args.steps) * ms)) if spmm_ms else None,
@@ -393,9 +524,10 @@ def run_ours(args):
         hu, hp, hn = (CUDA.pin(t.cpu()) for t in (ub, pb, nb))
 
         def api_step():
-            if not args.graph:
-                u_ = hu.to(dev, non_blocking=True); p_ = hp.to(dev, non_blocking=True); n_ = hn.to(dev, non_blocking=True)
-            return (eng.fused_step(u_, p_, n_, lam) if not args.graph else gstep(hu, hp, hn)).item()
+            if graphed:
+                return gstep(hu, hp, hn).item()
+            u_ = hu.to(dev, non_blocking=True); p_ = hp.to(dev, non_blocking=True); n_ = hn.to(dev, non_blocking=True)
+            return eng.fused_step(u_, p_, n_, lam).item()
         for _ in range(3):
             api_step()
         sync()
@@ -407,7 +539,7 @@ def run_ours(args):
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
         e2e = {"value": 2 * K * nnz / (float(e_ms) * 1e-3), "unit": "edge-traversals/s", "ms_per_step": float(e_ms),
                "h2d_bytes_per_step": 3 * B * 8, "d2h_bytes_per_step": 4,
-               "path": "ShardedLightGCN.fused_step(host-pinned batch) -> loss.item()"}
+               "path": "ShardedLightGCN.fused_step(host-pinned batch) -> loss.item()" + (" [CUDA-graph replay]" if graphed else "")}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -417,19 +549,21 @@ def run_ours(args):
         cstep()
         c0 = time.perf_counter()
         reps = 0
-        while reps < 3 or (time.perf_counter() - c0 < 10 and reps < 20):
+        while reps < 2 or (time.perf_counter() - c0 < 10 and reps < 20):
             cstep(); reps += 1
         cdt = (time.perf_counter() - c0) / reps
         cpu_baseline = {"value": 2 * K * cnnz / cdt, "unit": "edge-traversals/s", "cores": torch.get_num_threads(),
                         "kind": "port", "ms_per_step": cdt * 1e3,
-                        "sample": f"{args.workload}-shaped graph at 1/{CPU_SAMPLE_SCALE} scale (U={Us}, I={Is}, E={Es}, nnz={cnnz}, "
-                                  f"{args.degree}), {reps} full epochs after 1 warm-up; oracle port, torch CSR (MKL) SpMM + autograd"}
+                        "sample": f"the full {args.workload}-shaped graph (U={Us}, I={Is}, E={Es}, nnz={cnnz}, {args.degree}; same generator "
+                                  f"and seed as the GPU arm), {reps} full epochs after 1 warm-up; oracle port, torch CSR (MKL) SpMM + autograd"}
 
     if rank == 0:
         line = base_line(args, value, ms, nnz)
         line["config"]["spmm_variant"] = tuned if tuned is not None else "default (autotune off)"
         if exchange is not None:
             line["exchange"] = exchange
+        if shard_parity is not None:
+            line["shard_parity"] = shard_parity
         line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                      "cpu_baseline": cpu_baseline, "loss": float(loss),
                      "interactions_per_s": E / (ms * 1e-3)})
@@ -697,11 +831,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true",
                     help="keep the default SpMM kernel variant instead of timing the candidates on this graph at set-up")
-    ap.add_argument("--graph", action="store_true", help="replay the step from one CUDA graph (opt-in, not yet measured)")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "symm"],
-                    help="multi-GPU item-block exchange: NCCL all-reduce (measured default) or the symmetric-memory multimem kernel")
-    ap.add_argument("--schedule", default="layer", choices=["layer", "pipelined", "merged"],
-                    help="multi-GPU overlap schedule (dist.ShardedLightGCN); 'layer' is the measured default")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from one CUDA graph: N=1 only when 'on' (launch-bound small graphs); N>1 'auto' captures the step, "
+                         "requires the replay to reproduce the eager loss and keeps whichever is faster")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "symm"],
+                    help="multi-GPU item-block exchange: own kernel over symmetric memory (multimem / peer), NCCL all-reduce, or auto = symm when it sets up")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "chains", "layer"],
+                    help="multi-GPU schedule (dist.ShardedLightGCN): the two layer chains on two streams, one stream, or auto = time both at set-up")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload in HETERO_SIZES:

@@ -51,6 +51,11 @@ int lgb_sm_count(int* out_host);
 int lgb_csr_build_ws_bytes(int64_t nnz, int64_t n_rows, size_t* bytes_host);
 int lgb_csr_build(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n_rows, int64_t n_cols,
                   int32_t* rowptr, int32_t* colidx, int64_t* perm, void* ws, size_t ws_bytes, void* stream);
+/* torch_sparse's SparseTensor asserts row.max() < M and col.max() < N (the check that catches item ids which were not
+ * shifted by both_indexes_from_zero, data/lightgcn_loader.py:39-43).  lgb_csr_build counts such entries on the device
+ * (and clamps them, so nothing is written out of bounds); this call -- the ONE entry point that synchronises `stream` --
+ * reads the count back from the workspace of that build and returns LGB_ERANGE when it is not zero. */
+int lgb_csr_build_check(const void* ws, void* stream);
 
 /* CSR -> CSC: colptr[n_cols+1], rowidx[nnz], csr2csc[nnz] = argsort(col*n_rows+row) (stable).  The
  * transposed operand of the SpMM backward (torch_sparse SPMMSum::backward; model/lightgcn.py:85-87). */
@@ -163,6 +168,10 @@ int lgb_zero(void* p, size_t bytes, void* stream);
  * stand-alone pass, for rows whose sum arrives from a collective (multi-GPU item rows). out may alias acc or y. */
 int lgb_accumulate(const float* y, const float* acc, const float* resid, int64_t n, float div, float* out,
                    void* stream);
+/* out = (((s0 + s1) + s2) + ...) / div over `count` (<= 8) equally-shaped fp32 buffers (srcs_host: HOST array of device
+ * pointers): mean(stack(embs, dim=1), dim=1) of model/lightgcn.py:67-68 in one pass, same left-to-right order as the
+ * fused accumulate epilogue of lgb_spmm.  out must not alias a source. */
+int lgb_mean_rows(const float* const* srcs_host, int32_t count, int64_t n, float div, float* out, void* stream);
 
 /* out = cat(a[na,d], b[nb,d]) * scale   (one pass; cat/split/mean backward of model/lightgcn.py:58,67-72). */
 int lgb_scale_concat(const float* a, int64_t na, const float* b, int64_t nb, int32_t d, float scale,
@@ -183,6 +192,9 @@ int lgb_scale_concat(const float* a, int64_t na, const float* b, int64_t nb, int
  * [N,d] buffers (duplicates add up); without indices they are plain stores into [B,d] buffers.
  * ws: 2*lgb_bpr_blocks(B) floats.  loss: device float[1].
  * ------------------------------------------------------------------------------------------- */
+#define LGB_BPR_FILTER_USER_ROWS_ONLY 1   /* the owned-user filter skips only the USER operand of a foreign triple (its item rows are
+                                            still processed): the layer-0 regulariser gradients of a user-sharded table whose
+                                            item block is replicated.  Only with du0 / dp0 / dn0 outputs. */
 typedef struct lgb_bpr_args {
   const float* uf; const float* u0; const float* pf; const float* p0; const float* nf; const float* n0;
   const int64_t* iu; const int64_t* ip; const int64_t* in;   /* all three NULL, or all three set */
@@ -191,7 +203,7 @@ typedef struct lgb_bpr_args {
   int32_t d;
   float lambda;
   float gscale;            /* extra factor folded into the *_f gradients, e.g. 1/(K+1) */
-  int32_t _pad;
+  int32_t flags;           /* LGB_BPR_* */
   int64_t user_lo;         /* with index arrays: only triples with user_lo <= iu[b] < user_hi are processed and the   */
   int64_t user_hi;         /* user row becomes iu[b]-user_lo (a rank's shard of a global batch); user_hi == 0 = no filter */
   const float* gout;       /* device scalar upstream gradient or NULL */
@@ -201,6 +213,13 @@ typedef struct lgb_bpr_args {
 } lgb_bpr_args;
 int64_t lgb_bpr_blocks(int64_t B);
 int lgb_bpr(const lgb_bpr_args* a, void* stream);
+/* A global batch against a user-sharded table (multi-GPU BPR; the reference gathers from one table, run_pipeline_lightgcn.py:133-144):
+ *   gather : dst[b, :] = lo <= idx[b] < hi ? src[idx[b]-lo, :] : 0      (summed over ranks = the gathered batch rows)
+ *   scatter: dst[idx[b]-lo, :] += src[b, :] for the owned b             (atomic; dst zeroed or holding earlier terms) */
+int lgb_gather_rows_owned(const float* src, const int64_t* idx, int64_t B, int32_t d, int64_t lo, int64_t hi,
+                          float* dst, void* stream);
+int lgb_scatter_add_rows_owned(const float* src, const int64_t* idx, int64_t B, int32_t d, int64_t lo, int64_t hi,
+                               float* dst, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Edge decoder -- model/encoder_decoder.py:55-72.
@@ -265,6 +284,25 @@ int lgb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
  *   lgb_peer_allreduce_f32     : per-peer UVA pointers (peer_ptrs_host[world], HOST array of device addresses)
  * ------------------------------------------------------------------------------------------- */
 int lgb_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int32_t rank, int32_t world, void* stream);
+/* The exchange the sharded engine ships: the two barriers and the reduce + republish loop in ONE launch, no host
+ * synchronisation, replayable from a CUDA graph.  `x` describes ONE symmetric arena (same size on every rank): its
+ * multicast address (NULL when the fabric has none: peer loads / stores are used), the arena's address on every rank
+ * and a symmetric, zero-initialised array of n_channels * lgb_exchange_pad_words(world) uint32 signal slots on every
+ * rank.  The call reduces the n_floats at byte_offset of the arena in place.  Exchanges that may be in flight at the
+ * same time (different streams) must use different channels; every rank must issue the exchanges of one channel in the
+ * same order.  LGB_EXCHANGE_NO_BARRIER skips both barriers (single-process tests only).  A barrier that waits longer
+ * than ~4 s traps. */
+#define LGB_EXCHANGE_MAX_WORLD 16
+#define LGB_EXCHANGE_NO_BARRIER 1
+typedef struct lgb_exchange {
+  void* multicast_base;                          /* NVSwitch multicast mapping of the arena, or NULL */
+  void* peer_base[LGB_EXCHANGE_MAX_WORLD];       /* the arena on rank r (UVA / symmetric-memory pointer) */
+  void* pad_base[LGB_EXCHANGE_MAX_WORLD];        /* the signal-slot array on rank r */
+  int32_t rank, world, n_channels, _pad;
+} lgb_exchange;
+int lgb_exchange_pad_words(int32_t world);
+int lgb_exchange_allreduce_f32(const lgb_exchange* x, int64_t byte_offset, int64_t n_floats, int32_t channel,
+                               int32_t flags, void* stream);
 int lgb_peer_allreduce_f32(const uint64_t* peer_ptrs_host, int64_t n_floats, int32_t rank, int32_t world,
                            void* stream);
 

@@ -34,12 +34,18 @@ class LgbBprArgs(C.Structure):
     _fields_ = [
         ("uf", c_vp), ("u0", c_vp), ("pf", c_vp), ("p0", c_vp), ("nf", c_vp), ("n0", c_vp),
         ("iu", c_vp), ("ip", c_vp), ("in_", c_vp),
-        ("B", c_i64), ("B_norm", c_i64), ("d", c_i32), ("lambda_", c_f32), ("gscale", c_f32), ("_pad", c_i32),
+        ("B", c_i64), ("B_norm", c_i64), ("d", c_i32), ("lambda_", c_f32), ("gscale", c_f32), ("flags", c_i32),
         ("user_lo", c_i64), ("user_hi", c_i64),
         ("gout", c_vp),
         ("duf", c_vp), ("du0", c_vp), ("dpf", c_vp), ("dp0", c_vp), ("dnf", c_vp), ("dn0", c_vp),
         ("loss", c_vp), ("ws", c_vp),
     ]
+
+
+class LgbExchange(C.Structure):
+    """struct lgb_exchange (include/laplace_b200.h)."""
+    _fields_ = [("multicast_base", c_vp), ("peer_base", c_vp * 16), ("pad_base", c_vp * 16),
+                ("rank", c_i32), ("world", c_i32), ("n_channels", c_i32), ("_pad", c_i32)]
 
 
 # name -> (restype, argtypes); must list EVERY function include/laplace_b200.h declares
@@ -50,6 +56,7 @@ PROTOTYPES = {
     "lgb_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "lgb_csr_build_ws_bytes": (C.c_int, [c_i64, c_i64, C.POINTER(c_sz)]),
     "lgb_csr_build": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "lgb_csr_build_check": (C.c_int, [c_vp, c_vp]),
     "lgb_csr_transpose_ws_bytes": (C.c_int, [c_i64, c_i64, C.POINTER(c_sz)]),
     "lgb_csr_transpose": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgb_gather_f32": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
@@ -66,10 +73,13 @@ PROTOTYPES = {
     "lgb_row_div_by_degree": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_gcn_values": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "lgb_accumulate": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "lgb_mean_rows": (C.c_int, [C.POINTER(c_vp), c_i32, c_i64, c_f32, c_vp, c_vp]),
     "lgb_zero": (C.c_int, [c_vp, c_sz, c_vp]),
     "lgb_scale_concat": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_f32, c_vp, c_vp]),
     "lgb_bpr_blocks": (c_i64, [c_i64]),
     "lgb_bpr": (C.c_int, [C.POINTER(LgbBprArgs), c_vp]),
+    "lgb_gather_rows_owned": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_vp]),
+    "lgb_scatter_add_rows_owned": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i64, c_i64, c_vp, c_vp]),
     "lgb_edge_concat_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "lgb_edge_concat_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "lgb_edge_dot_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
@@ -82,6 +92,8 @@ PROTOTYPES = {
     "lgb_adam_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp]),
     "lgb_multimem_allreduce_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp]),
     "lgb_peer_allreduce_f32": (C.c_int, [C.POINTER(C.c_uint64), c_i64, c_i32, c_i32, c_vp]),
+    "lgb_exchange_pad_words": (C.c_int, [c_i32]),
+    "lgb_exchange_allreduce_f32": (C.c_int, [C.POINTER(LgbExchange), c_i64, c_i64, c_i32, c_i32, c_vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -78,8 +78,11 @@ class DeviceCSR:
     # ---- construction -------------------------------------------------------------------
     @classmethod
     def from_coo(cls, row: torch.Tensor, col: torch.Tensor, n_rows: int, n_cols: int,
-                 chunk: int = DEFAULT_CHUNK, want_perm: bool = False) -> "DeviceCSR":
-        """SparseTensor(row, col, sparse_sizes) semantics (reference data/lightgcn_loader.py:65-79)."""
+                 chunk: int = DEFAULT_CHUNK, want_perm: bool = False, validate: bool = True) -> "DeviceCSR":
+        """SparseTensor(row, col, sparse_sizes) semantics (reference data/lightgcn_loader.py:65-79), including its
+        range assertion: an index outside ``sparse_sizes`` raises (``validate`` costs one stream synchronisation; a caller
+        that builds several graphs per batch may pass False and call ``check_built()`` once on the last one -- out-of-range
+        entries are clamped on the device either way, so nothing is ever written out of bounds)."""
         _lib.require_cuda(row, col)
         lib = _lib.load()
         row, col = _lib.i64c(row), _lib.i64c(col)
@@ -94,10 +97,21 @@ class DeviceCSR:
         with torch.cuda.device(dev):
             check(lib.lgb_csr_build(ptr(row), ptr(col), nnz, n_rows, n_cols, ptr(rowptr), ptr(colidx), ptr(perm),
                                     ptr(ws), ws.numel(), stream()), "csr_build")
+            if validate:
+                check(lib.lgb_csr_build_check(ptr(ws), stream()), "csr_build (index range)")
         _lib.count_launch(3)
         g = cls(n_rows, n_cols, rowptr, colidx, None, chunk)
         g.perm = perm
+        g._build_ws = None if validate else ws          # keeps the status word alive until check_built()
         return g
+
+    def check_built(self) -> None:
+        """Deferred index-range check of a graph built with ``validate=False`` (synchronises the current stream)."""
+        ws = getattr(self, "_build_ws", None)
+        if ws is not None:
+            with torch.cuda.device(self.device):
+                check(_lib.load().lgb_csr_build_check(ptr(ws), stream()), "csr_build (index range)")
+            self._build_ws = None
 
     def _build_plan(self) -> None:
         lib = _lib.load()

@@ -42,12 +42,14 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
   float sp = 0.f, reg = 0.f;
 
   int64_t ru = 0, rp = 0, rn = 0;
+  bool own_u = true;                  // LGB_BPR_FILTER_USER_ROWS_ONLY: foreign triples keep their item rows
   if (active) {
     ru = INDEXED ? a.iu[b] : b;
     rp = INDEXED ? a.ip[b] : b;
     rn = INDEXED ? a.in[b] : b;
     if (INDEXED && a.user_hi > 0) {   // this rank only owns users [user_lo, user_hi)
-      active = ru >= a.user_lo && ru < a.user_hi;
+      own_u = ru >= a.user_lo && ru < a.user_hi;
+      if (!(a.flags & LGB_BPR_FILTER_USER_ROWS_ONLY)) active = own_u;
       ru -= a.user_lo;
     }
   }
@@ -57,10 +59,10 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
   for (int q = 0; q < VPL; ++q) {
     const int f = lig + q * G;
     const bool ok = active && f < d4;
-    uf[q] = ok ? ld_gather_f4((const float4*)a.uf + ru * d4 + f) : f4_zero();
+    uf[q] = (ok && own_u) ? ld_gather_f4((const float4*)a.uf + ru * d4 + f) : f4_zero();
     pf[q] = ok ? ld_gather_f4((const float4*)a.pf + rp * d4 + f) : f4_zero();
     nf[q] = ok ? ld_gather_f4((const float4*)a.nf + rn * d4 + f) : f4_zero();
-    u0[q] = (ok && a.u0) ? ld_gather_f4((const float4*)a.u0 + ru * d4 + f) : f4_zero();
+    u0[q] = (ok && own_u && a.u0) ? ld_gather_f4((const float4*)a.u0 + ru * d4 + f) : f4_zero();
     p0[q] = (ok && a.p0) ? ld_gather_f4((const float4*)a.p0 + rp * d4 + f) : f4_zero();
     n0[q] = (ok && a.n0) ? ld_gather_f4((const float4*)a.n0 + rn * d4 + f) : f4_zero();
     pos += dot4(uf[q], pf[q]);
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
         const float4 gp = scale4(uf[q], cf);
         const float4 gn = scale4(uf[q], -cf);
         if (INDEXED) {
-          if (a.duf) red_add_f4((float4*)a.duf + ru * d4 + f, gu);
+          if (a.duf && own_u) red_add_f4((float4*)a.duf + ru * d4 + f, gu);
           if (a.dpf) red_add_f4((float4*)a.dpf + rp * d4 + f, gp);
           if (a.dnf) red_add_f4((float4*)a.dnf + rn * d4 + f, gn);
         } else {
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_kernel(const BprParams p) {
       }
       if (want_0) {
         if (INDEXED) {
-          if (a.du0) red_add_f4((float4*)a.du0 + ru * d4 + f, scale4(u0[q], c0));
+          if (a.du0 && own_u) red_add_f4((float4*)a.du0 + ru * d4 + f, scale4(u0[q], c0));
           if (a.dp0) red_add_f4((float4*)a.dp0 + rp * d4 + f, scale4(p0[q], c0));
           if (a.dn0) red_add_f4((float4*)a.dn0 + rn * d4 + f, scale4(n0[q], c0));
         } else {
@@ -143,19 +145,24 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_scalar_kernel(const BprParams
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (BPR_THREADS / 32) + warp;
   bool active = b < a.B;
+  bool own_u = true;
   const int d = a.d;
   int64_t ru = 0, rp = 0, rn = 0;
   if (active) {
     ru = INDEXED ? a.iu[b] : b; rp = INDEXED ? a.ip[b] : b; rn = INDEXED ? a.in[b] : b;
-    if (INDEXED && a.user_hi > 0) { active = ru >= a.user_lo && ru < a.user_hi; ru -= a.user_lo; }
+    if (INDEXED && a.user_hi > 0) {
+      own_u = ru >= a.user_lo && ru < a.user_hi;
+      if (!(a.flags & LGB_BPR_FILTER_USER_ROWS_ONLY)) active = own_u;
+      ru -= a.user_lo;
+    }
   }
   float pos = 0.f, neg = 0.f, rsq = 0.f;
   if (active)
     for (int f = lane; f < d; f += 32) {
-      const float u = a.uf[ru * d + f];
+      const float u = own_u ? a.uf[ru * d + f] : 0.f;
       pos += u * a.pf[rp * d + f];
       neg += u * a.nf[rn * d + f];
-      if (a.u0) { const float v = a.u0[ru * d + f]; rsq += v * v; }
+      if (a.u0 && own_u) { const float v = a.u0[ru * d + f]; rsq += v * v; }
       if (a.p0) { const float v = a.p0[rp * d + f]; rsq += v * v; }
       if (a.n0) { const float v = a.n0[rn * d + f]; rsq += v * v; }
     }
@@ -169,12 +176,12 @@ __global__ void __launch_bounds__(BPR_THREADS) bpr_scalar_kernel(const BprParams
     const float cf = -g * sig / (float)(a.B_norm > 0 ? a.B_norm : a.B) * a.gscale;
     const float c0 = 2.f * a.lambda * g;
     for (int f = lane; f < d; f += 32) {
-      const float u = a.uf[ru * d + f], pp = a.pf[rp * d + f], nn = a.nf[rn * d + f];
+      const float u = own_u ? a.uf[ru * d + f] : 0.f, pp = a.pf[rp * d + f], nn = a.nf[rn * d + f];
       if (INDEXED) {
-        if (a.duf) atomicAdd(a.duf + ru * d + f, cf * (pp - nn));
+        if (a.duf && own_u) atomicAdd(a.duf + ru * d + f, cf * (pp - nn));
         if (a.dpf) atomicAdd(a.dpf + rp * d + f, cf * u);
         if (a.dnf) atomicAdd(a.dnf + rn * d + f, -cf * u);
-        if (a.du0) atomicAdd(a.du0 + ru * d + f, c0 * a.u0[ru * d + f]);
+        if (a.du0 && own_u) atomicAdd(a.du0 + ru * d + f, c0 * a.u0[ru * d + f]);
         if (a.dp0) atomicAdd(a.dp0 + rp * d + f, c0 * a.p0[rp * d + f]);
         if (a.dn0) atomicAdd(a.dn0 + rn * d + f, c0 * a.n0[rn * d + f]);
       } else {
@@ -217,6 +224,23 @@ __global__ void __launch_bounds__(1024) bpr_finalize_kernel(const float* __restr
   }
 }
 
+// Rows of a user-sharded table for a GLOBAL batch: dst[b] = src[idx[b] - lo] when this rank owns user idx[b], else 0
+// (the sum over ranks of these buffers is the gathered batch); and the way back: dst[idx[b] - lo] += src[b] for owned b.
+__global__ void __launch_bounds__(256) gather_rows_owned_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                                                int64_t B, int d, int64_t lo, int64_t hi, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d) return;
+  const int64_t b = i / d, u = idx[b];
+  dst[i] = (u >= lo && u < hi) ? src[(u - lo) * d + (i - b * d)] : 0.f;
+}
+__global__ void __launch_bounds__(256) scatter_add_rows_owned_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx,
+                                                                     int64_t B, int d, int64_t lo, int64_t hi, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * d) return;
+  const int64_t b = i / d, u = idx[b];
+  if (u >= lo && u < hi) atomicAdd(dst + (u - lo) * d + (i - b * d), src[i]);
+}
+
 static int groups_per_block(int d) {
   if (d % 4 != 0) return BPR_THREADS / 32;
   const int d4 = d / 4;
@@ -254,6 +278,8 @@ int lgb_bpr(const lgb_bpr_args* a, void* stream_) {
   const int n_idx = (a->iu != nullptr) + (a->ip != nullptr) + (a->in != nullptr);
   LGB_REQUIRE(n_idx == 0 || n_idx == 3, LGB_EINVAL, "lgb_bpr: index arrays must be all NULL or all set");
   LGB_REQUIRE(!a->loss || a->ws, LGB_EINVAL, "lgb_bpr: loss requested without workspace");
+  LGB_REQUIRE(!(a->flags & LGB_BPR_FILTER_USER_ROWS_ONLY) || !(a->loss || a->duf || a->dpf || a->dnf), LGB_EINVAL,
+              "lgb_bpr: LGB_BPR_FILTER_USER_ROWS_ONLY serves the layer-0 regulariser gradients only (no loss, no *_f gradients)");
   if (a->B == 0) {
     if (a->loss) LGB_CUDA(cudaMemsetAsync(a->loss, 0, sizeof(float), stream));
     return LGB_OK;
@@ -270,6 +296,26 @@ int lgb_bpr(const lgb_bpr_args* a, void* stream_) {
     bpr_finalize_kernel<<<1, 1024, 0, stream>>>(a->ws, p.nblocks, a->B_norm > 0 ? a->B_norm : a->B, a->lambda, a->loss);
     LGB_LAUNCH_CHECK();
   }
+  return LGB_OK;
+}
+
+int lgb_gather_rows_owned(const float* src, const int64_t* idx, int64_t B, int32_t d, int64_t lo, int64_t hi, float* dst,
+                          void* stream) {
+  LGB_REQUIRE(B >= 0 && d > 0 && lo <= hi && (B == 0 || (idx && dst && (src || lo == hi))), LGB_EINVAL,
+              "lgb_gather_rows_owned: bad argument");
+  if (B == 0) return LGB_OK;
+  gather_rows_owned_kernel<<<(unsigned)((B * d + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, B, d, lo, hi, dst);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_scatter_add_rows_owned(const float* src, const int64_t* idx, int64_t B, int32_t d, int64_t lo, int64_t hi, float* dst,
+                               void* stream) {
+  LGB_REQUIRE(B >= 0 && d > 0 && lo <= hi && (B == 0 || (src && idx && (dst || lo == hi))), LGB_EINVAL,
+              "lgb_scatter_add_rows_owned: bad argument");
+  if (B == 0) return LGB_OK;
+  scatter_add_rows_owned_kernel<<<(unsigned)((B * d + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, B, d, lo, hi, dst);
+  LGB_LAUNCH_CHECK();
   return LGB_OK;
 }
 

@@ -85,6 +85,24 @@ __device__ __forceinline__ float4 ld_stream_f4_hint(const float4* p, uint64_t po
                : "l"(p), "l"(pol));
   return v;
 }
+// Epilogue operands (acc_in / resid rows): read once, but the caller may update them IN PLACE (acc_out == acc_in), so they
+// must not go through the read-only (.nc) path, whose data has to stay constant for the whole kernel.
+__device__ __forceinline__ float4 ld_once_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_once_f4_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return v;
+}
 // Ask L2 for a line that will be read later in this thread's dependent chain (no register, no scoreboard entry).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 256-bit per-lane global accesses (new on sm_100: SASS LDG.E.256 / STG.E.256): 32 contiguous bytes of an embedding row in
@@ -102,6 +120,14 @@ __device__ __forceinline__ f4x2 ld_stream_f8(const float4* p) {   // read-once 3
   asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
                : "l"(p));
+  return v;
+}
+__device__ __forceinline__ f4x2 ld_once_f8(const float4* p) {     // see ld_once_f4: may alias an output of the same kernel
+  f4x2 v;
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+               : "l"(p)
+               : "memory");
   return v;
 }
 __device__ __forceinline__ void st_f8(float4* p, const float4& a, const float4& b) {

@@ -28,11 +28,21 @@ static int bits_for(uint64_t max_value_exclusive) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Indices outside [0, n_rows) x [0, n_cols) (e.g. item ids that were not shifted by both_indexes_from_zero) are COUNTED in
+// *bad and clamped into range, so that nothing downstream writes out of bounds; the caller turns a non-zero count into the
+// error torch_sparse's SparseTensor raises for the same input (lgb_csr_build_check).
 __global__ void make_keys_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t nnz,
-                                 int64_t n_cols, int64_t* __restrict__ keys, int32_t* __restrict__ idx) {
+                                 int64_t n_rows, int64_t n_cols, int64_t* __restrict__ keys, int32_t* __restrict__ idx,
+                                 int32_t* __restrict__ bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nnz) {
-    keys[i] = row[i] * n_cols + col[i];
+    int64_t r = row[i], c = col[i];
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) {
+      atomicAdd(bad, 1);
+      r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);
+      c = c < 0 ? 0 : (c >= n_cols ? n_cols - 1 : c);
+    }
+    keys[i] = r * n_cols + c;
     if (idx) idx[i] = (int32_t)i;
   }
 }
@@ -214,7 +224,7 @@ int lgb_sm_count(int* out) {
   return LGB_OK;
 }
 
-// workspace layout: keys_in | keys_out | idx_in | idx_out | cub temp
+// workspace layout: 256 bytes of status (ws[0] = count of out-of-range indices) | keys_in | keys_out | idx_in | idx_out | cub temp
 int lgb_csr_build_ws_bytes(int64_t nnz, int64_t n_rows, size_t* bytes) {
   LGB_REQUIRE(bytes && nnz >= 0 && n_rows >= 0, LGB_EINVAL, "lgb_csr_build_ws_bytes: bad argument");
   LGB_REQUIRE(nnz < (1ll << 31) && n_rows < (1ll << 31) - 1, LGB_ERANGE,
@@ -222,7 +232,7 @@ int lgb_csr_build_ws_bytes(int64_t nnz, int64_t n_rows, size_t* bytes) {
   size_t temp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, temp, (const int64_t*)nullptr, (int64_t*)nullptr, (const int32_t*)nullptr,
                                   (int32_t*)nullptr, (int)nnz, 0, 64, (cudaStream_t)0);
-  *bytes = 2 * align_up((size_t)nnz * 8) + 2 * align_up((size_t)nnz * 4) + align_up(temp) + 256;
+  *bytes = 256 + 2 * align_up((size_t)nnz * 8) + 2 * align_up((size_t)nnz * 4) + align_up(temp) + 256;
   return LGB_OK;
 }
 
@@ -236,11 +246,15 @@ int lgb_csr_build(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n
   if (rc) return rc;
   LGB_REQUIRE(n_cols < (1ll << 31), LGB_ERANGE, "lgb_csr_build: n_cols=%lld exceeds int32", (long long)n_cols);
   LGB_REQUIRE(ws_bytes >= need && (ws || nnz == 0), LGB_EWS, "lgb_csr_build: workspace %zu < %zu", ws_bytes, need);
+  LGB_REQUIRE(nnz == 0 || (n_rows > 0 && n_cols > 0), LGB_EINVAL, "lgb_csr_build: %lld entries in an empty %lld x %lld matrix",
+              (long long)nnz, (long long)n_rows, (long long)n_cols);
+  if (ws) LGB_CUDA(cudaMemsetAsync(ws, 0, 256, stream));   // ws[0]: int32 count of out-of-range indices (lgb_csr_build_check)
   if (nnz == 0) {
     LGB_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (size_t)(n_rows + 1), stream));
     return LGB_OK;
   }
-  char* p = (char*)ws;
+  int32_t* bad = (int32_t*)ws;
+  char* p = (char*)ws + 256;
   int64_t* keys_in = (int64_t*)p;  p += align_up((size_t)nnz * 8);
   int64_t* keys_out = (int64_t*)p; p += align_up((size_t)nnz * 8);
   int32_t* idx_in = (int32_t*)p;   p += align_up((size_t)nnz * 4);
@@ -248,7 +262,7 @@ int lgb_csr_build(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n
   void* temp = p;
   size_t temp_bytes = ws_bytes - (size_t)(p - (char*)ws);
   const int T = 256;
-  make_keys_kernel<<<blocks_for(nnz, T), T, 0, stream>>>(row, col, nnz, n_cols, keys_in, idx_in);
+  make_keys_kernel<<<blocks_for(nnz, T), T, 0, stream>>>(row, col, nnz, n_rows, n_cols, keys_in, idx_in, bad);
   LGB_LAUNCH_CHECK();
   int end_bit = bits_for((uint64_t)n_rows * (uint64_t)(n_cols > 0 ? n_cols : 1));
   LGB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, idx_in, idx_out, (int)nnz, 0, end_bit,
@@ -256,6 +270,15 @@ int lgb_csr_build(const int64_t* row, const int64_t* col, int64_t nnz, int64_t n
   split_keys_kernel<<<blocks_for(nnz + 1, T), T, 0, stream>>>(keys_out, idx_out, nnz, n_rows, n_cols, rowptr, colidx,
                                                                perm);
   LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_csr_build_check(const void* ws, void* stream_) {
+  LGB_REQUIRE(ws, LGB_EINVAL, "lgb_csr_build_check: null workspace");
+  int32_t bad = 0;
+  LGB_CUDA(cudaMemcpyAsync(&bad, ws, sizeof(bad), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  LGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
+  LGB_REQUIRE(bad == 0, LGB_ERANGE, "lgb_csr_build: %d entries have a row / column index outside sparse_sizes", (int)bad);
   return LGB_OK;
 }
 

@@ -144,14 +144,14 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
       y1.x = __fdiv_rn(y1.x, c); y1.y = __fdiv_rn(y1.y, c); y1.z = __fdiv_rn(y1.z, c); y1.w = __fdiv_rn(y1.w, c);
     }
     if (p.resid) {
-      const f4x2 t = ld_stream_f8(reinterpret_cast<const float4*>(p.resid) + o);
+      const f4x2 t = ld_once_f8(reinterpret_cast<const float4*>(p.resid) + o);
       y0 = f4_add(y0, t.a); y1 = f4_add(y1, t.b);
     }
     if (p.Y) st_f8(reinterpret_cast<float4*>(p.Y) + o, y0, y1);
     if (p.acc_out) {
       float4 a0 = y0, a1 = y1;
       if (p.acc_in) {
-        const f4x2 t = ld_stream_f8(reinterpret_cast<const float4*>(p.acc_in) + o);
+        const f4x2 t = ld_once_f8(reinterpret_cast<const float4*>(p.acc_in) + o);
         a0 = f4_add(t.a, y0); a1 = f4_add(t.b, y1);
       }
       if (p.acc_div != 1.0f) {
@@ -173,14 +173,14 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
     }
     if (p.resid) {
       const float4* src = reinterpret_cast<const float4*>(p.resid) + rowoff + f;
-      y = f4_add(y, EF ? ld_stream_f4_hint(src, pol) : ld_stream_f4(src));
+      y = f4_add(y, EF ? ld_once_f4_hint(src, pol) : ld_once_f4(src));
     }
     if (p.Y) st_f4(reinterpret_cast<float4*>(p.Y) + rowoff + f, y);
     if (p.acc_out) {
       float4 a = y;
       if (p.acc_in) {
         const float4* src = reinterpret_cast<const float4*>(p.acc_in) + rowoff + f;
-        a = f4_add(EF ? ld_stream_f4_hint(src, pol) : ld_stream_f4(src), y);
+        a = f4_add(EF ? ld_once_f4_hint(src, pol) : ld_once_f4(src), y);
       }
       if (p.acc_div != 1.0f) {
         a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
       for (int q = 0; q < VPL; ++q) {
         const int f = lane + q * G;
         const bool ok = row_out && f < p.d4;
-        pre_acc[q] = (ok && p.acc_in) ? ld_stream_f4(reinterpret_cast<const float4*>(p.acc_in) + (size_t)r0 * p.d4 + f) : f4_zero();
-        pre_res[q] = (ok && p.resid) ? ld_stream_f4(reinterpret_cast<const float4*>(p.resid) + (size_t)r0 * p.d4 + f) : f4_zero();
+        pre_acc[q] = (ok && p.acc_in) ? ld_once_f4(reinterpret_cast<const float4*>(p.acc_in) + (size_t)r0 * p.d4 + f) : f4_zero();
+        pre_res[q] = (ok && p.resid) ? ld_once_f4(reinterpret_cast<const float4*>(p.resid) + (size_t)r0 * p.d4 + f) : f4_zero();
       }
       float4 acc[VPL];
 #pragma unroll
@@ -858,7 +858,8 @@ __global__ void row_div_kernel(const float* __restrict__ X, const int32_t* __res
   out[i] = __fdiv_rn(X[i], (float)max(rowptr[r + 1] - rowptr[r], 1));
 }
 
-__global__ void accumulate_kernel(const float* __restrict__ y, const float* acc, const float* __restrict__ resid, int64_t n,
+// y, acc and out may alias (in-place accumulate): no __restrict__ on them
+__global__ void accumulate_kernel(const float* y, const float* acc, const float* __restrict__ resid, int64_t n,
                                   float div, float* out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -868,6 +869,31 @@ __global__ void accumulate_kernel(const float* __restrict__ y, const float* acc,
     if (acc) v = acc[i] + v;
     if (div != 1.0f) v = __fdiv_rn(v, div);
     out[i] = v;
+  }
+}
+
+// out = (((s0 + s1) + s2) + ...) / div over up to MEAN_MAX equally-shaped buffers: the layer mean of LightGCN
+// (model/lightgcn.py:67-68) in ONE pass when the layer outputs are kept (the sharded engine's two independent layer chains),
+// same left-to-right fp32 order as the fused accumulate epilogue.
+constexpr int MEAN_MAX = 8;
+struct MeanSrcs { const float* s[MEAN_MAX]; };
+__global__ void __launch_bounds__(256) mean_rows_kernel(const MeanSrcs srcs, int count, int64_t n, float div, float* __restrict__ out, int vec) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    const int64_t n4 = n / 4;
+    for (; i < n4; i += stride) {
+      float4 a = ld_stream_f4(reinterpret_cast<const float4*>(srcs.s[0]) + i);
+      for (int k = 1; k < count; ++k) a = f4_add(a, ld_stream_f4(reinterpret_cast<const float4*>(srcs.s[k]) + i));
+      if (div != 1.0f) { a.x = __fdiv_rn(a.x, div); a.y = __fdiv_rn(a.y, div); a.z = __fdiv_rn(a.z, div); a.w = __fdiv_rn(a.w, div); }
+      st_f4(reinterpret_cast<float4*>(out) + i, a);
+    }
+  } else {
+    for (; i < n; i += stride) {
+      float a = srcs.s[0][i];
+      for (int k = 1; k < count; ++k) a += srcs.s[k][i];
+      out[i] = div != 1.0f ? __fdiv_rn(a, div) : a;
+    }
   }
 }
 
@@ -940,9 +966,15 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   p.mean = (flags & LGB_SPMM_MEAN) ? 1 : 0; p.partial = partial_ws;
   p.split_row = split_row; p.y_tail = y_tail;
   if (p.n_tasks > 0) {
-    LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->long_rows && g->long_ptr, LGB_EINVAL,
-                "lgb_spmm: plan has %lld tasks but plan arrays / partial workspace missing", (long long)p.n_tasks);
+    LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->task_end && g->long_rows && g->long_ptr, LGB_EINVAL,
+                "lgb_spmm: plan has %lld tasks but plan arrays (task_row/start/end, long_rows/ptr) / partial workspace missing",
+                (long long)p.n_tasks);
   }
+  // vector paths: every row pointer the kernels touch with 128-bit (256-bit: variants 23-27) accesses must be aligned
+  const uintptr_t all_ptrs = (uintptr_t)X | (uintptr_t)Y | (uintptr_t)resid | (uintptr_t)acc_in | (uintptr_t)acc_out |
+                             (uintptr_t)partial_ws | (uintptr_t)y_tail;
+  LGB_REQUIRE(d % 4 != 0 || (all_ptrs & 15) == 0, LGB_EINVAL,
+              "lgb_spmm: X / Y / resid / acc_in / acc_out / partial_ws / y_tail must be 16-byte aligned when d %% 4 == 0");
   if (d % 4 != 0) {
     // scalar path ignores the plan (tiny shapes only)
     const int64_t blocks = (p.n_rows + SPMM_WARPS - 1) / SPMM_WARPS;
@@ -954,7 +986,9 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   // Variant 0 is the tuned default.  Measured on B200 (profiles/r1b_*): the kernel is latency-bound, so the
   // configuration that keeps 64 warps resident per SM (<= 32 registers: gather unroll 2, __launch_bounds__(128,16))
   // beats deeper unrolls (72 regs -> 28 warps) by 1.3x and the software-pipelined persistent variant by 1.5x.
-  const int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xFF;
+  int variant = (flags >> LGB_SPMM_VARIANT_SHIFT) & 0xFF;
+  if (variant >= 23 && variant <= 27 && ((all_ptrs & 31) != 0 || (d * 4) % 32 != 0))
+    variant = 0;   // the 256-bit forms need 32-byte aligned rows: run the default kernel instead of faulting
   if ((int64_t)g->n_cols * d4 > 0x7fffffffll || variant == 17) {
     // element index into X does not fit 32 bits (a table of > 34 GB): the one kernel family compiled with 64-bit indexing
     // (variant 17 forces it, so the tests can reach it with small tables)
@@ -1054,6 +1088,26 @@ int lgb_accumulate(const float* y, const float* acc, const float* resid, int64_t
   if (n == 0) return LGB_OK;
   const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
   accumulate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, acc, resid, n, div, out);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_mean_rows(const float* const* srcs_host, int32_t count, int64_t n, float div, float* out, void* stream) {
+  LGB_REQUIRE(srcs_host && count >= 1 && count <= MEAN_MAX && n >= 0 && div != 0.f && (n == 0 || out), LGB_EINVAL,
+              "lgb_mean_rows: bad argument (1 <= count <= %d)", MEAN_MAX);
+  if (n == 0) return LGB_OK;
+  MeanSrcs srcs;
+  uintptr_t bits = (uintptr_t)out;
+  for (int k = 0; k < MEAN_MAX; ++k) {
+    srcs.s[k] = k < count ? srcs_host[k] : nullptr;
+    LGB_REQUIRE(k >= count || srcs.s[k], LGB_EINVAL, "lgb_mean_rows: source %d is NULL", k);
+    LGB_REQUIRE(k >= count || srcs.s[k] != out, LGB_EINVAL, "lgb_mean_rows: out aliases source %d", k);
+    bits |= (uintptr_t)srcs.s[k];
+  }
+  const int vec = (n % 4 == 0) && ((bits & 15) == 0);
+  const int64_t work = vec ? n / 4 : n;
+  const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, 148 * 16);
+  mean_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(srcs, count, n, div, out, vec);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
 }

@@ -1,36 +1,50 @@
-"""Multi-GPU LightGCN: users range-sharded, items replicated, one all-reduce of the [I, d] item block per
-propagation layer (SURVEY.md 8e "bipartite-aware 1.5-D row sharding").  One process per GPU, NCCL through
-``torch.distributed`` (the reference has no distributed code at all: this layer is new).
+"""Multi-GPU LightGCN: users range-sharded, items replicated, one exchange of the [I, d] item block per propagation
+layer (SURVEY.md 8e "bipartite-aware 1.5-D row sharding").  One process per GPU; ``torch.distributed`` is the plumbing
+(rendezvous, symmetric-memory allocation), the exchange itself is a hand-written kernel over NVSwitch multicast /
+NVLink peer memory (csrc/peer.cu), NCCL all-reduce being the fallback.  The reference has no distributed code at all:
+this layer is new.
 
 Per rank g (owning users [u_g, u_{g+1}), split at nnz-balanced points):
-    local table   [U_g + I, d]   rows 0..U_g-1 = owned user embeddings, rows U_g.. = ALL item embeddings (replicated)
-    local graph   the symmetric block [[0, R_g], [R_g^T, 0]] with the GLOBAL symmetric normalisation
-                  (user degrees are local, item degrees are all-reduced once at build time)
-    two row views of that CSR (free: rowptr slices)
-        G_users : rows 0..U_g-1      users <- items   complete locally (items are replicated)
-        G_items : rows U_g..U_g+I-1  items <- users   PARTIAL sums over the owned users only
-A layer is   Y_items(partial) = G_items X   ->  all-reduce(Y_items) on the comm stream
-          || Y_users = G_users X with the fused accumulate epilogue on the compute stream   (overlap)
-          -> item rows: acc += all-reduced Y_items (small [I, d] pass).
-User embeddings never move.  The backward is the same pattern on the (symmetric) block with the
-residual r = dE_f/(K+1); BPR triples are handled by the rank that owns the user, item-row gradient
-contributions are partial sums folded into the all-reduces.
+    table     [U_g + I, d]     rows 0..U_g-1 = owned user embeddings, rows U_g.. = ALL item embeddings (replicated)
+    G_users   [U_g, I]   CSR   R_g    with the GLOBAL symmetric normalisation (item degrees all-reduced once at build time)
+    G_items   [I, U_g]   CSR   R_g^T  (partial sums over the owned users only)
+A propagation layer k maps (xu, xi) -> (yu, yi):
+    yu = G_users xi                          complete locally (items are replicated)
+    yi = exchange(G_items xu)                sum over ranks of the partial item rows
+yu_k only needs xi_k and yi_k only needs xu_k, so the K layers fall apart into TWO INDEPENDENT CHAINS
+    chain 0:  U(0) -> I(1) -> X(1) -> U(2) -> I(3) -> X(3) ...          (U = users SpMM, I = items SpMM, X = exchange)
+    chain 1:  I(0) -> X(0) -> U(1) -> I(2) -> X(2) -> U(3) ...
+which run on two streams: while one chain waits for its exchange the other computes, and the two SpMM kernels of a
+layer fill each other's tail.  The exchange kernels run on high-priority streams so that their few CTAs are scheduled
+ahead of the queued SpMM CTAs.  The layer mean is one pass over the kept layer outputs at the end (lgb_mean_rows, same
+left-to-right order as the single-GPU fused epilogue).  The backward is the same pair of chains on the (symmetric)
+block with the residual r = dE_f/(K+1): user rows add r in the SpMM epilogue, the item-row residual is added to rank
+0's partial sums so that the exchange delivers it exactly once.
 
-The collective / kernel calls go through a small ``ops`` object so that the partition + exchange logic
-can be exercised on the CPU with gloo and an oracle-backed ops object in tests/ (the product ops object
-is CUDA-only and fails loudly otherwise).
+BPR: the batch's user rows (final and layer-0: 2*B*d floats) are gathered by their owners into a small symmetric
+buffer and exchanged; every rank then evaluates ALL B triples -- loss and item-row gradients come out complete and
+bit-identical on every rank without a 27 MB collective -- and scatters the user-row gradients of the users it owns.
+A step therefore moves 2K item blocks plus one 2*B*d block; user embeddings never move.
+
+The kernel / collective calls go through a small ``ops`` object so that the partition + exchange logic can be exercised
+on the CPU with gloo and an oracle-backed ops object in tests/ (the product ops objects are CUDA-only and fail loudly
+otherwise).
 """
 from __future__ import annotations
 
+import contextlib
+import ctypes as C
 from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from ._lib import check, ptr, stream
-from .bpr import LgbBprArgs, _launch as _bpr_launch, _ws as _bpr_ws
+from ._lib import LgbBprArgs, LgbExchange, check, ptr, stream
+from .bpr import _launch as _bpr_launch, _ws as _bpr_ws
 from .csr import DEFAULT_CHUNK, DeviceCSR
+
+N_CHANNELS = 3          # exchange channels: one per layer chain + the BPR batch rows
 
 
 # --------------------------------------------------------------------------------------------
@@ -59,44 +73,99 @@ def local_block(users: torch.Tensor, items: torch.Tensor, lo: int, hi: int) -> T
 
 
 # --------------------------------------------------------------------------------------------
-# CUDA ops object
+# CUDA ops objects
 # --------------------------------------------------------------------------------------------
+class _Done:
+    def wait(self):
+        pass
+
+
+class _StreamWait:
+    """Handle of an exchange running on a side stream: wait() makes the stream that is current THEN wait for it."""
+
+    def __init__(self, comm, device):
+        self.comm, self.device = comm, device
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+
 class CudaOps:
-    """liblaplace_b200 kernels + NCCL collectives.  ``comm`` stream carries the all-reduces."""
+    """liblaplace_b200 kernels; the item-block exchange is an NCCL all-reduce on a high-priority side stream (the fallback
+    of ``SymmOps``, and the only collective path on a fabric without peer access)."""
+
+    kind = "nccl"
 
     def __init__(self, device: torch.device, group=None):
         if device.type != "cuda":
             raise RuntimeError("ShardedLightGCN needs CUDA devices (no CPU fallback); tests inject their own ops object")
         self.device, self.group = device, group
-        self.comm = torch.cuda.Stream(device=device)
+        hi_pri = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
+        # one comm stream per exchange channel; NCCL serialises its collectives anyway, so this class uses one for all
+        self.comm = [torch.cuda.Stream(device=device, priority=hi_pri)] * N_CHANNELS
+        self.chains = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
         self._bpr_ws = None
         self.exchange_events = None     # set to a list to record (start, end, bytes) CUDA events of every item-block exchange
 
-    # graph ----------------------------------------------------------------------------------
-    def build_graph(self, row, col, n, dinv):
+    # streams --------------------------------------------------------------------------------------
+    def fork(self, two_streams: bool):
+        """Stream contexts of the two layer chains, ordered after the work queued on the current stream."""
+        if not two_streams:
+            return [contextlib.nullcontext(), contextlib.nullcontext()]
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.chains:
+            s.wait_stream(cur)
+        return [torch.cuda.stream(s) for s in self.chains]
+
+    def join(self, two_streams: bool):
+        if two_streams:
+            cur = torch.cuda.current_stream(self.device)
+            for s in self.chains:
+                cur.wait_stream(s)
+
+    # graph ----------------------------------------------------------------------------------------
+    def build_views(self, row, col, Ug: int, I: int, dinv):
+        """The local symmetric block [[0, R_g], [R_g^T, 0]] -> (G_users [Ug, I], G_items [I, Ug]) sharing one colidx / val array
+        pair: rows [0, Ug) with their column ids shifted to item numbering, rows [Ug, Ug+I) as they are (user numbering)."""
+        n = Ug + I
         g = DeviceCSR.from_coo(row, col, n, n, chunk=0)
         val = torch.empty(g.nnz, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(_lib.load().lgb_gcn_values(ptr(g.rowptr), ptr(g.colidx), n, g.nnz, ptr(dinv), ptr(val), stream()), "gcn_values")
         _lib.count_launch()
-        g.val = val
-        return g
+        split = int(g.rowptr[Ug])                       # entries of the user rows come first (CSR order)
+        g.colidx[:split] -= Ug
+        gu = DeviceCSR(Ug, I, g.rowptr[: Ug + 1], g.colidx, val, chunk=DEFAULT_CHUNK)
+        gi = DeviceCSR(I, Ug, g.rowptr[Ug:], g.colidx, val, chunk=DEFAULT_CHUNK)
+        gu.nnz, gi.nnz = split, g.nnz - split           # entries of the view (the arrays themselves are shared)
+        gu._struct = gi._struct = None
+        return gu, gi
+
+    def alloc_exchange(self, shapes):
+        """Buffers that ``exchange_async`` can sum over ranks in place."""
+        return [torch.zeros(*s, dtype=torch.float32, device=self.device) for s in shapes]
+
+    # kernels --------------------------------------------------------------------------------------
+    def spmm(self, g, X, Y, resid=None):
+        if g.n_rows == 0:
+            return
+        if g.n_cols == 0:                       # a rank without users (world > #users): its partial sums are zero
+            Y.zero_() if resid is None else Y.copy_(resid)
+            return
+        g.spmm(X, Y=Y, resid=resid)
 
     def row_view(self, g: DeviceCSR, lo: int, hi: int) -> DeviceCSR:
-        """Rows [lo, hi) of g as a CSR of its own (rowptr slice; colidx/val shared, offsets stay absolute)."""
+        """Rows [lo, hi) of g as a CSR of its own (rowptr slice; colidx/val shared, offsets stay absolute) -- probes."""
         v = DeviceCSR(hi - lo, g.n_cols, g.rowptr[lo:hi + 1], g.colidx, g.val, chunk=DEFAULT_CHUNK)
-        v.nnz = int(g.rowptr[hi]) - int(g.rowptr[lo])   # entries of the view (the arrays themselves are shared)
+        v.nnz = int(g.rowptr[hi]) - int(g.rowptr[lo])
         v._struct = None
         return v
 
-    def spmm(self, g, X, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
-        g.spmm(X, Y=Y, resid=resid, acc_in=acc_in, acc_out=acc_out, acc_div=acc_div, want_y=Y is not None)
-
-    def spmm_split(self, g, X, split_row, y_tail, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
-        """One launch over ALL local rows: rows < split_row get the fused epilogue, rows >= split_row (the partial item
-        rows) are stored raw to y_tail."""
-        g.spmm(X, Y=Y, resid=resid, acc_in=acc_in, acc_out=acc_out, acc_div=acc_div, want_y=Y is not None,
-               split_row=split_row, y_tail=y_tail)
+    def mean_rows(self, srcs, div, out):
+        arr = (C.c_void_p * len(srcs))(*[t.data_ptr() for t in srcs])
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_mean_rows(arr, len(srcs), out.numel(), float(div), ptr(out), stream()), "mean_rows")
+        _lib.count_launch()
 
     def accumulate(self, y, acc, resid, div, out):
         with torch.cuda.device(self.device):
@@ -107,34 +176,40 @@ class CudaOps:
         with torch.cuda.device(self.device):
             check(_lib.load().lgb_zero(ptr(t), t.numel() * t.element_size(), stream()), "zero")
 
-    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, user_lo=0, user_hi=0, loss=None, dEf=None, dE0_users=None,
-            dE0_items=None, gscale=1.0):
-        """BPR over triples (u, p, n).  Either the caller already compacted them to this rank's users (local user
-        ids, user_hi == 0), or it passes the GLOBAL batch with global user ids and the owned range
-        [user_lo, user_hi): the kernel then skips foreign triples (static shapes, no host sync).  B_norm = global B."""
-        d = Ef.shape[1]
-        off = Ug * d * 4
+    def gather_owned(self, src, idx, lo, hi, dst):
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_gather_rows_owned(ptr(src), ptr(idx), idx.numel(), src.shape[1], int(lo), int(hi), ptr(dst), stream()),
+                  "gather_rows_owned")
+        _lib.count_launch()
+
+    def scatter_add_owned(self, src, idx, lo, hi, dst):
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_scatter_add_rows_owned(ptr(src), ptr(idx), idx.numel(), src.shape[1], int(lo), int(hi), ptr(dst), stream()),
+                  "scatter_add_rows_owned")
+        _lib.count_launch()
+
+    def bpr(self, uf, u0, pf, p0, iu, ip, in_, lam, B_norm, gscale=1.0, user_lo=0, user_hi=0, user_rows_only=False,
+            loss=None, duf=None, du0=None, dpf=None, dp0=None):
+        """lgb_bpr on explicit operand tables: user operand (uf, u0) indexed by iu, positive AND negative operand (pf, p0) by
+        ip / in_; gradients accumulate into duf / du0 (user side) and dpf / dp0 (both item sides)."""
+        d = pf.shape[1]
         a = LgbBprArgs()
-        a.uf, a.pf, a.nf = Ef.data_ptr(), Ef.data_ptr() + off, Ef.data_ptr() + off
-        a.u0, a.p0, a.n0 = E0.data_ptr(), E0.data_ptr() + off, E0.data_ptr() + off
-        a.iu, a.ip, a.in_ = ptr(u), ptr(p), ptr(n)
-        a.B, a.B_norm, a.d, a.lambda_, a.gscale = u.numel(), int(B_norm), d, float(lam), float(gscale)
-        a.user_lo, a.user_hi = int(user_lo), int(user_hi)
-        if dEf is not None:
-            a.duf, a.dpf, a.dnf = dEf.data_ptr(), dEf.data_ptr() + off, dEf.data_ptr() + off
-        if dE0_users is not None:
-            a.du0 = dE0_users.data_ptr()
-        if dE0_items is not None:
-            a.dp0 = a.dn0 = dE0_items.data_ptr()
+        a.uf, a.u0, a.pf, a.p0, a.nf, a.n0 = ptr(uf), ptr(u0), ptr(pf), ptr(p0), ptr(pf), ptr(p0)
+        a.iu, a.ip, a.in_ = ptr(iu), ptr(ip), ptr(in_)
+        a.B, a.B_norm, a.d, a.lambda_, a.gscale = iu.numel(), int(B_norm), d, float(lam), float(gscale)
+        a.user_lo, a.user_hi, a.flags = int(user_lo), int(user_hi), 1 if user_rows_only else 0
+        a.duf, a.du0 = ptr(duf), ptr(du0)
+        a.dpf = a.dnf = ptr(dpf)
+        a.dp0 = a.dn0 = ptr(dp0)
         if loss is not None:
-            if self._bpr_ws is None or self._bpr_ws.numel() < 2 * int(_lib.load().lgb_bpr_blocks(max(u.numel(), 1))):
-                self._bpr_ws = _bpr_ws(max(u.numel(), 1), Ef.device)
+            if self._bpr_ws is None or self._bpr_ws.numel() < 2 * int(_lib.load().lgb_bpr_blocks(max(iu.numel(), 1))):
+                self._bpr_ws = _bpr_ws(max(iu.numel(), 1), pf.device)
             a.loss, a.ws = loss.data_ptr(), ptr(self._bpr_ws)
-        if u.numel() == 0 or (user_hi > 0 and user_hi <= user_lo):      # nothing to do on this rank
+        if iu.numel() == 0:
             if loss is not None:
                 self.zero(loss)
             return
-        _bpr_launch(a, Ef.device)
+        _bpr_launch(a, pf.device)
 
     def adam(self, p, g, m, v, lr, beta1, beta2, eps, step):
         with torch.cuda.device(self.device):
@@ -142,119 +217,156 @@ class CudaOps:
                   "adam_step")
         _lib.count_launch()
 
-    # collectives -------------------------------------------------------------------------------
-    def all_reduce_async(self, t: torch.Tensor):
-        """Sum-all-reduce of ``t`` on the comm stream, ordered after the work already queued on the
-        compute stream; returns a handle whose wait() makes the compute stream wait for the result."""
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+    # collectives ----------------------------------------------------------------------------------
+    def _multi(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def exchange_async(self, t: torch.Tensor, channel: int = 0):
+        """In-place sum over ranks of a buffer from ``alloc_exchange``, on the channel's high-priority side stream, ordered after
+        the work already queued on the current stream; returns a handle whose wait() makes the then-current stream wait."""
+        if not self._multi():
             return _Done()
         cur = torch.cuda.current_stream(self.device)
-        self.comm.wait_stream(cur)
-        with torch.cuda.stream(self.comm):
-            if self.exchange_events is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(self.comm)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-            if self.exchange_events is not None:
-                e1.record(self.comm)
-                self.exchange_events.append((e0, e1, t.numel() * t.element_size()))
-        return _StreamWait(self.comm, cur)
+        comm = self.comm[channel]
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            ev = self._ev_start(comm)
+            self._exchange(t, channel, comm)
+            self._ev_end(ev, comm, t)
+        return _StreamWait(comm, self.device)
+
+    all_reduce_async = exchange_async          # older name (dist_rows.py, tools)
+
+    def _exchange(self, t, channel, comm):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _ev_start(self, comm):
+        if self.exchange_events is None:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record(comm)
+        return e0
+
+    def _ev_end(self, e0, comm, t):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(comm)
+            self.exchange_events.append((e0, e1, t.numel() * t.element_size()))
 
     def all_reduce(self, t: torch.Tensor):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if self._multi():
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
 
 class SymmOps(CudaOps):
-    """Item-block exchange WITHOUT NCCL: the block is staged in CUDA symmetric memory and summed by
-    lgb_multimem_allreduce_f32 (NVSwitch multicast: multimem.ld_reduce + multimem.st, rank g owns slice g) or, when
-    the fabric has no multicast, lgb_peer_allreduce_f32 (P2P loads/stores over NVLink), bracketed by symmetric-memory
-    barriers.  Opt-in: ShardedLightGCN(..., exchange="symm").  Written in round 1 after the GPU budget was spent:
-    compiles (SASS shows LDGMC.E.ADD.F32x4), logic mirrors torch's two-shot multimem all-reduce, NOT yet run on B200."""
+    """Item-block exchange WITHOUT NCCL: the exchange buffers live in ONE arena of CUDA symmetric memory (every rank maps every
+    peer's copy and, with NVLS, one multicast address that fans out to all copies) and are summed in place by
+    ``lgb_exchange_allreduce_f32`` -- entry barrier, multimem.ld_reduce of the rank's slice (reduced inside the NVSwitch),
+    multimem.st back to all copies, exit barrier, all in one launch, no host synchronisation, CUDA-graph replayable.  Without
+    multicast the same kernel uses peer loads / stores over NVLink."""
+
+    kind = "symm"
 
     def __init__(self, device: torch.device, group=None):
         super().__init__(device, group)
         import torch.distributed._symmetric_memory as symm_mem
         self._symm = symm_mem
-        self._stage = {}
+        hi_pri = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
+        self.comm = [torch.cuda.Stream(device=device, priority=hi_pri) for _ in range(N_CHANNELS)]
+        self._arena = self._x = self._handle = None
+        self.multicast = False
 
-    def _staging(self, numel: int):
-        if numel not in self._stage:
-            t = self._symm.empty(numel, dtype=torch.float32, device=self.device)
-            h = self._symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
-            self._stage[numel] = (t, h)
-        return self._stage[numel]
-
-    def all_reduce_async(self, t: torch.Tensor):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
-            return _Done()
-        n = t.numel()
-        if n % 4 != 0 or not t.is_contiguous():
-            return super().all_reduce_async(t)
-        stage, h = self._staging(n)
+    def alloc_exchange(self, shapes):
+        if not self._multi():
+            return super().alloc_exchange(shapes)
+        if self._arena is not None:
+            raise RuntimeError("SymmOps.alloc_exchange: one arena per ops object (allocate every exchange buffer in one call)")
         lib = _lib.load()
-        cur = torch.cuda.current_stream(self.device)
-        self.comm.wait_stream(cur)
-        with torch.cuda.stream(self.comm):
-            stage.copy_(t.reshape(-1))
-            h.barrier(channel=0, timeout_ms=20000)                                   # every rank's partial sums are staged
-            off = int(getattr(h, "offset", 0))
-            mc = int(h.multicast_ptr) if h.multicast_ptr else 0
-            with torch.cuda.device(self.device):
-                if mc:
-                    check(lib.lgb_multimem_allreduce_f32(mc + off, n, h.rank, h.world_size, self.comm.cuda_stream),
-                          "multimem_allreduce")
-                else:
-                    import ctypes as C
-                    arr = (C.c_uint64 * h.world_size)(*[int(p) + off for p in h.buffer_ptrs])
-                    check(lib.lgb_peer_allreduce_f32(arr, n, h.rank, h.world_size, self.comm.cuda_stream), "peer_allreduce")
-            _lib.count_launch()
-            h.barrier(channel=1, timeout_ms=20000)                                   # every slice is republished on every rank
-            t.reshape(-1).copy_(stage)
-        return _StreamWait(self.comm, cur)
+        grp = self.group if self.group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 63) // 64 * 64                       # 256-byte aligned sub-buffers
+        pad_words = N_CHANNELS * int(lib.lgb_exchange_pad_words(world))
+        pad_off = total
+        total += (pad_words + 63) // 64 * 64
+        arena = self._symm.empty(total, dtype=torch.float32, device=self.device)
+        arena.zero_()                                          # data AND signal slots start at 0
+        torch.cuda.synchronize(self.device)
+        h = self._symm.rendezvous(arena, grp)
+        base_off = int(getattr(h, "offset", 0) or 0)
+        x = LgbExchange()
+        mc = int(h.multicast_ptr) if getattr(h, "multicast_ptr", 0) else 0
+        x.multicast_base = (mc + base_off) if mc else None
+        for r in range(world):
+            x.peer_base[r] = int(h.buffer_ptrs[r]) + base_off
+            x.pad_base[r] = int(h.buffer_ptrs[r]) + base_off + pad_off * 4
+        x.rank, x.world, x.n_channels = rank, world, N_CHANNELS
+        self._arena, self._x, self._handle, self.multicast = arena, x, h, bool(mc)
+        dist.barrier(group=grp)                                # every rank has zeroed its arena before anybody signals
+        return [arena[o:o + n].view(*s) for o, n, s in zip(offs, sizes, shapes)]
+
+    def _exchange(self, t, channel, comm):
+        off = t.data_ptr() - self._arena.data_ptr() if self._arena is not None else -1
+        if off < 0 or off + t.numel() * 4 > self._arena.numel() * 4 or t.numel() % 4 != 0 or not t.is_contiguous():
+            raise RuntimeError("SymmOps: the exchanged tensor must be a contiguous buffer from alloc_exchange with numel % 4 == 0")
+        with torch.cuda.device(self.device):
+            check(_lib.load().lgb_exchange_allreduce_f32(C.byref(self._x), off, t.numel(), channel, 0, comm.cuda_stream),
+                  "exchange_allreduce")
+        _lib.count_launch()
 
 
-class _Done:
-    def wait(self):
-        pass
-
-
-class _StreamWait:
-    def __init__(self, comm, cur):
-        self.comm, self.cur = comm, cur
-
-    def wait(self):
-        self.cur.wait_stream(self.comm)
+def make_ops(device, group=None, exchange: str = "auto"):
+    """'symm' (own kernel over symmetric memory), 'nccl', or 'auto' = symm when every rank can set it up, else nccl."""
+    if exchange == "nccl":
+        return CudaOps(device, group)
+    if exchange == "symm":
+        return SymmOps(device, group)
+    ok = 1.0
+    try:
+        ops = SymmOps(device, group)
+    except Exception:
+        ops, ok = None, 0.0
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor([ok], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        ok = float(t)
+    return ops if ok > 0.5 else CudaOps(device, group)
 
 
 # --------------------------------------------------------------------------------------------
 # the sharded engine
 # --------------------------------------------------------------------------------------------
 class ShardedLightGCN:
-    """LightGCN fwd + BPR + bwd over a user-sharded graph.  Every rank passes the same (users, items) COO
-    (or any superset of its own users' edges plus all item-degree information via ``item_degree``)."""
+    """LightGCN fwd + BPR + bwd over a user-sharded graph.  Every rank passes the same (users, items) COO.
+
+    After ``fused_step``: ``E_f_users`` / ``E_f_items`` (final embeddings: owned user rows, replicated item rows),
+    ``grad_users`` / ``grad_items`` (dLoss/dE0; the item rows are bit-identical on every rank; ``grad_items`` lives in an
+    exchange buffer that the NEXT step's forward overwrites -- consume it, e.g. with ``adam_step``, before that)."""
 
     def __init__(self, num_users: int, num_items: int, embedding_dim: int, num_iterations: int,
                  users: torch.Tensor, items: torch.Tensor, device, group=None, ops=None,
                  rank: Optional[int] = None, world: Optional[int] = None, init_tables=None,
-                 schedule: str = "layer", static_batch: bool = False, exchange: str = "nccl"):
+                 schedule: str = "chains", exchange: str = "auto", max_batch: int = 4096):
         self.U, self.I, self.d, self.K = int(num_users), int(num_items), int(embedding_dim), int(num_iterations)
         self.device = torch.device(device)
-        if schedule not in ("layer", "pipelined", "merged"):
-            raise ValueError(f"schedule={schedule!r}")
-        self.schedule, self.static_batch = schedule, bool(static_batch)
+        if schedule not in ("chains", "layer"):
+            raise ValueError(f"schedule={schedule!r} (chains: the two layer chains on two streams; layer: one stream)")
+        if exchange not in ("auto", "nccl", "symm"):
+            raise ValueError(f"exchange={exchange!r}")
+        self.schedule = schedule
         inited = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank(group) if inited else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if inited else 1)
-        if exchange not in ("nccl", "symm"):
-            raise ValueError(f"exchange={exchange!r}")
-        self.ops = ops if ops is not None else (SymmOps if exchange == "symm" else CudaOps)(self.device, group)
+        self.ops = ops if ops is not None else make_ops(self.device, group, exchange)
         users, items = users.to(self.device), items.to(self.device)
 
         udeg = torch.bincount(users, minlength=self.U)
         self.bounds = balanced_user_bounds(udeg, self.world)
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
-        self.Ug = self.hi - self.lo
+        self.Ug = Ug = self.hi - self.lo
         row, col, lu, li = local_block(users, items, self.lo, self.hi)
         self.local_edges = int(lu.numel())
         # global degrees: users are wholly local; item degrees are summed over ranks
@@ -262,47 +374,64 @@ class ShardedLightGCN:
         self.ops.all_reduce(ideg)
         deg = torch.cat([udeg[self.lo:self.hi].to(torch.float32), ideg])
         dinv = torch.where(deg > 0, 1.0 / torch.sqrt(deg), torch.zeros_like(deg))
-        n = self.Ug + self.I
-        self.n = n
-        g = self.ops.build_graph(row, col, n, dinv)
-        self.g_users = self.ops.row_view(g, 0, self.Ug)
-        self.g_items = self.ops.row_view(g, self.Ug, n)
-        self.g_full = g
-        self.g_all = self.ops.row_view(g, 0, n) if schedule == "merged" else None   # all rows + split plan
+        self.n = n = Ug + self.I
+        self.g_users, self.g_items = self.ops.build_views(row, col, Ug, self.I, dinv)
+        del row, col, lu, li
 
-        # parameters: one local table; the item block is identical on every rank
+        # parameters: one local table (users then items); the item block is identical on every rank
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.table = torch.empty(n, self.d, **f32)
+        I, d, K = self.I, self.d, self.K
+        self.table = torch.empty(n, d, **f32)
         if init_tables is not None:
             Wu, Wi = init_tables
-            self.table[: self.Ug].copy_(Wu[self.lo:self.hi])
-            self.table[self.Ug:].copy_(Wi)
+            self.table[:Ug].copy_(Wu[self.lo:self.hi])
+            self.table[Ug:].copy_(Wi)
         else:
             gen = torch.Generator(device=self.device).manual_seed(1000 + self.rank)
-            self.table[: self.Ug].normal_(0, 0.1, generator=gen)
+            self.table[:Ug].normal_(0, 0.1, generator=gen)
             gen_i = torch.Generator(device=self.device).manual_seed(999)
-            self.table[self.Ug:].normal_(0, 0.1, generator=gen_i)
-        self.grad = torch.empty(n, self.d, **f32)
-        self.E_f = torch.empty(n, self.d, **f32)
-        self._ya = torch.empty(n, self.d, **f32)
-        self._yb = torch.empty(n, self.d, **f32)
-        self._r = torch.empty(n + 1, self.d, **f32)   # + one row that carries the scalar loss through the all-reduce
+            self.table[Ug:].normal_(0, 0.1, generator=gen_i)
+        self.max_batch = int(max_batch)
+        # layer outputs: user rows in plain HBM, item rows in exchange buffers (+ the 2*B*d batch-row buffer of the BPR section)
+        self._yu = [torch.empty(Ug, d, **f32) for _ in range(K)]
+        bufs = self.ops.alloc_exchange([(I, d)] * max(K, 1) + [(2, self.max_batch, d)])
+        self._yi, self._stage_full = bufs[:-1], bufs[-1]
+        self.E_f_users, self.E_f_items = torch.empty(Ug, d, **f32), torch.empty(I, d, **f32)
+        self.grad_users = torch.empty(Ug, d, **f32)
+        self.grad_items = self._yi[K - 1] if K > 0 else torch.empty(I, d, **f32)
+        self._ru, self._ri = torch.empty(Ug, d, **f32), torch.empty(I, d, **f32)
+        self._dstage = torch.empty(self.max_batch, d, **f32)
+        self._iota = torch.arange(self.max_batch, dtype=torch.int64, device=self.device)
         self._loss = torch.zeros((), **f32)
         self.loss = self._loss
+
+    # ---- views kept for callers of the round-1 layout (tests, tools): concatenations, NOT the live buffers --------------
+    @property
+    def E_f(self):
+        return torch.cat([self.E_f_users, self.E_f_items])
+
+    @property
+    def grad(self):
+        return torch.cat([self.grad_users, self.grad_items])
+
+    @property
+    def users_weight(self):
+        return self.table[: self.Ug]
+
+    @property
+    def items_weight(self):
+        return self.table[self.Ug:]
 
     def graphs(self):
         return [self.g_users, self.g_items]
 
     def autotune(self):
-        """Per-rank plan-time choice of the SpMM kernel variant for each row view (DeviceCSR.autotune); ranks may choose
-        differently -- the item rows are all-reduced, so the replicated blocks stay identical."""
+        """Per-rank plan-time choice of the SpMM kernel variant / slice size for each view (DeviceCSR.autotune); ranks may
+        choose differently -- the item rows are summed by the exchange, so the replicated blocks stay identical."""
         chunks = (DEFAULT_CHUNK, 256)      # a rank's launch is bounded below by one slice's serial chain: try shorter slices
-        views = {"users": (self.g_users, True), "items": (self.g_items, False)}
-        if self.g_all is not None:
-            views["all"] = (self.g_all, True)
         out = {}
-        for name, (g, fused) in views.items():
-            g.autotune(self.d, fused_epilogue=fused, chunks=chunks)
+        for name, g in (("users", self.g_users), ("items", self.g_items)):
+            g.autotune(self.d, fused_epilogue=False, chunks=chunks)
             out[name] = dict(g.autotune_report.get("chosen", {"variant": g.variant}), ms=g.autotune_report["ms"],
                              rejected=g.autotune_report["rejected"])
         return out
@@ -310,23 +439,22 @@ class ShardedLightGCN:
     # ---- optimizer step on the local shard (run_pipeline_lightgcn.py:103,159 -- optim.Adam over both tables) ------------
     def adam_step(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8) -> None:
         """One fused Adam step (lgb_adam_step, same arithmetic as torch.optim.Adam) on the local table with the gradients the
-        last ``fused_step`` left in ``self.grad``: the owned user rows are updated by their owner only; the item rows carry
-        identical gradients on every rank (they were all-reduced), so the replicated item block stays bit-identical without
-        a broadcast.  State (exp_avg, exp_avg_sq, step) lives on the engine."""
+        last ``fused_step`` left behind: the owned user rows are updated by their owner only; the item rows carry identical
+        gradients on every rank, so the replicated item block stays bit-identical without a broadcast."""
         if not hasattr(self, "_adam"):
             self._adam = dict(step=0, m=torch.zeros_like(self.table), v=torch.zeros_like(self.table))
-        st = self._adam
+        st, Ug = self._adam, self.Ug
         st["step"] += 1
-        self.ops.adam(self.table, self.grad, st["m"], st["v"], float(lr), float(betas[0]), float(betas[1]), float(eps), st["step"])
+        hp = (float(lr), float(betas[0]), float(betas[1]), float(eps), st["step"])
+        if Ug:
+            self.ops.adam(self.table[:Ug], self.grad_users, st["m"][:Ug], st["v"][:Ug], *hp)
+        self.ops.adam(self.table[Ug:], self.grad_items, st["m"][Ug:], st["v"][Ug:], *hp)
 
     def autotune_step(self, user_indices, pos_item_indices, neg_item_indices, lambda_val: float, reps: int = 5,
-                      candidates=((None, False), (None, True)), timer=None) -> dict:
-        """Plan-time choice of the step form on THIS machine: every candidate (schedule, static_batch) -- by default the
-        measured host-filtered step and the static-shape step (kernel-side owned-user filter, loss riding on the gradient
-        all-reduce, that all-reduce hidden behind the first backward SpMM) under the current schedule -- must reproduce the
-        first candidate's loss and gradients on the given batch on EVERY rank, and is then timed (barrier, CUDA events, max
-        over ranks); the fastest is kept.  Every rank runs the same candidates in the same order, so the collective sequence
-        stays matched.  Returns a report."""
+                      candidates=("chains", "layer"), timer=None) -> dict:
+        """Plan-time choice of the schedule on THIS machine: every candidate must reproduce the first candidate's loss and
+        gradients on the given batch on EVERY rank (agreement by a MIN all-reduce) and is then timed (barrier, CUDA events,
+        max over ranks); the fastest is kept.  Every rank runs the same candidates in the same order."""
         inited = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.ops.group) > 1
 
         def agree(value: float, op) -> float:
@@ -347,246 +475,113 @@ class ShardedLightGCN:
             e1.synchronize()
             return e0.elapsed_time(e1) / reps
         timer = timer or default_timer
-        keep = (self.schedule, self.static_batch)
+        keep = self.schedule
         report, ref, best, best_ms = {"ms": {}, "rejected": {}}, None, keep, float("inf")
-        for schedule, static in candidates:
-            schedule = schedule or keep[0]
-            if schedule == "merged" and self.g_all is None:      # the all-rows view (+ its plan and kernel choice) is built on demand
-                self.g_all = self.ops.row_view(self.g_full, 0, self.n)
-                if self.g_users.variant is not None:
-                    self.g_all.autotune(self.d, chunks=(DEFAULT_CHUNK, 256))
-            key = f"{schedule}/{'static' if static else 'host-filtered'}"
-            self.schedule, self.static_batch = schedule, bool(static)
+        for schedule in candidates:
+            self.schedule = schedule
             loss = self.fused_step(user_indices, pos_item_indices, neg_item_indices, lambda_val).clone()
-            grad = self.grad.clone()
+            grad = self.grad
             if ref is None:
                 ref = (loss, grad)
             else:
                 same = bool(torch.allclose(loss, ref[0], rtol=1e-5, atol=1e-7)) and \
                     bool(torch.allclose(grad, ref[1], rtol=1e-4, atol=1e-6 * float(ref[1].abs().max()) + 1e-12))
                 if agree(1.0 if same else 0.0, dist.ReduceOp.MIN) < 0.5:
-                    report["rejected"][key] = "loss / gradients differ from the first candidate on at least one rank"
+                    report["rejected"][schedule] = "loss / gradients differ from the first candidate on at least one rank"
                     continue
             ms = agree(timer(lambda: self.fused_step(user_indices, pos_item_indices, neg_item_indices, lambda_val)), dist.ReduceOp.MAX)
-            report["ms"][key] = ms
+            report["ms"][schedule] = ms
             if ms < best_ms:
-                best, best_ms = (schedule, bool(static)), ms
-        self.schedule, self.static_batch = best
-        report["chosen"] = {"schedule": best[0], "static_batch": best[1]}
+                best, best_ms = schedule, ms
+        self.schedule = best
+        report["chosen"] = {"schedule": best}
         return report
 
-    @property
-    def users_weight(self):
-        return self.table[: self.Ug]
-
-    @property
-    def items_weight(self):
-        return self.table[self.Ug:]
-
-    # ---- schedule "layer" (default; measured on 2/4/8 B200): one all-reduce per layer, overlapped with the users SpMM ----
-    def _layer(self, X, Y, resid=None, acc_in=None, acc_out=None, acc_div=1.0, write_y=True):
-        """Y[:Ug] = G_users X (+resid) ; Y[Ug:] = allreduce(G_items X) (+resid);
-        acc_out (optional) = (acc_in + that) / acc_div on both row blocks."""
-        Ug, ops = self.Ug, self.ops
-        yi = Y[Ug:]
-        ops.spmm(self.g_items, X, Y=yi)                                     # partial item rows
-        h = ops.all_reduce_async(yi)                                          # ... summed over ranks (comm stream)
-        ops.spmm(self.g_users, X, Y=Y[:Ug] if write_y else None,              # overlaps with the all-reduce
-                 resid=None if resid is None else resid[:Ug],
-                 acc_in=None if acc_in is None else acc_in[:Ug],
-                 acc_out=None if acc_out is None else acc_out[:Ug], acc_div=acc_div)
-        self._finish_items(h, Y, resid, acc_in, acc_out, acc_div)
-
-    def _finish_items(self, h, y, resid, acc_in, acc_out, div):
-        """Wait for the all-reduce of y's item rows, then apply the epilogue the SpMM could not fuse for them."""
-        Ug, ops = self.Ug, self.ops
-        h.wait()
-        yi = y[Ug:]
-        if acc_out is not None:
-            ops.accumulate(yi, None if acc_in is None else acc_in[Ug:], None if resid is None else resid[Ug:], div, acc_out[Ug:])
-        elif resid is not None:
-            ops.accumulate(yi, None, resid[Ug:], 1.0, yi)
-
-    # ---- schedule "pipelined" (opt-in): the all-reduce hidden behind TWO SpMM launches -----------------------------
-    # Bipartite dependencies:  users^{k+1} <- items^k (needs the all-reduced item rows)
-    #                          items^{k+1} <- users^k (local rows only)
-    # so all-reduce(items^{k+1}) is only needed by users^{k+2}: it can overlap with users^{k+1} AND items^{k+2}.
-    # Validated against the oracle over gloo (tests/test_dist_gloo.py); B200 measurement pending.
-    def _propagate_pipelined(self, x0, K, resid=None, acc0=None, acc=None, acc_div_last=1.0, out_last=None,
-                             before_last_reduce=None, x0_items_pending=None):
-        Ug, ops = self.Ug, self.ops
-        bufs = [self._ya, self._yb]
-        x, pending = x0, None            # pending = epilogue of the layer whose item rows are still being reduced
+    # ---- K propagation layers as two independent chains ---------------------------------------------------------------
+    def _propagate(self, xu, xi, resid_u=None, resid_i=None, last_u=None):
+        """(xu, xi) -> K layers of  yu = G_users xi (+resid_u),  yi = exchange(G_items xu (+resid_i on rank 0)).
+        Returns ([yu_0..yu_{K-1}], [yi_0..yi_{K-1}]); on return everything is ordered on the current stream.
+        last_u: buffer that receives yu_{K-1} instead of the internal one."""
+        K, ops = self.K, self.ops
+        two = self.schedule == "chains"
+        ctx = ops.fork(two)
+        yus, yis, pending = [], [], None
+        ri = resid_i if self.rank == 0 else None          # delivered exactly once through the sum over ranks
         for k in range(K):
-            last = k == K - 1
-            y = out_last if (last and out_last is not None) else bufs[k % 2]
-            ops.spmm(self.g_items, x, Y=y[Ug:])                               # items^{k+1} partial (reads user rows of x)
-            if k == 0 and x0_items_pending is not None:                        # x0's item rows were still being all-reduced
-                x0_items_pending.wait()
-            if last and before_last_reduce is not None:
-                before_last_reduce(y[Ug:])
-            if pending is not None:                                            # x's item rows must be complete now
-                self._finish_items(*pending)
-            h = ops.all_reduce_async(y[Ug:])
-            div = acc_div_last if last else 1.0
-            a_in = None if acc is None else (acc0 if k == 0 else acc)
-            ops.spmm(self.g_users, x, Y=None if (last and acc is not None) else y[:Ug],
-                     resid=None if resid is None else resid[:Ug],
-                     acc_in=None if a_in is None else a_in[:Ug],
-                     acc_out=None if acc is None else acc[:Ug], acc_div=div)
-            pending = (h, y, resid, a_in, acc, div)
-            x = y
+            ci, cu = (1, 0) if k % 2 == 0 else (0, 1)      # chain of I(k) / of U(k)
+            yi = self._yi[k]
+            yu = last_u if (k == K - 1 and last_u is not None) else self._yu[k]
+            with ctx[ci]:
+                ops.spmm(self.g_items, xu, yi, resid=ri)                       # partial item rows <- owned users
+                h = ops.exchange_async(yi, channel=ci)                           # ... summed over ranks
+            with ctx[cu]:
+                if pending is not None:
+                    pending.wait()                                               # xi = yi_{k-1} must be complete (same chain)
+                ops.spmm(self.g_users, xi, yu, resid=resid_u)                   # owned user rows <- all items
+            yus.append(yu); yis.append(yi)
+            xu, xi, pending = yu, yi, h
+        ops.join(two)
         if pending is not None:
-            self._finish_items(*pending)
-        return x
+            pending.wait()
+        return yus, yis
 
-    # ---- schedule "merged" (opt-in): ONE launch per layer over all local rows (split epilogue), exchange exposed ------
-    # Halves the launch count and doubles the work per launch (at 1/8 of the graph a launch is bound by per-row latency
-    # chains, not bytes); pays with a fully exposed exchange, so it is meant for the fast multimem exchange.
-    # Validated over gloo; B200 measurement pending.
-    def _layer_merged(self, X, Y, resid=None, acc_in=None, acc_out=None, acc_div=1.0, write_y=True, before_reduce=None):
-        Ug, ops = self.Ug, self.ops
-        ops.spmm_split(self.g_all, X, Ug, Y[Ug:], Y=Y if write_y else None, resid=resid, acc_in=acc_in, acc_out=acc_out,
-                       acc_div=acc_div)
-        if before_reduce is not None:
-            before_reduce(Y[Ug:])
-        self._finish_items(ops.all_reduce_async(Y[Ug:]), Y, resid, acc_in, acc_out, acc_div)
-
-    def forward(self) -> torch.Tensor:
-        """E_f = mean_k A^k E0 on the local rows (item rows replicated)."""
-        K, E0, Ef = self.K, self.table, self.E_f
+    def forward(self):
+        """E_f = mean_k A^k E0 on the local rows (item rows replicated) -> (E_f_users, E_f_items)."""
+        K, Ug, ops = self.K, self.Ug, self.ops
+        Wu, Wi = self.table[:Ug], self.table[Ug:]
         if K == 0:
-            Ef.copy_(E0)
-            return Ef
-        if self.schedule == "merged":
-            x, y = E0, self._ya
-            for k in range(K):
-                last = k == K - 1
-                self._layer_merged(x, y, acc_in=E0 if k == 0 else Ef, acc_out=Ef, acc_div=float(K + 1) if last else 1.0,
-                                   write_y=not last)
-                x, y = y, (self._yb if y is self._ya else self._ya)
-            return Ef
-        if self.schedule == "pipelined":
-            self._propagate_pipelined(E0, K, acc0=E0, acc=Ef, acc_div_last=float(K + 1))
-            return Ef
-        x, y = E0, self._ya
-        for k in range(K):
-            last = k == K - 1
-            self._layer(x, y, acc_in=E0 if k == 0 else Ef, acc_out=Ef, acc_div=float(K + 1) if last else 1.0,
-                        write_y=not last)
-            x, y = y, (self._yb if y is self._ya else self._ya)
-        return Ef
+            self.E_f_users.copy_(Wu); self.E_f_items.copy_(Wi)
+            return self.E_f_users, self.E_f_items
+        yus, yis = self._propagate(Wu, Wi)
+        if Ug:
+            ops.mean_rows([Wu] + yus, float(K + 1), self.E_f_users)
+        ops.mean_rows([Wi] + yis, float(K + 1), self.E_f_items)
+        return self.E_f_users, self.E_f_items
 
-    def backward(self, r: torch.Tensor, before_last_reduce=None, r_items_pending=None) -> torch.Tensor:
-        """grad = sum_k (A^T)^k r with r = dE_f/(K+1).  The local block is symmetric, so A^T is the same pair of row views.
-        r's item rows must be the sum over ranks: either already (r_items_pending None) or once r_items_pending.wait()
-        returns -- the first layer's items SpMM only reads r's USER rows, so that all-reduce is hidden behind it."""
-        K = self.K
-        if K == 0 or self.schedule == "merged":
-            if r_items_pending is not None:          # nothing to hide it behind
-                r_items_pending.wait()
-                r_items_pending = None
-        if K == 0:
-            self.grad.copy_(r)
-            return self.grad
-        if self.schedule == "pipelined":
-            return self._propagate_pipelined(r, K, resid=r, out_last=self.grad, before_last_reduce=before_last_reduce,
-                                             x0_items_pending=r_items_pending)
-        g = r
-        bufs = [self._ya, self._yb]
-        for k in range(K):
-            last = k == K - 1
-            dst = self.grad if last else bufs[k % 2]
-            if self.schedule == "merged":
-                self._layer_merged(g, dst, resid=r, before_reduce=before_last_reduce if last else None)
-                g = dst
-                continue
-            if (last and before_last_reduce is not None) or (k == 0 and r_items_pending is not None):
-                Ug, ops = self.Ug, self.ops
-                ops.spmm(self.g_items, g, Y=dst[Ug:])                     # reads user rows of g only
-                if k == 0 and r_items_pending is not None:
-                    r_items_pending.wait()                                # from here on r's item rows are needed
-                if last and before_last_reduce is not None:
-                    before_last_reduce(dst[Ug:])                          # fold extra partial item-row terms into this all-reduce
-                h = ops.all_reduce_async(dst[Ug:])
-                ops.spmm(self.g_users, g, Y=dst[:Ug], resid=r[:Ug])
-                self._finish_items(h, dst, r, None, None, 1.0)
-            else:
-                self._layer(g, dst, resid=r)
-            g = dst
-        return self.grad
+    def backward(self, ru: torch.Tensor, ri: torch.Tensor):
+        """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (Horner: g <- A g + r; the local block is symmetric).  ri must be the
+        complete item-row residual (identical on every rank)."""
+        if self.K == 0:
+            self.grad_users.copy_(ru); self.grad_items.copy_(ri)
+            return self.grad_users, self.grad_items
+        self._propagate(ru, ri, resid_u=ru, resid_i=ri, last_u=self.grad_users)
+        return self.grad_users, self.grad_items
 
     @torch.no_grad()
     def fused_step(self, user_indices: torch.Tensor, pos_item_indices: torch.Tensor, neg_item_indices: torch.Tensor,
                    lambda_val: float) -> torch.Tensor:
-        """Global batch in (the same B triples on every rank), global loss out (0-dim tensor, identical on every
-        rank); gradients in ``self.grad`` (rows [:Ug] owned users, rows [Ug:] replicated items, identical on every
-        rank)."""
-        if self.static_batch:
-            return self._fused_step_static(user_indices, pos_item_indices, neg_item_indices, lambda_val)
-        ops, Ug, K = self.ops, self.Ug, self.K
-        u, p, n = (t.to(self.device) for t in (user_indices, pos_item_indices, neg_item_indices))
+        """Global batch in (the same B triples on every rank), global loss out (0-dim tensor, bit-identical on every rank);
+        gradients in ``grad_users`` (owned rows) / ``grad_items`` (replicated rows, identical on every rank).  Static
+        shapes, no host synchronisation: CUDA-graph capturable (``capture``)."""
+        ops, Ug, K, d = self.ops, self.Ug, self.K, self.d
+        u, p, n = (_lib.i64c(t.to(self.device)) for t in (user_indices, pos_item_indices, neg_item_indices))
         B = u.numel()
-        mine = (u >= self.lo) & (u < self.hi)                               # triples of the users this rank owns
-        lu, lp, ln = (u[mine] - self.lo).contiguous(), p[mine].contiguous(), n[mine].contiguous()
-        Ef = self.forward()
-        r = self._r[: self.n]
-        ops.zero(r)
-        loss = self._loss
-        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, loss=loss, dEf=r, gscale=1.0 / (K + 1))
-        # item-row gradient contributions of the local triples are partial sums: reduce them (and the loss)
-        h = ops.all_reduce_async(r[Ug:])
-        ops.all_reduce(loss)
+        if B > self.max_batch:
+            raise RuntimeError(f"batch of {B} triples > max_batch={self.max_batch} (the symmetric batch-row buffer is sized at construction)")
+        Wu, Wi = self.table[:Ug], self.table[Ug:]
+        Efu, Efi = self.forward()
+        # the batch's user rows, gathered by their owners: stage[0] = E_f rows, stage[1] = layer-0 rows
+        stage = self._stage_full.view(-1)[: 2 * B * d].view(2, B, d)
+        ops.gather_owned(Efu, u, self.lo, self.hi, stage[0])
+        ops.gather_owned(Wu, u, self.lo, self.hi, stage[1])
+        h = ops.exchange_async(stage, channel=2)
+        ru, ri, dst = self._ru, self._ri, self._dstage[:B]
+        ops.zero(ru); ops.zero(ri); ops.zero(dst)
         h.wait()
-        G = self.backward(r)
-        # + 2*lambda*E0 on the batch rows: users locally; items are partial over ranks -> reduce a small buffer
-        reg_items = self._ya[Ug:]
-        ops.zero(reg_items)
-        ops.bpr(Ef, self.table, Ug, lu, lp, ln, lambda_val, B, dE0_users=G, dE0_items=reg_items)
-        ops.all_reduce_async(reg_items).wait()
-        ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
+        # every rank evaluates ALL triples: loss and item-row gradients complete and identical everywhere
+        loss = self._loss
+        ops.bpr(stage[0], stage[1], Efi, Wi, self._iota[:B], p, n, lambda_val, B, gscale=1.0 / (K + 1), loss=loss, duf=dst, dpf=ri)
+        ops.scatter_add_owned(dst, u, self.lo, self.hi, ru)
+        Gu, Gi = self.backward(ru, ri)
+        # + 2*lambda*E0 on the batch rows: owned users locally, item rows redundantly (identical) on every rank
+        ops.bpr(Efu, Wu, Efi, Wi, u, p, n, lambda_val, B, user_lo=self.lo, user_hi=self.hi, user_rows_only=True, du0=Gu, dp0=Gi)
         self.loss = loss
         return loss
 
-    @torch.no_grad()
-    def _fused_step_static(self, user_indices, pos_item_indices, neg_item_indices, lambda_val: float) -> torch.Tensor:
-        """Same step with static shapes and no host synchronisation (CUDA-graph capturable): the kernel filters the
-        global batch by the owned user range, the loss rides in an extra row of the residual buffer (one all-reduce
-        for item-row gradients + loss) and the item regulariser terms ride on the last backward all-reduce.
-        Validated over gloo (tests/test_dist_gloo.py); B200 measurement pending."""
-        ops, Ug, K = self.ops, self.Ug, self.K
-        u, p, n = (_lib.i64c(t.to(self.device)) for t in (user_indices, pos_item_indices, neg_item_indices))
-        B = u.numel()
-        Ef = self.forward()
-        r = self._r                                   # [n + 1, d]: the extra row carries the loss through the all-reduce
-        ops.zero(r)
-        loss_slot = r[self.n, :1].view(())
-        flt = dict(user_lo=self.lo, user_hi=self.hi)
-        ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, loss=loss_slot, dEf=r, gscale=1.0 / (K + 1), **flt)
-        h_r = ops.all_reduce_async(r[Ug:])            # item-row gradients + loss: ONE all-reduce, hidden behind the first
-        rr = r[: self.n]                              # backward layer's items SpMM (which only reads r's user rows)
-
-        def add_item_reg(items_partial):              # 2*lambda*E0[p], E0[n] of the local triples
-            ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, dE0_items=items_partial, **flt)
-        if K == 0:
-            G = self.backward(rr, r_items_pending=h_r)
-            reg_items = self._ya[Ug:]
-            ops.zero(reg_items)
-            add_item_reg(reg_items)
-            ops.all_reduce_async(reg_items).wait()
-            ops.accumulate(reg_items, G[Ug:], None, 1.0, G[Ug:])
-        else:
-            G = self.backward(rr, before_last_reduce=add_item_reg, r_items_pending=h_r)
-        ops.bpr(Ef, self.table, Ug, u, p, n, lambda_val, B, dE0_users=G, **flt)   # owned users: local
-        self.loss = loss_slot
-        return loss_slot
-
-    # ---- CUDA-graph replay of the whole step (opt-in; the 8-GPU step is ~40 launches of 0.1-0.2 ms each) -------------
+    # ---- CUDA-graph replay of the whole step (kernels on three streams + the exchange kernels) --------------------------
     def capture(self, batch_size: int, lambda_val: float):
-        """Capture the static-shape step for a fixed batch size; returns step(u, p, n) -> loss that replays the graph.
-        Opt-in and not yet measured on B200 (bench.py --graph)."""
+        """Capture the step for a fixed batch size; returns step(u, p, n) -> loss that replays the graph."""
         dev = self.device
-        self.static_batch = True
         su, sp, sn = (torch.zeros(batch_size, dtype=torch.int64, device=dev) for _ in range(3))
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -53,10 +53,12 @@ class SparseTensor:
 
     def to(self, device, *args, **kwargs) -> "SparseTensor":
         device = torch.device(device)
-        if device == self.device:
-            return self
-        if self._csr is not None and device.type != "cuda":
-            raise RuntimeError("moving a built SparseTensor back to the CPU is not supported")
+        here = self.device
+        if device.type == here.type and (device.index is None or device.index == here.index):
+            return self            # 'cuda' names the device the tensor already lives on: keep the cached CSR / gcn_norm
+        if self._csr is not None:
+            raise RuntimeError("moving a built SparseTensor to another device is not supported (its COO copy was freed "
+                               "when the CSR was built): construct it again from row/col")
         out = SparseTensor(row=self._row.to(device), col=self._col.to(device),
                            value=None if self._value is None else self._value.to(device), sparse_sizes=self._sizes)
         out.chunk = self.chunk

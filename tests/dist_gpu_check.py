@@ -16,16 +16,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    # DIST_CHECK_MODE = "schedule,static,exchange", e.g. "pipelined,1,symm"; default = the measured configuration
-    mode = os.environ.get("DIST_CHECK_MODE", "layer,0,nccl").split(",")
+    # DIST_CHECK_MODE = "schedule,exchange[,graph]", e.g. "chains,symm,graph"; default = what bench.py ships
+    mode = os.environ.get("DIST_CHECK_MODE", "chains,auto").split(",")
     if mode[0] == "rows":                      # DIST_CHECK_MODE = "rows,R" / "rows,S": the generic row-sharded engine
         return check_rows(dev, mode[1] if len(mode) > 1 else "R")
     for K in (3, 2):
         pb = make_problem(seed=K, U=2000, I=300, E=40000, d=64, K=K, B=512)
         eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], dev,
                               init_tables=(pb["Wu"].to(dev), pb["Wi"].to(dev)),
-                              schedule=mode[0], static_batch=mode[1] == "1", exchange=mode[2])
-        loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+                              schedule=mode[0], exchange=mode[1], max_batch=512)
+        step = eng.capture(512, pb["lam"]) if "graph" in mode[2:] else (lambda u, p, n: eng.fused_step(u, p, n, pb["lam"]))
+        for _ in range(3):                    # repeated: every buffer, signal slot and stream dependency is re-used
+            loss = step(pb["u"].to(dev), pb["p"].to(dev), pb["n"].to(dev))
         torch.cuda.synchronize()
         o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
         tol = dict(rtol=1e-5, atol=1e-7)
@@ -34,7 +36,8 @@ def main():
         torch.testing.assert_close(eng.E_f[eng.Ug:].cpu(), o_if, **tol)
         torch.testing.assert_close(eng.grad[: eng.Ug].cpu(), o_gu[eng.lo:eng.hi], rtol=1e-5, atol=1e-9)
         torch.testing.assert_close(eng.grad[eng.Ug:].cpu(), o_gi, rtol=1e-5, atol=1e-9)
-    print(f"DIST_OK rank={dist.get_rank()} users=[{eng.lo},{eng.hi}) edges={eng.local_edges}", flush=True)
+    print(f"DIST_OK rank={dist.get_rank()} mode={','.join(mode)} exchange={eng.ops.kind} multicast={getattr(eng.ops, 'multicast', False)} "
+          f"users=[{eng.lo},{eng.hi}) edges={eng.local_edges}", flush=True)
     dist.destroy_process_group()
 
 

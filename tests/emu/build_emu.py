@@ -51,12 +51,19 @@ ASM_BODIES = {
     "ld_stream_i32_hint": "return *p;",
     "ld_stream_f32_hint": "return *p;",
     "ld_stream_f4_hint": "return *p;",
+    "ld_once_f4": "return *p;",
+    "ld_once_f4_hint": "return *p;",
+    "ld_once_f8": "f4x2 v; v.a = p[0]; v.b = p[1]; return v;",
     "cp_async_commit": "",
     "cp_async_wait": "",
     # NVSwitch multicast (csrc/peer.cu): the "multicast address" is a key registered with emu_multicast_bind(); a load-reduce
     # sums the peers' copies, a store writes all of them
     "multimem_ld_reduce_f4": "return emu::mc_ld_reduce(mc);",
     "multimem_st_f4": "emu::mc_st(mc, v);",
+    # signal slots of the in-kernel barrier (only reachable with barriers on, which the single-process emulation never asks for)
+    "cas_sys": "uint32_t old = *p; if (old == cmp) *p = val; return old;",
+    "fence_sys": "",
+    "trap_now": "",
 }
 
 

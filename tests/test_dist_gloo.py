@@ -1,6 +1,6 @@
 """CPU tests (gloo, world_size 2 and 3) of the multi-GPU host logic in laplace_gnn_recommendation_b200/dist.py:
-nnz-balanced user partition, local symmetric blocks with GLOBAL normalisation, the per-layer item-block
-all-reduce, sharded BPR with partial item gradients.  The kernels are replaced by an oracle-backed ops object
+nnz-balanced user partition, local blocks with GLOBAL normalisation, the two independent layer chains with one item-block
+exchange per layer, BPR on the exchanged batch rows (loss and item gradients complete on every rank).  The kernels are replaced by an oracle-backed ops object
 defined HERE (tests may use the oracle; the product never does); the collectives are real (gloo)."""
 import os
 import socket
@@ -18,32 +18,37 @@ from oracle import lightgcn_oracle as lo
 class CpuOracleOps:
     """Same interface as dist.CudaOps, arithmetic by the CPU oracle, collectives over gloo."""
 
-    def build_graph(self, row, col, n, dinv):
+    group = None
+
+    def fork(self, two_streams):
+        import contextlib
+        return [contextlib.nullcontext(), contextlib.nullcontext()]
+
+    def join(self, two_streams):
+        pass
+
+    def build_views(self, row, col, Ug, I, dinv):
+        n = Ug + I
         rowptr, c, _ = lo.csr_from_coo(row, col, n, n)
         r = lo.rows_from_rowptr(rowptr)
-        return dict(rowptr=rowptr, col=c, val=(1.0 * dinv[r]) * dinv[c], n=n)
+        val = (1.0 * dinv[r]) * dinv[c]
+        s = int(rowptr[Ug])
+        gu = dict(rowptr=rowptr[: Ug + 1].clone(), col=c[:s] - Ug, val=val[:s], n=Ug, n_cols=I)
+        gi = dict(rowptr=rowptr[Ug:] - s, col=c[s:], val=val[s:], n=I, n_cols=Ug)
+        return gu, gi
 
-    def row_view(self, g, lo_, hi):
-        s, e = int(g["rowptr"][lo_]), int(g["rowptr"][hi])
-        return dict(rowptr=g["rowptr"][lo_:hi + 1] - s, col=g["col"][s:e], val=g["val"][s:e], n=hi - lo_)
+    def alloc_exchange(self, shapes):
+        return [torch.zeros(*sh) for sh in shapes]
 
-    def spmm(self, g, X, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
-        y = lo.spmm(g["rowptr"], g["col"], g["val"], X)
-        if resid is not None:
-            y = y + resid
-        if acc_out is not None:
-            acc_out.copy_(((acc_in if acc_in is not None else 0) + y) / acc_div)
-        if Y is not None:
-            Y.copy_(y)
+    def spmm(self, g, X, Y, resid=None):
+        y = lo.spmm(g["rowptr"], g["col"], g["val"], X) if X.shape[0] else torch.zeros(g["n"], X.shape[1])
+        Y.copy_(y if resid is None else y + resid)
 
-    def spmm_split(self, g, X, split_row, y_tail, Y=None, resid=None, acc_in=None, acc_out=None, acc_div=1.0):
-        y = lo.spmm(g["rowptr"], g["col"], g["val"], X)
-        y_tail.copy_(y[split_row:])
-        yu = y[:split_row] if resid is None else y[:split_row] + resid[:split_row]
-        if acc_out is not None:
-            acc_out[:split_row].copy_(((acc_in[:split_row] if acc_in is not None else 0) + yu) / acc_div)
-        if Y is not None:
-            Y[:split_row].copy_(yu)
+    def mean_rows(self, srcs, div, out):
+        acc = srcs[0]
+        for t in srcs[1:]:
+            acc = acc + t
+        out.copy_(acc / div)
 
     def accumulate(self, y, acc, resid, div, out):
         v = y if resid is None else y + resid
@@ -54,27 +59,41 @@ class CpuOracleOps:
     def zero(self, t):
         t.zero_()
 
-    def bpr(self, Ef, E0, Ug, u, p, n, lam, B_norm, user_lo=0, user_hi=0, loss=None, dEf=None, dE0_users=None,
-            dE0_items=None, gscale=1.0):
-        B = B_norm
+    def gather_owned(self, src, idx, lo_, hi, dst):
+        mine = (idx >= lo_) & (idx < hi)
+        dst.zero_()
+        dst[mine] = src[idx[mine] - lo_]
+
+    def scatter_add_owned(self, src, idx, lo_, hi, dst):
+        mine = (idx >= lo_) & (idx < hi)
+        dst.index_add_(0, idx[mine] - lo_, src[mine])
+
+    def bpr(self, uf, u0, pf, p0, iu, ip, in_, lam, B_norm, gscale=1.0, user_lo=0, user_hi=0, user_rows_only=False,
+            loss=None, duf=None, du0=None, dpf=None, dp0=None):
+        own = torch.ones_like(iu, dtype=torch.bool)
         if user_hi > 0:
-            mine = (u >= user_lo) & (u < user_hi)
-            u, p, n = u[mine] - user_lo, p[mine], n[mine]
-        uf, pf, nf = Ef[u], Ef[Ug + p], Ef[Ug + n]
-        u0, p0, n0 = E0[u], E0[Ug + p], E0[Ug + n]
-        x = (uf * pf).sum(-1) - (uf * nf).sum(-1)
+            own = (iu >= user_lo) & (iu < user_hi)
+            if not user_rows_only:
+                iu, ip, in_, own = iu[own], ip[own], in_[own], own[own]
+            iu = iu - user_lo
+        d = pf.shape[1]
+        ufr = torch.zeros(iu.numel(), d); u0r = torch.zeros(iu.numel(), d)
+        ufr[own] = uf[iu[own]]; u0r[own] = u0[iu[own]]
+        pfr, nfr, p0r, n0r = pf[ip], pf[in_], p0[ip], p0[in_]
+        x = (ufr * pfr).sum(-1) - (ufr * nfr).sum(-1)
         if loss is not None:
-            loss.copy_(-F.softplus(x).sum() / B + lam * ((u0 ** 2).sum() + (p0 ** 2).sum() + (n0 ** 2).sum()))
-        c = (-torch.sigmoid(x) / B * gscale).unsqueeze(1)
-        if dEf is not None:
-            dEf.index_add_(0, u, c * (pf - nf))
-            dEf.index_add_(0, Ug + p, c * uf)
-            dEf.index_add_(0, Ug + n, -c * uf)
-        if dE0_users is not None:
-            dE0_users.index_add_(0, u, 2 * lam * u0)
-        if dE0_items is not None:
-            dE0_items.index_add_(0, p, 2 * lam * p0)
-            dE0_items.index_add_(0, n, 2 * lam * n0)
+            loss.copy_(-F.softplus(x).sum() / B_norm + lam * ((u0r ** 2).sum() + (p0r ** 2).sum() + (n0r ** 2).sum()))
+        c = (-torch.sigmoid(x) / B_norm * gscale).unsqueeze(1)
+        if duf is not None:
+            duf.index_add_(0, iu[own], (c * (pfr - nfr))[own])
+        if dpf is not None:
+            dpf.index_add_(0, ip, c * ufr)
+            dpf.index_add_(0, in_, -c * ufr)
+        if du0 is not None and du0.numel():
+            du0.index_add_(0, iu[own], 2 * lam * u0r[own])
+        if dp0 is not None:
+            dp0.index_add_(0, ip, 2 * lam * p0r)
+            dp0.index_add_(0, in_, 2 * lam * n0r)
 
     def adam(self, p, g, m, v, lr, beta1, beta2, eps, step):
         m.lerp_(g, 1 - beta1)
@@ -82,13 +101,20 @@ class CpuOracleOps:
         bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
         p.addcdiv_(m, (v.sqrt() / (bc2 ** 0.5)).add_(eps), value=-lr / bc1)
 
-    class _Done:
-        def wait(self):
-            pass
+    class _Lazy:
+        """An exchange that only happens when somebody waits for it: the latest moment a real asynchronous collective may
+        complete.  Code that reads the buffer before wait() sees the un-reduced partial sums and fails the parity check."""
 
-    def all_reduce_async(self, t):
-        self.all_reduce(t)
-        return self._Done()
+        def __init__(self, ops, t):
+            self.ops, self.t = ops, t
+
+        def wait(self):
+            if self.t is not None:
+                self.ops.all_reduce(self.t)
+                self.t = None
+
+    def exchange_async(self, t, channel=0):
+        return self._Lazy(self, t)
 
     def all_reduce(self, t):
         if dist.is_initialized() and dist.get_world_size() > 1:
@@ -112,13 +138,14 @@ def single_process_reference(pb):
 
 
 def make_emu_ops(lazy: bool = True):
-    """dist.CudaOps itself -- row views, lgb_gcn_values, lgb_spmm(_split), lgb_accumulate, lgb_bpr with B_norm and the
-    owned-user filter -- with the kernels served by the CPU emulation of the library (tests/emu/) and the collectives by
-    gloo.  Only the two CUDA-stream specifics of the class are replaced."""
+    """dist.CudaOps itself -- the two CSR views of the local block, lgb_gcn_values, lgb_spmm, lgb_mean_rows, the owned-row
+    gather / scatter, lgb_bpr on explicit operand tables (incl. the user-rows-only filter) -- with the kernels served by the
+    CPU emulation of the library (tests/emu/) and the collectives by gloo.  Only the CUDA-stream specifics are replaced."""
+    import contextlib
     from laplace_gnn_recommendation_b200.dist import CudaOps, _Done
 
     class _Lazy:
-        """Handle of an all-reduce that only happens when somebody waits for it: the latest moment a real asynchronous
+        """Handle of an exchange that only happens when somebody waits for it: the latest moment a real asynchronous
         collective may complete.  Code that reads the buffer before wait() sees the un-reduced partial sums and fails the
         parity check -- the CPU stand-in for a missing stream dependency."""
 
@@ -132,13 +159,21 @@ def make_emu_ops(lazy: bool = True):
 
     class EmuOps(CudaOps):
         def __init__(self, device, group=None):
-            self.device, self.group, self.comm, self._bpr_ws = device, group, None, None
+            self.device, self.group, self.comm, self.chains, self._bpr_ws, self.exchange_events = device, group, None, None, None, None
 
-        def all_reduce_async(self, t):
+        def fork(self, two_streams):
+            return [contextlib.nullcontext(), contextlib.nullcontext()]
+
+        def join(self, two_streams):
+            pass
+
+        def exchange_async(self, t, channel=0):
             if lazy:
                 return _Lazy(self, t)
             self.all_reduce(t)
             return _Done()
+
+        all_reduce_async = exchange_async
 
     return EmuOps(torch.device("cpu"))
 
@@ -151,7 +186,7 @@ def _worker(rank, world, port, cases, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.set_num_threads(1)
-        for ci, (K, schedule, static_batch, ops_kind, d) in enumerate(cases):
+        for ci, (K, schedule, ops_kind, d) in enumerate(cases):
             pb = make_problem(K=K, d=d)
             if ops_kind == "emu":
                 from tests.emu.harness import emulated
@@ -161,12 +196,12 @@ def _worker(rank, world, port, cases, out_dir):
             with ctx:
                 ops = make_emu_ops() if ops_kind == "emu" else CpuOracleOps()
                 eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=ops,
-                                      init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, static_batch=static_batch)
+                                      init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, max_batch=128)
                 loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
                 tuned = None
                 if ops_kind == "emu" and ci == len(cases) - 1:      # plan-time choice of the step form, once per world size
                     import time
-                    tuned = eng.autotune_step(pb["u"], pb["p"], pb["n"], pb["lam"], candidates=((None, False), (None, True), ("pipelined", True)),
+                    tuned = eng.autotune_step(pb["u"], pb["p"], pb["n"], pb["lam"], candidates=("chains", "layer"),
                                               timer=lambda fn: (time.perf_counter(), fn(), time.perf_counter())[2] * 0 + 1.0 + rank)
                     loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])      # the installed winner still computes the step
                 snap = dict(loss=loss.clone(), Ef=eng.E_f.clone(), grad=eng.grad.clone())
@@ -185,16 +220,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-# (K, schedule, static_batch, ops_kind, d).  "oracle": the kernels are the CPU oracle (host logic only); "emu": dist.CudaOps
-# drives the REAL kernel sources under the CPU emulator (tests/emu/) -- covers lgb_spmm_split, the BPR owned-user filter /
-# B_norm and the row views under every schedule without a GPU, with lazy all-reduce handles (see make_emu_ops).
+# (K, schedule, ops_kind, d).  "oracle": the kernels are the CPU oracle (host logic only); "emu": dist.CudaOps drives the REAL
+# kernel sources under the CPU emulator (tests/emu/) -- covers the remapped CSR views, lgb_mean_rows, the owned-row gather /
+# scatter and the BPR user-rows-only filter under both schedules without a GPU, with lazy exchange handles (see make_emu_ops).
 CASES = {
-    2: [(3, "layer", False, "oracle", 16), (1, "layer", True, "oracle", 16), (3, "pipelined", True, "oracle", 16),
-        (3, "merged", True, "oracle", 16), (1, "merged", False, "oracle", 16), (1, "pipelined", True, "oracle", 16),
-        (3, "layer", False, "emu", 64), (3, "merged", True, "emu", 64), (2, "merged", False, "emu", 32),
-        (3, "pipelined", False, "emu", 64), (0, "layer", True, "emu", 64)],
-    3: [(2, "layer", False, "oracle", 16), (2, "pipelined", False, "oracle", 16), (2, "merged", False, "oracle", 16),
-        (2, "pipelined", True, "emu", 64), (1, "layer", True, "emu", 128), (2, "merged", True, "emu", 32)],
+    2: [(3, "chains", "oracle", 16), (1, "layer", "oracle", 16), (2, "chains", "oracle", 16), (0, "chains", "oracle", 16),
+        (3, "chains", "emu", 64), (3, "layer", "emu", 64), (2, "chains", "emu", 32), (1, "chains", "emu", 128), (0, "layer", "emu", 64)],
+    3: [(2, "layer", "oracle", 16), (3, "chains", "oracle", 16), (4, "chains", "oracle", 16),
+        (2, "chains", "emu", 64), (1, "layer", "emu", 128), (4, "chains", "emu", 32)],
 }
 
 
@@ -206,8 +239,8 @@ def test_sharded_step_equals_single_process_oracle(tmp_path, world):
     build_emu.build()          # once, in the parent: the spawned ranks only load it
     cases = CASES[world]
     mp.spawn(_worker, args=(world, _free_port(), cases, str(tmp_path)), nprocs=world, join=True)
-    for ci, (K, schedule, static_batch, ops_kind, d) in enumerate(cases):
-        what = f"world={world} K={K} schedule={schedule} static={static_batch} ops={ops_kind} d={d}"
+    for ci, (K, schedule, ops_kind, d) in enumerate(cases):
+        what = f"world={world} K={K} schedule={schedule} ops={ops_kind} d={d}"
         pb = make_problem(K=K, d=d)
         o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
         outs = [torch.load(tmp_path / f"case{ci}_rank{r}.pt") for r in range(world)]
@@ -241,7 +274,7 @@ def test_sharded_step_equals_single_process_oracle(tmp_path, world):
             assert torch.equal(o["table"][Ug:], outs[0]["table"][Ug0:]), what            # replicated item block: same bits on every rank
         if outs[0]["tuned"] is not None:             # autotune_step: every rank reports the same, complete, rejection-free table
             t0 = outs[0]["tuned"]
-            assert len(t0["ms"]) == 3 and not t0["rejected"] and all(o["tuned"] == t0 for o in outs), t0
+            assert len(t0["ms"]) == 2 and not t0["rejected"] and all(o["tuned"] == t0 for o in outs), t0
             assert all(v == float(world) for v in t0["ms"].values())          # max over ranks of the (1 + rank) the fake timer returns
 
 

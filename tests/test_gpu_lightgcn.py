@@ -140,6 +140,22 @@ def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
     assert torch.equal(y1, y2)
 
 
+def test_csr_build_rejects_out_of_range_indices(cuda_dev):
+    """torch_sparse's SparseTensor asserts row.max() < M / col.max() < N (what catches item ids that were not shifted by
+    both_indexes_from_zero, data/lightgcn_loader.py:39-43): the build must raise, and must not write out of bounds."""
+    row = torch.tensor([0, 1, 2, 9]); col = torch.tensor([3, 2, 1, 0])
+    for bad_row, bad_col in ((torch.tensor([0, 1, 10, 9]), col), (row, torch.tensor([3, 12, 1, 0])), (torch.tensor([0, -1, 2, 9]), col)):
+        with pytest.raises(RuntimeError, match="outside sparse_sizes"):
+            DeviceCSR.from_coo(bad_row.to(cuda_dev), bad_col.to(cuda_dev), 10, 10)
+    g = DeviceCSR.from_coo(torch.tensor([0, 1, 10, 9]).to(cuda_dev), col.to(cuda_dev), 10, 10, validate=False)   # deferred check
+    assert int(g.rowptr[-1]) == 4                     # clamped on the device: the arrays stay well-formed
+    with pytest.raises(RuntimeError, match="outside sparse_sizes"):
+        g.check_built()
+    DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), 10, 10)                                  # in range: fine
+    with pytest.raises(RuntimeError):
+        DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), 10, 0)                               # entries in an empty matrix
+
+
 def test_spmm_empty_and_ragged(cuda_dev):
     d = 64
     g = DeviceCSR.from_coo(torch.empty(0, dtype=torch.long, device=cuda_dev), torch.empty(0, dtype=torch.long, device=cuda_dev), 10, 10)
@@ -354,14 +370,19 @@ def test_topk_against_oracle(cuda_dev, k, I, d):
 
 # ------------------------------------------------------------------ sharded engine (CUDA ops)
 def test_sharded_engine_single_rank_matches_oracle(cuda_dev):
-    """world=1: exercises dist.CudaOps (row views of the local CSR, lgb_gcn_values, lgb_accumulate, B_norm)."""
+    """world=1: exercises dist.CudaOps (the two CSR views of the local block, lgb_gcn_values, lgb_mean_rows, the owned-row
+    gather / scatter, lgb_bpr on explicit operand tables) on two streams."""
     from laplace_gnn_recommendation_b200.dist import ShardedLightGCN
     from tests.test_dist_gloo import make_problem, single_process_reference
     for K in (3, 1, 2):
         pb = make_problem(seed=K, U=500, I=120, E=9000, d=64, K=K, B=256)
         eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], cuda_dev,
-                              init_tables=(pb["Wu"].to(cuda_dev), pb["Wi"].to(cuda_dev)), rank=0, world=1)
+                              init_tables=(pb["Wu"].to(cuda_dev), pb["Wi"].to(cuda_dev)), rank=0, world=1, max_batch=256,
+                              schedule="chains" if K != 2 else "layer")
         loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+        if K == 3:                            # the same step replayed from a CUDA graph (three streams captured)
+            gstep = eng.capture(256, pb["lam"])
+            loss = gstep(pb["u"].to(cuda_dev), pb["p"].to(cuda_dev), pb["n"].to(cuda_dev)).clone()
         o_loss, o_gu, o_gi, o_uf, o_if = single_process_reference(pb)
         close(loss, o_loss)
         close(eng.E_f[: pb["U"]], o_uf); close(eng.E_f[pb["U"]:], o_if)
@@ -374,8 +395,9 @@ def test_sharded_engine_two_gpus_nccl(cuda_dev, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = os.path.join(os.path.dirname(__file__), "dist_gpu_check.py")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29617", script], capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("DIST_OK") == 2
+    for mode in ("chains,auto", "chains,symm,graph", "layer,nccl"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29617", script], capture_output=True, text=True,
+                           timeout=300, env=dict(os.environ, DIST_CHECK_MODE=mode))
+        assert r.returncode == 0, mode + r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("DIST_OK") == 2, mode

@@ -1,8 +1,8 @@
 """ONE-GPU probe of the per-rank SpMM launches of an N-way sharded run (no NCCL, no torchrun): builds rank r's local
 block of the H&M-shaped graph exactly like dist.ShardedLightGCN does and times, per kernel variant and slice size,
 
-    items SpMM (partial item rows <- owned users)   users SpMM (owned user rows <- items, fused epilogue)
-    merged launch (lgb_spmm_split over all local rows)
+    items SpMM (partial item rows <- owned users)   users SpMM (owned user rows <- items, residual epilogue)
+    both launches of a layer on two streams (the engine's "chains" schedule)
 
 so the fixed per-launch cost seen in the scaling fit (profiles/README.md r1c: t = 0.09 ms + nnz / 34 G/s) can be attacked
 at 1x GPU-minutes instead of 8x.      python tools/shard_probe.py [--world 8] [--ranks 0,3,7] [--variants 0,16,12]
@@ -38,23 +38,36 @@ def main():
     users, items = make_graph(U, I, E, a.degree, 1234, dev)
     for rank in [int(x) for x in a.ranks.split(",")]:
         eng = ShardedLightGCN(U, I, a.d, 3, users, items, dev, rank=rank, world=a.world, ops=_common.make_ops(dev))   # no process group: local degrees
-        g, Ug, n = eng.g_full, eng.Ug, eng.n
-        X, Y, acc = eng.table, eng._ya, eng.E_f
-        X.normal_(0, 0.1); acc.normal_(0, 0.1)
-        print(f"rank {rank}/{a.world}: Ug={Ug} local_edges={eng.local_edges} max user deg={int((g.rowptr[1:Ug + 1] - g.rowptr[:Ug]).max())} "
-              f"max item deg={int((g.rowptr[Ug + 1:] - g.rowptr[Ug:-1]).max())}")
+        Ug, I = eng.Ug, eng.I
+        gu0, gi0 = eng.g_users, eng.g_items
+        Xu, Xi = eng.table[:Ug], eng.table[Ug:]
+        Yu, Yi, R = torch.empty_like(Xu), torch.empty_like(Xi), torch.randn_like(Xu)
+        eng.table.normal_(0, 0.1)
+        print(f"rank {rank}/{a.world}: Ug={Ug} local_edges={eng.local_edges} max user deg={int((gu0.rowptr[1:] - gu0.rowptr[:-1]).max())} "
+              f"max item deg={int((gi0.rowptr[1:] - gi0.rowptr[:-1]).max())}")
+        s0, s1 = (None, None) if _common.DRYRUN else (torch.cuda.Stream(), torch.cuda.Stream())
+
+        def both(gu, gi, v):                       # the two SpMM launches of one layer on two streams (the engine's "chains" form)
+            cur = torch.cuda.current_stream()
+            s0.wait_stream(cur); s1.wait_stream(cur)
+            with torch.cuda.stream(s0):
+                gi.spmm(Xu, Y=Yi, variant=v)
+            with torch.cuda.stream(s1):
+                gu.spmm(Xi, Y=Yu, resid=R, variant=v)
+            cur.wait_stream(s0); cur.wait_stream(s1)
         for chunk in [int(x) for x in a.chunks.split(",")]:
-            view = lambda lo, hi: DeviceCSR(hi - lo, g.n_cols, g.rowptr[lo:hi + 1], g.colidx, g.val, chunk=chunk)   # noqa: E731
-            gu, gi, ga = view(0, Ug), view(Ug, n), view(0, n)
+            def view(g0):
+                v = DeviceCSR(g0.n_rows, g0.n_cols, g0.rowptr, g0.colidx, g0.val, chunk=chunk)
+                v.nnz = g0.nnz
+                return v
+            gu, gi = view(gu0), view(gi0)
             print(f"  chunk {chunk}: users view long={gu.n_long} tasks={gu.n_tasks} | items view long={gi.n_long} tasks={gi.n_tasks}")
             for v in [int(x) for x in a.variants.split(",")]:
-                t_i = timeit(lambda: gi.spmm(X, Y=Y[Ug:], variant=v))
-                t_u = timeit(lambda: gu.spmm(X, Y=Y[:Ug], acc_in=acc[:Ug], acc_out=acc[:Ug], variant=v))
-                t_m = float("nan")
-                if v not in (2, 3):
-                    t_m = timeit(lambda: ga.spmm(X, Y=Y, acc_in=acc, acc_out=acc, variant=v, split_row=Ug, y_tail=Y[Ug:]))
+                t_i = timeit(lambda: gi.spmm(Xu, Y=Yi, variant=v))
+                t_u = timeit(lambda: gu.spmm(Xi, Y=Yu, resid=R, variant=v))
+                t_b = timeit(lambda: both(gu, gi, v)) if not _common.DRYRUN else float("nan")
                 print(f"    variant {v:2d}: items {t_i * 1e3:7.1f} us | users {t_u * 1e3:7.1f} us | sum {(t_i + t_u) * 1e3:7.1f} us | "
-                      f"merged launch {t_m * 1e3:7.1f} us   ({eng.local_edges / 1e6:.2f} M edges per direction)")
+                      f"both on two streams {t_b * 1e3:7.1f} us   ({eng.local_edges / 1e6:.2f} M edges per direction)")
         del eng
         _common.empty_cache()
 
