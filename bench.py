@@ -252,7 +252,8 @@ def sharded_parity_check(args, dev, rank, world):
     eng = ShardedLightGCN(U, I, d, K, users, items, dev, schedule="chains" if args.schedule == "auto" else args.schedule,
                           exchange=args.exchange, ops=ops, init_tables=(Wu, Wi), max_batch=B)
     ud, pd, nd = u.to(dev), p.to(dev), n.to(dev)
-    out = {"exchange": getattr(eng.ops, "kind", "?"), "multicast": bool(getattr(eng.ops, "multicast", False)), "schedule": eng.schedule}
+    out = {"exchange": getattr(eng.ops, "kind", "?"), "multicast": bool(getattr(eng.ops, "multicast", False)),
+           "mode": getattr(eng.ops, "mode", None), "schedule": eng.schedule}
     forms = {"eager": lambda: eng.fused_step(ud, pd, nd, lam)}
     if want_graph(args, eng):
         try:
@@ -435,7 +436,8 @@ def run_ours(args):
         bus = [2.0 * n * (world - 1) / world for n in x_bytes]
         exchange = {"collective": ("own kernel over symmetric memory (lgb_exchange_allreduce_f32: barrier + multimem.ld_reduce / multimem.st + barrier)"
                                    if getattr(eng.ops, "kind", "") == "symm" else "NCCL all-reduce") + " of the replicated item block",
-                    "multicast": bool(getattr(eng.ops, "multicast", False)), "per_step": len(ev) // max(args.steps, 1),
+                    "multicast": bool(getattr(eng.ops, "multicast", False)), "mode": getattr(eng.ops, "mode", None),
+                    "mode_choice": getattr(eng.ops, "mode_report", None), "per_step": len(ev) // max(args.steps, 1),
                     "mean_ms": statistics.mean(x_ms), "mean_bytes": statistics.mean(x_bytes),
                     "bus_GBps": sum(bus) / 1e9 / (sum(x_ms) * 1e-3), "nvlink_peak_GBps_per_direction": 900.0,
                     "frac_of_nominal": sum(bus) / 1e9 / (sum(x_ms) * 1e-3) / 900.0,

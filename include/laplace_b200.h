@@ -290,10 +290,13 @@ int lgb_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int32_t ra
  * and a symmetric, zero-initialised array of n_channels * lgb_exchange_pad_words(world) uint32 signal slots on every
  * rank.  The call reduces the n_floats at byte_offset of the arena in place.  Exchanges that may be in flight at the
  * same time (different streams) must use different channels; every rank must issue the exchanges of one channel in the
- * same order.  LGB_EXCHANGE_NO_BARRIER skips both barriers (single-process tests only).  A barrier that waits longer
- * than ~4 s traps. */
+ * same order and with the same flags.  LGB_EXCHANGE_NO_BARRIER skips both barriers (single-process tests only).  A barrier
+ * that waits longer than ~4 s traps. */
 #define LGB_EXCHANGE_MAX_WORLD 16
 #define LGB_EXCHANGE_NO_BARRIER 1
+#define LGB_EXCHANGE_PEER 2            /* peer loads / stores even when a multicast address is given: (G-1)/G of the buffer per
+                                          link direction instead of (G+1)/G, at the price of G loads per element in the SM */
+#define LGB_EXCHANGE_BLOCKS_SHIFT 8    /* bits 8..15: CTAs of the launch (0 = 64; at most 128) -- the same value on every rank */
 typedef struct lgb_exchange {
   void* multicast_base;                          /* NVSwitch multicast mapping of the arena, or NULL */
   void* peer_base[LGB_EXCHANGE_MAX_WORLD];       /* the arena on rank r (UVA / symmetric-memory pointer) */

@@ -68,7 +68,7 @@ class DeviceCSR:
         self.perm: Optional[torch.Tensor] = None      # COO -> CSR permutation (int64) when built from COO
         self.csr2csc: Optional[torch.Tensor] = None   # set on the TRANSPOSED graph: its entry i is CSR entry csr2csc[i]
         self._t: Optional["DeviceCSR"] = None
-        self._partials: Dict[int, torch.Tensor] = {}
+        self._partials: Dict[tuple, torch.Tensor] = {}
         self._struct: Optional[LgbCsr] = None
         self.variant: Optional[int] = None             # kernel variant chosen by autotune() for THIS graph (None: the default)
         self.autotune_report: Optional[dict] = None
@@ -288,12 +288,15 @@ class DeviceCSR:
         return self._struct
 
     def _partial_ws(self, d: int) -> Optional[torch.Tensor]:
+        """Partial-sum scratch of the long-row slices: one per (width, STREAM) -- the sharded engine runs the same graph on two
+        streams at once (layer k of one chain next to layer k+1 of the other), and launches that overlap must not share it."""
         if self.n_tasks == 0:
             return None
-        buf = self._partials.get(d)
+        key = (d, torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0)
+        buf = self._partials.get(key)
         if buf is None or buf.numel() < self.n_tasks * d:
             buf = torch.empty(self.n_tasks * d, dtype=torch.float32, device=self.device)
-            self._partials[d] = buf
+            self._partials[key] = buf
         return buf
 
     # ---- the hot call -------------------------------------------------------------------

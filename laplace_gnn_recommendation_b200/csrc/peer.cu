@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) peer_allreduce_kernel(PeerPtrs peers, int
 // The body is the slice loop of the kernels above, four 16-byte accesses in flight per thread.  A spin that lasts longer
 // than ~4 s (a peer died, mismatched launch order) traps instead of hanging the GPU.
 constexpr int XCHG_THREADS = 512;
-constexpr int XCHG_MAX_BLOCKS = 64;
+constexpr int XCHG_MAX_BLOCKS = 128;      // signal slots are sized for this; the launch uses min(this, blocks asked for, work)
+constexpr int XCHG_DEFAULT_BLOCKS = 64;
 constexpr int XCHG_UNROLL = 4;
 constexpr long long XCHG_SPIN_LIMIT = 8000000000ll;   // clock64 ticks (~4 s at 1.9 GHz)
 
@@ -198,7 +199,7 @@ int lgb_exchange_allreduce_f32(const lgb_exchange* x, int64_t byte_offset, int64
               (int)x->n_channels);
   const bool barriers = !(flags & LGB_EXCHANGE_NO_BARRIER);
   XchgParams p;
-  p.mc = x->multicast_base ? (float4*)((char*)x->multicast_base + byte_offset) : nullptr;
+  p.mc = (x->multicast_base && !(flags & LGB_EXCHANGE_PEER)) ? (float4*)((char*)x->multicast_base + byte_offset) : nullptr;
   for (int r = 0; r < PEER_MAX; ++r) {
     p.peer[r] = r < x->world && x->peer_base[r] ? (float4*)((char*)x->peer_base[r] + byte_offset) : nullptr;
     p.pad[r] = r < x->world && x->pad_base[r] ? (uint32_t*)x->pad_base[r] + (size_t)channel * lgb_exchange_pad_words(x->world) : nullptr;
@@ -212,7 +213,9 @@ int lgb_exchange_allreduce_f32(const lgb_exchange* x, int64_t byte_offset, int64
   // the SAME grid on every rank (blocks pair up across ranks): sized from the slice length, which is rank-independent
   const int64_t per = (n_floats / 4 + x->world - 1) / x->world;
   int64_t blocks = (per + (int64_t)XCHG_THREADS * XCHG_UNROLL - 1) / ((int64_t)XCHG_THREADS * XCHG_UNROLL);
-  blocks = blocks < 1 ? 1 : (blocks > XCHG_MAX_BLOCKS ? XCHG_MAX_BLOCKS : blocks);
+  int64_t cap = (flags >> LGB_EXCHANGE_BLOCKS_SHIFT) & 0xFF;
+  cap = cap == 0 ? XCHG_DEFAULT_BLOCKS : (cap > XCHG_MAX_BLOCKS ? XCHG_MAX_BLOCKS : cap);
+  blocks = blocks < 1 ? 1 : (blocks > cap ? cap : blocks);
   if (p.mc)
     exchange_allreduce_kernel<true><<<(unsigned)blocks, XCHG_THREADS, 0, (cudaStream_t)stream>>>(p);
   else

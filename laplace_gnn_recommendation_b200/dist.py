@@ -274,7 +274,7 @@ class SymmOps(CudaOps):
         hi_pri = torch.cuda.Stream.priority_range()[1] if hasattr(torch.cuda.Stream, "priority_range") else -1
         self.comm = [torch.cuda.Stream(device=device, priority=hi_pri) for _ in range(N_CHANNELS)]
         self._arena = self._x = self._handle = None
-        self.multicast = False
+        self.multicast, self.mode, self.flags, self.mode_report = False, None, 0, None
 
     def alloc_exchange(self, shapes):
         if not self._multi():
@@ -306,14 +306,55 @@ class SymmOps(CudaOps):
         x.rank, x.world, x.n_channels = rank, world, N_CHANNELS
         self._arena, self._x, self._handle, self.multicast = arena, x, h, bool(mc)
         dist.barrier(group=grp)                                # every rank has zeroed its arena before anybody signals
-        return [arena[o:o + n].view(*s) for o, n, s in zip(offs, sizes, shapes)]
+        bufs = [arena[o:o + n].view(*s) for o, n, s in zip(offs, sizes, shapes)]
+        self._choose_mode(bufs[0], grp)
+        return bufs
+
+    def _choose_mode(self, buf, grp):
+        """Plan-time choice between the multicast form (in-switch reduction, (G+1)/G of the buffer per link direction) and
+        the peer form ((G-1)/G, but G loads per element): both are run on the largest exchange buffer, timed with CUDA
+        events, max over ranks; every rank takes the same decision.  LGB_EXCHANGE_MODE=multicast|peer pins it."""
+        import os
+        want = os.environ.get("LGB_EXCHANGE_MODE", "auto")
+        blocks = int(os.environ.get("LGB_EXCHANGE_BLOCKS", "0"))
+        self.flags = (blocks & 0xFF) << 8
+        self.mode_report = {"multicast_available": self.multicast}
+        if not self.multicast or want == "peer":
+            self.flags |= 2
+            self.mode = "peer"
+            return
+        self.mode = "multicast"
+        if want != "auto":
+            return
+        comm = self.comm[0]
+        times = {}
+        for name, fl in (("multicast", 0), ("peer", 2)):
+            self.flags = (self.flags & ~2) | fl
+            with torch.cuda.stream(comm):
+                for _ in range(2):
+                    self._exchange(buf, 0, comm)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(comm)
+                for _ in range(5):
+                    self._exchange(buf, 0, comm)
+                e1.record(comm)
+            e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 5], device=self.device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=grp)
+            times[name] = float(t)
+        self.mode = min(times, key=times.get)
+        self.flags = (self.flags & ~2) | (2 if self.mode == "peer" else 0)
+        self.mode_report.update(ms=times, chosen=self.mode, bytes=buf.numel() * 4)
+        buf.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=grp)
 
     def _exchange(self, t, channel, comm):
         off = t.data_ptr() - self._arena.data_ptr() if self._arena is not None else -1
         if off < 0 or off + t.numel() * 4 > self._arena.numel() * 4 or t.numel() % 4 != 0 or not t.is_contiguous():
             raise RuntimeError("SymmOps: the exchanged tensor must be a contiguous buffer from alloc_exchange with numel % 4 == 0")
         with torch.cuda.device(self.device):
-            check(_lib.load().lgb_exchange_allreduce_f32(C.byref(self._x), off, t.numel(), channel, 0, comm.cuda_stream),
+            check(_lib.load().lgb_exchange_allreduce_f32(C.byref(self._x), off, t.numel(), channel, int(getattr(self, "flags", 0)), comm.cuda_stream),
                   "exchange_allreduce")
         _lib.count_launch()
 

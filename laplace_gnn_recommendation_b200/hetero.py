@@ -44,10 +44,52 @@ def key2str(key) -> str:
 # --------------------------------------------------------------------------------------------
 # neighbour aggregation
 # --------------------------------------------------------------------------------------------
-def build_edge_csr(edge_index: torch.Tensor, n_src: int, n_dst: int) -> DeviceCSR:
-    """dst-major CSR of one edge type: row = edge_index[1] (target), col = edge_index[0] (source)."""
+# Per-batch graphs are built WITHOUT a host synchronisation (the batch set-up used to stall the stream five times per step):
+#   * no long-row split plan (chunk = 0; its slice count would have to be read back) -- neighbour lists of sampled batches are
+#     bounded by the loader's fan-out, a row is walked by one warp / lane group;
+#   * the index-range check of the CSR build and the "is this edge type the flip of that one" test leave their verdicts on the
+#     device; they are copied to pinned memory asynchronously and examined at the START OF THE NEXT BATCH (or by
+#     ``flush_deferred_checks()``), when they have long been computed.  Out-of-range indices are clamped on the device, so a
+#     bad batch cannot write out of bounds in the meantime; it raises one step late.
+BATCH_GRAPH_CHUNK = int(os.environ.get("LGB_HETERO_CHUNK", "0"))
+_deferred: List[tuple] = []          # (event, pinned int32 tensor, message)
+
+
+def _defer_check(flag: torch.Tensor, message: str) -> None:
+    """flag: device int32 scalar-like tensor that must be 0."""
+    host = torch.empty(1, dtype=torch.int32).pin_memory() if flag.is_cuda else torch.empty(1, dtype=torch.int32)
+    host.copy_(flag.reshape(-1)[:1], non_blocking=True)
+    ev = None
+    if flag.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+    _deferred.append((ev, host, message))
+
+
+def flush_deferred_checks() -> None:
+    """Examine the verdicts the previous batches left behind (waits for their copies only, not for the stream)."""
+    while _deferred:
+        ev, host, message = _deferred.pop(0)
+        if ev is not None:
+            ev.synchronize()
+        if int(host[0]) != 0:
+            _deferred.clear()
+            raise RuntimeError(message)
+
+
+def build_edge_csr(edge_index: torch.Tensor, n_src: int, n_dst: int, deferred: bool = False) -> DeviceCSR:
+    """dst-major CSR of one edge type: row = edge_index[1] (target), col = edge_index[0] (source).
+    deferred=True (the per-batch path): no split plan and the index-range verdict is examined one batch later."""
     _lib.require_cuda(edge_index)
-    return DeviceCSR.from_coo(edge_index[1], edge_index[0], n_dst, n_src)
+    if not deferred:
+        return DeviceCSR.from_coo(edge_index[1], edge_index[0], n_dst, n_src)
+    g = DeviceCSR.from_coo(edge_index[1], edge_index[0], n_dst, n_src, chunk=BATCH_GRAPH_CHUNK, validate=False)
+    ws = getattr(g, "_build_ws", None)
+    if ws is not None:
+        _defer_check(ws[:4].view(torch.int32), "an edge_index of the previous batch holds node ids outside its node-feature "
+                                               "matrices (lgb_csr_build: index outside sparse_sizes)")
+        g._build_ws = None
+    return g
 
 
 class _Aggregate(torch.autograd.Function):
@@ -198,7 +240,7 @@ def _fan_in(outs: List[torch.Tensor], aggr: str) -> torch.Tensor:
 
 
 def _is_flip_of(a: torch.Tensor, b: torch.Tensor) -> bool:
-    """a == b.flip(0), entry for entry (one fused comparison; the bool read-back is the only host sync of the batch set-up)."""
+    """a == b.flip(0), entry for entry (host-synchronising: used once per edge-type pair, see HeteroEncoder._flip_mate)."""
     return bool(torch.equal(a[0], b[1]) and torch.equal(a[1], b[0]))
 
 
@@ -216,19 +258,41 @@ class HeteroEncoder(nn.Module):
         self.bake_dropout_training = bake_dropout_training
         self.layers = nn.ModuleList([
             nn.ModuleDict({key2str(et): copy.deepcopy(layer) for et in self.edge_types}) for layer in module.layers])
+        self._flip_of: Dict[tuple, Optional[tuple]] = {}      # edge type -> the edge type it is the flip of (decided on the first batch)
+
+    def _flip_mate(self, et, graphs, edge_index_dict):
+        """The already-built edge type that ``et`` is the exact flip of (``rev_buys`` of ``buys``, what ToUndirected produces), or
+        None.  A property of the data pipeline, not of one batch: decided on the first batch with a host-side comparison and
+        from then on re-verified on the device, the verdict examined one batch later (no host synchronisation per step)."""
+        ei = edge_index_dict[et]
+        if et not in self._flip_of:
+            self._flip_of[et] = next((o for o in graphs if o[0] == et[2] and o[2] == et[0]
+                                      and edge_index_dict[o].shape == ei.shape and _is_flip_of(ei, edge_index_dict[o])), None)
+            return self._flip_of[et]
+        mate = self._flip_of[et]
+        if mate is None or mate not in graphs:
+            return None
+        other = edge_index_dict[mate]
+        if other.shape != ei.shape:
+            raise RuntimeError(f"edge type {et} was the flip of {mate} on the first batch but has a different number of edges now")
+        differs = ((ei[0] != other[1]) | (ei[1] != other[0])).any().to(torch.int32)
+        _defer_check(differs, f"edge type {et} was the exact flip of {mate} on the first batch but not on the previous one: "
+                              "construct the model with reuse_flipped_edge_types=False")
+        return mate
+
+    reuse_flipped_edge_types = True
 
     def forward(self, x_dict: Dict[str, torch.Tensor], edge_index_dict) -> Dict[str, torch.Tensor]:
         x = dict(x_dict)
+        flush_deferred_checks()                    # verdicts of the previous batch (index range, flipped edge types)
         # one CSR (+ lazily its transpose) per edge type per batch, shared by all layers and the backward; an edge type
-        # that is the exact flip of another one (``rev_buys`` of ``buys``, what ToUndirected produces) IS that one's
-        # transpose, so the pair costs two sorts instead of four
+        # that is the exact flip of another one IS that one's transpose, so the pair costs two sorts instead of four
         graphs: Dict[tuple, DeviceCSR] = {}
         for et in self.edge_types:
             ei = edge_index_dict[et]
-            mate = next((o for o in graphs if o[0] == et[2] and o[2] == et[0]
-                         and edge_index_dict[o].shape == ei.shape and _is_flip_of(ei, edge_index_dict[o])), None)
+            mate = self._flip_mate(et, graphs, edge_index_dict) if self.reuse_flipped_edge_types else None
             graphs[et] = graphs[mate].transpose() if mate is not None else \
-                build_edge_csr(ei, x[et[0]].shape[0], x[et[2]].shape[0])
+                build_edge_csr(ei, x[et[0]].shape[0], x[et[2]].shape[0], deferred=True)
         for li, convs in enumerate(self.layers):
             last = li == len(self.layers) - 1
             if not last and self.p_dropout_features is not None:
@@ -362,6 +426,21 @@ def padded_stack(tensors: List[torch.Tensor], value=0) -> torch.Tensor:
     return torch.stack([F.pad(x, (0, full - x.size(-1)), value=value) if full > x.size(-1) else x for x in tensors], dim=0)
 
 
+def rebatch_by_user(out: torch.Tensor, users: torch.Tensor, value) -> torch.Tensor:
+    """The re-batching of ``infer`` (model/encoder_decoder.py:161-164: ``unique`` + one boolean mask per user + padded_stack)
+    as one segmented scatter: row r holds the scores of the r-th smallest user id in their original edge order, right-padded
+    with ``value``.  Same [users_in_batch, max_candidates] result, no per-user Python loop."""
+    uniq, inv, counts = torch.unique(users, sorted=True, return_inverse=True, return_counts=True)
+    if uniq.numel() == 0:
+        return out.new_empty(0, 0)
+    order = torch.sort(inv, stable=True).indices                  # edges grouped by user, original order kept inside a group
+    starts = torch.cumsum(counts, 0) - counts
+    pos = torch.arange(users.numel(), device=users.device) - starts[inv[order]]
+    res = out.new_full((uniq.numel(), int(counts.max())), float(value))
+    res[inv[order], pos] = out[order]
+    return res
+
+
 class Encoder_Decoder_Model(nn.Module):
     """Drop-in for model/encoder_decoder.py:75-164 (same ctor kwargs, forward / infer /
     initialize_encoder_input_size, same state_dict keys)."""
@@ -416,6 +495,4 @@ class Encoder_Decoder_Model(nn.Module):
     def infer(self, x_dict, edge_index_dict: dict, edge_label_index: torch.Tensor) -> torch.Tensor:
         self.eval()
         out = self.forward(x_dict, edge_index_dict, edge_label_index).detach()
-        users = edge_label_index[0].unique(sorted=True)
-        out_per_user = [out[edge_label_index[0] == user] for user in users]
-        return padded_stack(out_per_user, value=-(1 << 50))
+        return rebatch_by_user(out, edge_label_index[0], value=-(1 << 50))

@@ -317,16 +317,33 @@ def test_reverse_edge_type_shares_the_transposed_csr(cuda_dev, monkeypatch):
     monkeypatch.setattr(hetero, "build_edge_csr", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
     z_shared = enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()})
     assert len(calls) == 1
-    monkeypatch.setattr(hetero, "_is_flip_of", lambda a, b: False)           # force two independent builds of the same edges
+    z_again = enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()})   # later batches: decided once, verified on the device
+    assert len(calls) == 2
+    hetero.flush_deferred_checks()
+    enc.reuse_flipped_edge_types = False                                     # force two independent builds of the same edges
     z_own = enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()})
-    assert len(calls) == 3
+    assert len(calls) == 4
     for k in z_shared:
-        assert torch.equal(z_shared[k], z_own[k])                            # same arrays, same summation order: same bits
+        assert torch.equal(z_shared[k], z_own[k]) and torch.equal(z_shared[k], z_again[k])   # same arrays, same summation order: same bits
+    # a pipeline that stops producing flipped pairs is caught -- one batch late, without a host synchronisation per step
+    enc.reuse_flipped_edge_types = True
+    enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: other})
+    with pytest.raises(RuntimeError, match="exact flip"):
+        hetero.flush_deferred_checks()
+    # node ids outside the feature matrices: clamped on the device, reported one batch late as well
+    bad = e.clone(); bad[1, 0] = Na + 5
+    enc(dict(x), {hetero.EDGE_KEY: bad, hetero.REV_EDGE_KEY: bad.flip(0).contiguous()})
+    with pytest.raises(RuntimeError, match="outside"):
+        enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()})
+    hetero.flush_deferred_checks()
     monkeypatch.undo()
     calls.clear()
     monkeypatch.setattr(hetero, "build_edge_csr", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
-    enc(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: other})
+    torch.manual_seed(0)
+    enc2 = lg.to_hetero(hetero.GNNEncoder(lg.get_SAGEConv_layers(2, 16, 8, "mean"), None, None), metadata, aggr="sum").to(cuda_dev)
+    enc2(dict(x), {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: other})          # a reverse type with its own edges is built on its own
     assert len(calls) == 2
+    hetero.flush_deferred_checks()
 
 
 @pytest.mark.parametrize("k,I,d,U", [(12, 3706, 64, 70), (256, 3706, 64, 33), (12, 500, 32, 64), (1000, 1200, 16, 9), (5, 3, 8, 17),
