@@ -16,7 +16,7 @@ nvidia-smi topo -m > $O/b${N}_topo.txt 2>&1
 if [ -z "$QUICK" ]; then
   MODES="chains,auto chains,symm,graph layer,symm chains,nccl layer,nccl rows,R rows,S"
 else
-  MODES="chains,auto chains,symm,graph chains,nccl"
+  MODES="chains,auto chains,symm,graph"
 fi
 for mode in $MODES; do
   DIST_CHECK_MODE=$mode TR 150 tests/dist_gpu_check.py > $O/b${N}_check_${mode//,/_}.log 2>&1
