@@ -8,6 +8,7 @@ host-side mirror of the reference interface (``LightGCN``, ``bpr_loss``, ``Spars
 There is no CPU fallback: the kernels fail loudly when the shared library or a CUDA device is missing.
 """
 from . import _lib  # noqa: F401
+from .aliases import HeteroData, install_aliases, patch_driver  # noqa: F401
 from .bpr import bpr_indexed, bpr_loss  # noqa: F401
 from .csr import DeviceCSR  # noqa: F401
 from .hetero import (EdgeDecoder, Encoder_Decoder_Model, GNNEncoder, HeteroEncoder, SAGEConv, aggregate,  # noqa: F401
@@ -26,5 +27,6 @@ __all__ = [
     "SeenItems", "topk_dict", "SAGEConv", "to_hetero", "GNNEncoder", "HeteroEncoder", "EdgeDecoder",
     "Encoder_Decoder_Model", "get_SAGEConv_layers", "get_linear_layers", "aggregate", "build_edge_csr",
     "edge_concat", "edge_dot", "both_indexes_from_zero", "split", "make_lightgcn_splits", "evaluation",
-    "get_metrics_lightgcn", "get_metrics_universal", "recall_precision_ndcg", "FusedAdam",
+    "get_metrics_lightgcn", "get_metrics_universal", "recall_precision_ndcg", "FusedAdam", "install_aliases", "patch_driver",
+    "HeteroData",
 ]

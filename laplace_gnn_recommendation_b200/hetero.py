@@ -52,12 +52,23 @@ def key2str(key) -> str:
 #     ``flush_deferred_checks()``), when they have long been computed.  Out-of-range indices are clamped on the device, so a
 #     bad batch cannot write out of bounds in the meantime; it raises one step late.
 BATCH_GRAPH_CHUNK = int(os.environ.get("LGB_HETERO_CHUNK", "0"))
-_deferred: List[tuple] = []          # (event, pinned int32 tensor, message)
+_deferred: List[tuple] = []          # (event, pinned int32 slot, message)
+_slots: Dict[bool, torch.Tensor] = {}    # one pinned ring per process (a cudaHostAlloc per check would serialise with the copies in flight)
+_RING = 256
 
 
 def _defer_check(flag: torch.Tensor, message: str) -> None:
     """flag: device int32 scalar-like tensor that must be 0."""
-    host = torch.empty(1, dtype=torch.int32).pin_memory() if flag.is_cuda else torch.empty(1, dtype=torch.int32)
+    ring = _slots.get(flag.is_cuda)
+    if ring is None:
+        ring = torch.zeros(_RING, dtype=torch.int32)
+        ring = ring.pin_memory() if flag.is_cuda else ring
+        _slots[flag.is_cuda] = ring
+        _slots["next"] = 0
+    if len(_deferred) >= _RING - 1:      # nobody flushed for a long time: do it now rather than overwrite a pending slot
+        flush_deferred_checks()
+    i = _slots["next"] = (_slots.get("next", 0) + 1) % _RING
+    host = ring[i:i + 1]
     host.copy_(flag.reshape(-1)[:1], non_blocking=True)
     ev = None
     if flag.is_cuda:
@@ -191,15 +202,17 @@ def get_SAGEConv_layers(num_layers: int, hidden_channels: int, out_channels: int
 
 
 def get_linear_layers(num_layers: int, in_channels: int, hidden_channels: int, out_channels: int) -> nn.ModuleList:
-    """model/layers.py:35-56."""
+    """model/layers.py:35-56.  The reference instantiates first / middle / last layer BEFORE it branches on num_layers (and
+    builds fresh ones for 1 and 2 layers): the same three initialisations are drawn here, so that a seeded run initialises
+    the decoder -- and everything constructed after it -- exactly like the reference."""
+    first = Linear(in_channels, hidden_channels)
+    middle = Linear(hidden_channels, hidden_channels)
+    last = Linear(hidden_channels, out_channels)
     if num_layers == 1:
         return nn.ModuleList([Linear(in_channels, out_channels)])
     if num_layers == 2:
         return nn.ModuleList([Linear(in_channels, hidden_channels), Linear(hidden_channels, out_channels)])
-    middle = Linear(hidden_channels, hidden_channels)
-    return nn.ModuleList([Linear(in_channels, hidden_channels)]
-                         + [copy.deepcopy(middle) for _ in range(num_layers - 2)]
-                         + [Linear(hidden_channels, out_channels)])
+    return nn.ModuleList([first] + [copy.deepcopy(middle) for _ in range(num_layers - 2)] + [last])
 
 
 # --------------------------------------------------------------------------------------------
