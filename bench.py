@@ -98,7 +98,8 @@ def lookup_traffic(workload, degree, d, n_gpus, plan):
         return None
     for c in caps:
         if (c["workload"], c["degree"], c["d"], c["n_gpus"]) == (workload, degree, d, n_gpus) and plan is not None and \
-                (c["variant"], c["chunk"], bool(c["degree_order"])) == (plan.get("variant"), plan.get("chunk"), bool(plan.get("degree_order"))):
+                (c["variant"], c["chunk"], bool(c["degree_order"]), int(c.get("hot_rows", 0))) == \
+                (plan.get("variant"), plan.get("chunk"), bool(plan.get("degree_order")), int(plan.get("hot_rows", 0))):
             return c
     return None
 
@@ -479,7 +480,7 @@ def run_ours(args):
     plan = None
     if world == 1:        # the plan the forward launches ran with (autotune's choice, or the env / flag defaults)
         plan = {"variant": g.variant if g.variant is not None else int(os.environ.get("LGB_SPMM_VARIANT", "0")),
-                "chunk": g.chunk, "degree_order": g.row_order is not None}
+                "chunk": g.chunk, "degree_order": g.row_order is not None, "hot_rows": int(getattr(g, "n_hot", 0))}
     cap = lookup_traffic(args.workload, args.degree, d, world, plan)
     traffic = cap["dram_bytes_per_call"] if cap else None
     floor = spmm_floor_bytes(spmm_events[0][2], spmm_events[0][3], d) if spmm_events else None

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 1
+#define LGB_ABI_VERSION 2
 
 enum {
   LGB_OK = 0,
@@ -112,6 +112,13 @@ typedef struct lgb_csr {
   const int32_t* task_row;
   const int32_t* task_start;
   const int32_t* task_end;   /* [n_tasks] exclusive end offset of each slice */
+  /* hot-column plan (optional; LGB_SPMM variant 30): the n_hot most-referenced columns of this matrix are kept in shared
+   * memory by every CTA.  colidx_hot is colidx with a hot column c replaced by ~slot (negative), slot = its position in
+   * hot_cols (descending column degree).  NULL / 0 = no plan. */
+  const int32_t* colidx_hot; /* [nnz] */
+  const int32_t* hot_cols;   /* [n_hot] */
+  int32_t n_hot;
+  int32_t _pad2;
 } lgb_csr;
 
 /* ---------------------------------------------------------------------------------------------

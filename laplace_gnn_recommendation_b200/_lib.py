@@ -26,6 +26,7 @@ class LgbCsr(C.Structure):
         ("chunk", c_i32), ("_pad", c_i32),
         ("n_long", c_i64), ("n_tasks", c_i64),
         ("long_rows", c_vp), ("long_ptr", c_vp), ("task_row", c_vp), ("task_start", c_vp), ("task_end", c_vp),
+        ("colidx_hot", c_vp), ("hot_cols", c_vp), ("n_hot", c_i32), ("_pad2", c_i32),
     ]
 
 
@@ -114,8 +115,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.lgb_abi_version() != 1:
-        raise RuntimeError(f"liblaplace_b200.so ABI {lib.lgb_abi_version()} != 1")
+    if lib.lgb_abi_version() != 2:
+        raise RuntimeError(f"liblaplace_b200.so ABI {lib.lgb_abi_version()} != 2")
     _lib = lib
     return lib
 

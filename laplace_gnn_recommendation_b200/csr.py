@@ -27,6 +27,9 @@ DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
 # the warp-per-row kernel it replaced, the sub-warp kernel at gather-unroll 4, and the four-rows-per-warp forms (20, 22: d in 33..64;
 # 23, 25: with 256-bit loads, d = 64; other widths run the default under those numbers)
 AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13, 20, 22, 23, 25)
+# the hot-column-cache kernels (variants 30 / 31, d in {32, 64}) with the number of operand rows their plan keeps in shared
+# memory (64 KB x two CTAs per SM, 128 / 192 KB x one CTA per SM at d = 64); tried on top of the list above
+HOT_CANDIDATES = ((30, 256), (31, 512), (31, 768))
 
 
 def _time_ms(fn, reps: int, device) -> float:
@@ -70,6 +73,9 @@ class DeviceCSR:
         self._t: Optional["DeviceCSR"] = None
         self._partials: Dict[tuple, torch.Tensor] = {}
         self._struct: Optional[LgbCsr] = None
+        self.n_hot = 0                                  # hot-column plan (variants 30 / 31): see set_hot()
+        self.hot_cols: Optional[torch.Tensor] = None
+        self.colidx_hot: Optional[torch.Tensor] = None
         self.variant: Optional[int] = None             # kernel variant chosen by autotune() for THIS graph (None: the default)
         self.autotune_report: Optional[dict] = None
         if self.chunk > 0:
@@ -154,7 +160,7 @@ class DeviceCSR:
 
     # ---- plan-time kernel selection --------------------------------------------------------
     def autotune(self, d: int, candidates=None, reps: int = 5, fused_epilogue: bool = True, chunks=None,
-                 degree_orders=(False,)) -> int:
+                 degree_orders=(False,), hot=None) -> int:
         """Pick the fastest lgb_spmm configuration for THIS graph and width on THIS device (one-off, like an FFT plan):
         kernel variant x slice size of the long-row plan (``chunks``, default: the current one) x row processing order
         (``degree_orders``).  Every configuration is first checked against the first one's result on random data (one that
@@ -163,6 +169,10 @@ class DeviceCSR:
         ``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
         if candidates is None:
             candidates = AUTOTUNE_CANDIDATES if d % 4 == 0 and d <= 64 else ((0, 26, 27) if d == 128 else (0,))
+            if hot is None and d in (32, 64):
+                hot = tuple((v, h * 64 // d) for v, h in HOT_CANDIDATES)
+        # every candidate is a (variant, rows of the hot-column plan) pair; 0 rows = no plan
+        candidates = [(v, 0) for v in candidates] + [(int(v), int(h)) for v, h in (hot or ())]
         chunks = tuple(chunks) if chunks else (self.chunk,)
         if self.chunk <= 0:
             chunks = (self.chunk,)
@@ -170,7 +180,8 @@ class DeviceCSR:
         report = {"d": d, "ms": {}, "rejected": {}}
         n_configs = len(candidates) * len(chunks) * len(degree_orders)
         if self.n_rows == 0 or self.nnz == 0 or n_configs <= 1:
-            self.variant = candidates[0] if candidates else None
+            self.variant = candidates[0][0] if candidates else None
+            self.set_hot(candidates[0][1] if candidates else 0)
             report["chosen"] = {"variant": self.variant, "chunk": self.chunk, "degree_order": self.row_order is not None}
             self.autotune_report = report
             return self.variant
@@ -185,9 +196,11 @@ class DeviceCSR:
             self._set_chunk(chunk)
             for order in degree_orders:
                 self.use_degree_order(bool(order))
-                for v in candidates:
-                    key = f"v{v}" + (f"/chunk{chunk}" if len(chunks) > 1 else "") + ("/degree-order" if order else "")
+                for cand in candidates:
+                    v, n_hot = cand
+                    key = f"v{v}" + (f"h{n_hot}" if n_hot else "") + (f"/chunk{chunk}" if len(chunks) > 1 else "") + ("/degree-order" if order else "")
                     try:
+                        self.set_hot(n_hot)
                         run = (lambda: self.spmm(X, Y=Y, acc_in=acc, acc_out=out, variant=v)) if fused_epilogue else (lambda: self.spmm(X, Y=Y, variant=v))   # noqa: E731
                         run()
                         if ref is None:
@@ -204,11 +217,14 @@ class DeviceCSR:
                         continue
                     report["ms"][key] = ms
                     if ms < best_ms:
-                        best, best_ms = (chunk, bool(order), v), ms
+                        best, best_ms = (chunk, bool(order), cand), ms
         self._set_chunk(best[0])
         self.use_degree_order(best[1])
-        self.variant, self.autotune_report = best[2], report
-        report["chosen"] = {"variant": best[2], "chunk": best[0], "degree_order": best[1]}
+        self.set_hot(best[2][1])
+        self.variant, self.autotune_report = best[2][0], report
+        report["chosen"] = {"variant": best[2][0], "chunk": best[0], "degree_order": best[1]}
+        if best[2][1]:
+            report["chosen"].update(hot_rows=best[2][1], hot_share=round(getattr(self, "hot_share", 0.0), 4))
         return self.variant
 
     def _set_chunk(self, chunk: int) -> None:
@@ -220,6 +236,29 @@ class DeviceCSR:
             if self.chunk > 0:
                 self._build_plan()
             self._struct = None
+
+    def set_hot(self, n_hot: int) -> "DeviceCSR":
+        """Build (or drop, n_hot = 0) the hot-column plan of variants 30 / 31: the n_hot most-referenced columns of THIS matrix
+        (by column degree over its own entries) and a copy of colidx in which such a column c appears as ~slot.  Plan-time
+        work (torch ops: bincount, topk, one gather); the hot path only reads the two arrays."""
+        n_hot = int(min(max(n_hot, 0), self.n_cols))
+        if n_hot == self.n_hot and (n_hot == 0 or self.colidx_hot is not None):
+            return self
+        self.n_hot, self.hot_cols, self.colidx_hot, self._struct = 0, None, None, None
+        if n_hot == 0 or self.nnz == 0:
+            return self
+        lo, hi = int(self.rowptr[0]), int(self.rowptr[-1])          # a row view shares colidx with its parent: its own range only
+        cols = self.colidx[lo:hi].long()
+        deg = torch.bincount(cols, minlength=self.n_cols)
+        hot = torch.topk(deg, n_hot).indices
+        slot = torch.full((self.n_cols,), -1, dtype=torch.int64, device=self.device)
+        slot[hot] = torch.arange(n_hot, device=self.device)
+        sl = slot[cols]
+        colh = self.colidx.clone()
+        colh[lo:hi] = torch.where(sl >= 0, -sl - 1, cols).to(torch.int32)
+        self.n_hot, self.hot_cols, self.colidx_hot = n_hot, hot.to(torch.int32).contiguous(), colh
+        self.hot_share = float(deg[hot].sum()) / max(hi - lo, 1)     # fraction of the entries served from shared memory
+        return self
 
     def with_values(self, val: Optional[torch.Tensor]) -> "DeviceCSR":
         """Same structure (arrays and plan shared), different values."""
@@ -284,6 +323,7 @@ class DeviceCSR:
             s.n_long, s.n_tasks = self.n_long, self.n_tasks
             s.long_rows, s.long_ptr = ptr(self.long_rows), ptr(self.long_ptr)
             s.task_row, s.task_start, s.task_end = ptr(self.task_row), ptr(self.task_start), ptr(self.task_end)
+            s.colidx_hot, s.hot_cols, s.n_hot = ptr(self.colidx_hot), ptr(self.hot_cols), int(self.n_hot)
             self._struct = s
         return self._struct
 
@@ -318,6 +358,8 @@ class DeviceCSR:
         lib = _lib.load()
         if variant is None:
             variant = SPMM_VARIANT if self.variant is None else self.variant
+        if variant in (30, 31) and self.n_hot == 0 and os.environ.get("LGB_SPMM_HOT"):
+            self.set_hot(int(os.environ["LGB_SPMM_HOT"]))      # a variant pinned from the environment brings its plan along
         flags = (1 if mean else 0) | (variant << 4)
         with torch.cuda.device(self.device):
             if y_tail is not None:

@@ -147,6 +147,13 @@ __device__ __forceinline__ void red_add_f4(float4* p, const float4& v) {
                : "memory");
 }
 
+// Base of the dynamic shared memory of the launch (helper so that the CPU emulator can substitute a plain buffer).
+__device__ __forceinline__ float4* dyn_smem_f4() {
+  extern __shared__ float4 lgb_dyn_smem[];
+  asm volatile("" ::: "memory");
+  return lgb_dyn_smem;
+}
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float w, const float4& v) {
   a.x = fmaf(w, v.x, a.x);

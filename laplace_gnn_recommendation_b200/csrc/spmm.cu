@@ -834,6 +834,174 @@ static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
   return LGB_OK;
 }
 
+
+// ---- hot-column cache (variant 30): the H most-referenced operand rows live in shared memory ------------------------------
+// ncu on the shipped kernel (profiles/r2a_*): 10.3 GB cross the L2 -> SM path per launch at an L1 hit rate of 33 %, long
+// scoreboard 26 per issue -- every gathered row pays an L2 (or DRAM) round trip in a dependent chain.  On a power-law graph a
+// handful of columns carries most of the non-zeros (H&M shape: the 256 most popular items are referenced by 65 % of the
+// user-row entries), far more than the L1 keeps alive next to the streamed rows.  Here every CTA first copies the plan's
+// n_hot hottest rows of X into shared memory (64 KB: 256 rows at d = 64, two 1024-thread CTAs per SM; 128 KB: 512 rows, one
+// CTA); the plan's recoded column array marks a hot column with ~slot, and such an entry is served by one LDS.128 instead of
+// an L2 round trip.  CTAs are persistent (the copy is paid once per CTA): warp w of the grid walks the work items
+// w, w + W, ... in the plan's order (slices of long rows first, then row groups) -- the same per-row summation order as the
+// sub-warp kernel, hence bit-identical results.
+constexpr int HOT_THREADS = 1024;
+constexpr int HOT_WARPS = HOT_THREADS / 32;
+
+template <int G, int UNROLL, int D4C>
+__device__ __forceinline__ float4 gather_hot(const float4* __restrict__ X4, const float4* hot, int cc, int lig) {
+  return cc < 0 ? hot[(~cc) * D4C + lig] : ld_gather_f4(X4 + ((uint32_t)cc * (uint32_t)D4C + (uint32_t)lig));
+}
+
+template <int G, int UNROLL, int D4C>
+__device__ __forceinline__ void accumulate_slice_hot(const SpmmParams& p, const int32_t* __restrict__ colh, const float4* hot, int s,
+                                                     int e, int lane, float4& acc) {
+  constexpr int NG = 32 / G;
+  static_assert(32 % (NG * UNROLL) == 0, "a batch of 32 entries must be a whole number of unrolled steps");
+  const int grp = lane / G, lig = lane % G;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  for (int base = s; base < e; base += 32) {
+    const int idx = base + lane;
+    int c = 0;
+    float w = 0.f;
+    if (idx < e) {
+      c = ld_stream_i32(colh + idx);
+      w = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+    }
+    const int cnt = min(32, e - base);
+    for (int j = 0; j < cnt; j += NG * UNROLL) {
+      float4 v[UNROLL];
+      float ww[UNROLL];
+      bool ok[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int k = j + u * NG + grp;
+        const int cc = __shfl_sync(FULL_MASK, c, k);
+        ww[u] = __shfl_sync(FULL_MASK, w, k);
+        ok[u] = k < cnt;
+        if (ok[u]) v[u] = gather_hot<G, UNROLL, D4C>(X4, hot, cc, lig);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (ok[u]) f4_fma(acc, ww[u], v[u]);
+    }
+  }
+#pragma unroll
+  for (int off = G; off < 32; off <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, off));
+}
+
+template <int G, int UNROLL, int D4C, int MINB>
+__global__ void __launch_bounds__(HOT_THREADS, MINB) spmm_hot_kernel(const SpmmParams p, const int32_t* __restrict__ colh,
+                                                                    const int32_t* __restrict__ hot_cols, int n_hot) {
+  static_assert(D4C == G, "one float4 per lane of the group");
+  constexpr int NG = 32 / G;
+  float4* hot = dyn_smem_f4();
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(p.X);
+  for (int i = threadIdx.x; i < n_hot * D4C; i += HOT_THREADS)
+    hot[i] = ld_gather_f4(X4 + ((size_t)hot_cols[i / D4C] * D4C + (i % D4C)));
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / G, lig = lane % G;
+  // 32-bit work-item arithmetic (the launcher checks that the item count fits): keeps the persistent loop inside the register budget
+  const int n_tasks = (int)p.n_tasks, n_rows = (int)p.n_rows;
+  const int total = n_tasks + (n_rows + NG - 1) / NG;
+  const int W = (int)gridDim.x * HOT_WARPS;
+  // consecutive work items go to different CTAs (the plan orders them by decreasing size)
+  for (int w = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x; w < total; w += W) {
+    if (w < n_tasks) {   // a slice of a long row: whole warp, partial sums
+      float4 acc = f4_zero();
+      accumulate_slice_hot<G, UNROLL, D4C>(p, colh, hot, p.task_start[w], p.task_end[w], lane, acc);
+      if (lane < G) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * D4C + lane, acc);
+      continue;
+    }
+    const int ri = (w - n_tasks) * NG + grp;      // every lane group fetches the bounds of its own row
+    int r = -1, s = 0, e = 0;
+    if (ri < n_rows) {
+      r = p.row_order ? p.row_order[ri] : (int)ri;
+      s = p.rowptr[r];
+      e = p.rowptr[r + 1];
+    }
+    int deg = e - s;
+    const bool is_long = p.chunk > 0 && deg > p.chunk;   // handled by its slices + stage 2
+    if (is_long) deg = 0;
+    if (__all_sync(FULL_MASK, deg <= SUBW_MAX)) {
+      int maxdeg = deg;
+#pragma unroll
+      for (int off = G; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL_MASK, maxdeg, off));
+      float4 acc[1] = {f4_zero()};
+      for (int base = 0; base < maxdeg; base += G) {
+        int c = 0;
+        float wv = 0.f;
+        if (base + lig < deg) {
+          c = ld_stream_i32(colh + s + base + lig);
+          wv = p.val ? ld_stream_f32(p.val + s + base + lig) : 1.f;
+        }
+        const int cnt = min(G, deg - base);
+        const int cntmax = min(G, maxdeg - base);
+        for (int j = 0; j < cntmax; j += UNROLL) {
+          float4 v[UNROLL];
+          float ww[UNROLL];
+          bool ok[UNROLL];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            const int k = j + u;
+            const int cc = __shfl_sync(FULL_MASK, c, k, G);
+            ww[u] = __shfl_sync(FULL_MASK, wv, k, G);
+            ok[u] = k < cnt;
+            if (ok[u]) v[u] = gather_hot<G, UNROLL, D4C>(X4, hot, cc, lig);
+          }
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u)
+            if (ok[u]) f4_fma(acc[0], ww[u], v[u]);
+        }
+      }
+      if (r >= 0 && !is_long) epilogue_row<G, 1>(p, r, e - s, lig, acc);
+      continue;
+    }
+    // mixed / longer rows: the whole warp walks the NG rows one after the other
+#pragma unroll 1
+    for (int g2 = 0; g2 < NG; ++g2) {
+      const int rr = __shfl_sync(FULL_MASK, r, g2 * G);
+      const int ss = __shfl_sync(FULL_MASK, s, g2 * G);
+      const int ee = __shfl_sync(FULL_MASK, e, g2 * G);
+      if (rr < 0 || (p.chunk > 0 && ee - ss > p.chunk)) continue;
+      float4 acc[1] = {f4_zero()};
+      accumulate_slice_hot<G, UNROLL, D4C>(p, colh, hot, ss, ee, lane, acc[0]);
+      if (lane < G) epilogue_row<G, 1>(p, rr, ee - ss, lane, acc);
+    }
+  }
+}
+
+// MINB = 2: two 1024-thread CTAs per SM (32 registers per thread, 64 resident warps, <= 100 KB of hot rows each);
+// MINB = 1: one CTA per SM (up to 64 registers, 32 resident warps, up to 200 KB of hot rows).
+template <int G, int UNROLL, int MINB>
+static int launch_hot(const SpmmParams& p, const lgb_csr* g, cudaStream_t stream) {
+  constexpr int NG = 32 / G;
+  const size_t smem = (size_t)g->n_hot * G * sizeof(float4);
+  const size_t cap = (MINB == 2 ? 100 : 200) * 1024;
+  LGB_REQUIRE(smem <= cap, LGB_EINVAL, "lgb_spmm: hot plan of %d rows needs %zu bytes of shared memory (this variant holds %zu)",
+              (int)g->n_hot, smem, cap);
+  static bool configured = false;
+  if (!configured) {
+    LGB_CUDA(cudaFuncSetAttribute(spmm_hot_kernel<G, UNROLL, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    configured = true;
+  }
+  const int64_t total = p.n_tasks + (p.n_rows + NG - 1) / NG;
+  LGB_REQUIRE(total < (1ll << 31) - (1 << 20), LGB_ERANGE, "lgb_spmm: too many work items for the hot-column kernel");
+  if (total > 0) {
+    const int64_t resident = (int64_t)sm_count() * MINB;
+    const int64_t blocks = std::min<int64_t>(resident, (total + HOT_WARPS - 1) / HOT_WARPS);
+    spmm_hot_kernel<G, UNROLL, G, MINB><<<(unsigned)blocks, HOT_THREADS, smem, stream>>>(p, g->colidx_hot, g->hot_cols, g->n_hot);
+    LGB_LAUNCH_CHECK();
+  }
+  if (p.n_long > 0) {
+    spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    LGB_LAUNCH_CHECK();
+  }
+  return LGB_OK;
+}
+
 // ---- segment max (PyG aggr="max") ----------------------------------------------------------
 __global__ void segment_max_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                                    const float* __restrict__ X, int64_t n_rows, int d, float* __restrict__ Y,
@@ -1011,6 +1179,13 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
     if (d4 <= 128) return launch_vec<32, 4, 1, 8, size_t>(p, 1, stream);
     set_error("lgb_spmm: d=%d > 512 not supported", d);
     return LGB_EINVAL;
+  }
+  if (variant == 30 || variant == 31) {   // hot-column cache: needs the plan's recoded column array and an exact one-float4-per-lane width
+    if (g->colidx_hot && g->hot_cols && g->n_hot > 0 && (d4 == 8 || d4 == 16) && !y_tail) {
+      if (variant == 30) return d4 == 8 ? launch_hot<8, 1, 2>(p, g, stream) : launch_hot<16, 1, 2>(p, g, stream);
+      return d4 == 8 ? launch_hot<8, 2, 1>(p, g, stream) : launch_hot<16, 2, 1>(p, g, stream);
+    }
+    variant = 0;
   }
   if (d4 <= 8) {
     if (variant == 1) return launch_vec<8, 1, 2, 16>(p, 1, stream);

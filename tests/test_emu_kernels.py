@@ -191,8 +191,9 @@ def test_autotune_picks_a_checked_variant(cuda_dev, monkeypatch):
     g = TL.DeviceCSR.from_coo(row, col, 400, 400, chunk=64)
     g = g.with_values(g.gcn_norm()[1])
     best = g.autotune(64)
-    assert best in csr.AUTOTUNE_CANDIDATES and g.variant == best
-    assert set(g.autotune_report["ms"]) == {f"v{v}" for v in csr.AUTOTUNE_CANDIDATES} and not g.autotune_report["rejected"]
+    assert best in csr.AUTOTUNE_CANDIDATES + (30, 31) and g.variant == best
+    assert set(g.autotune_report["ms"]) == {f"v{v}" for v in csr.AUTOTUNE_CANDIDATES} | {f"v{v}h{h}" for v, h in csr.HOT_CANDIDATES} \
+        and not g.autotune_report["rejected"]
     # slice size and row order are plan-time dimensions too; the winner's plan is the one left installed
     g.autotune(64, candidates=(0, 16), chunks=(64, 16), degree_orders=(False, True))
     ch = g.autotune_report["chosen"]
@@ -211,7 +212,7 @@ def test_autotune_picks_a_checked_variant(cuda_dev, monkeypatch):
     r, c, n = TL.lo.wiring_symmetric(ei[0], ei[1], U, I)
     adj = lg_module().SparseTensor(row=r, col=c, sparse_sizes=(n, n))
     fwd, bwd = m.autotune(adj)
-    assert fwd in csr.AUTOTUNE_CANDIDATES and bwd in csr.AUTOTUNE_CANDIDATES
+    assert fwd in csr.AUTOTUNE_CANDIDATES + (30, 31) and bwd in csr.AUTOTUNE_CANDIDATES + (30, 31)
     pb = make_problem(seed=1, U=200, I=60, E=3000, d=64, K=2, B=64)
     eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], 2, pb["users"], pb["items"], cuda_dev, ops=make_emu_ops(), rank=0, world=1)
     assert set(eng.autotune()) == {"users", "items"}
@@ -295,7 +296,7 @@ def test_bench_script_logic_dry_run(cuda_dev, monkeypatch, capsys, workload):
     assert "workload" in line["config"] and math.isfinite(line["loss"])
     if workload == "hm":
         tuned = line["config"]["spmm_variant"]
-        assert "error" not in tuned and tuned["forward"]["variant"] in csr.AUTOTUNE_CANDIDATES and not tuned["rejected"], tuned
+        assert "error" not in tuned and tuned["forward"]["variant"] in csr.AUTOTUNE_CANDIDATES + (30, 31) and not tuned["rejected"], tuned
 
 
 def _bench_rank(rank, world, port, out_dir):

@@ -60,6 +60,21 @@ def test_spmm_kernel_variants_agree(cuda_dev, d, n=5000, nnz=200000):
     for v in range(1, 28):
         for a, b in zip(outs[0], outs[v]):
             close(a, b, rtol=1e-5, atol=1e-5)
+    # variants 30 / 31: the hot-column cache (the plan's hottest operand rows in shared memory, persistent CTAs).  Same per-row
+    # summation order as the default sub-warp kernel => the SAME BITS, for any number of hot rows (none hot ... every column hot)
+    if d in (32, 64):
+        for variant, n_hot in ((30, 1), (30, 256 * 64 // d), (31, 768 * 64 // d), (31, 40), (30, n)):
+            if n_hot * d * 4 > (100 if variant == 30 else 200) * 1024:
+                continue
+            g.set_hot(n_hot)
+            assert g.n_hot == min(n_hot, n) and int((g.colidx_hot < 0).sum()) > 0
+            Y = torch.empty(n, d, device=cuda_dev); acc = torch.empty(n, d, device=cuda_dev)
+            g.spmm(X, Y=Y, resid=R, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
+            got = (Y, acc, g.spmm(X, variant=variant), g.with_values(None).spmm(X, mean=True, variant=variant))
+            for a, b in zip(outs[0], got):
+                assert torch.equal(a, b), (variant, n_hot)
+        g.set_hot(0)
+        close(g.spmm(X, variant=30), outs[0][2])              # without a plan the variant number runs the default kernel
 
 # ------------------------------------------------------------------ evaluation() (run_pipeline_lightgcn.py:20-73)
 def test_evaluation_matches_oracle(cuda_dev):

@@ -5,14 +5,14 @@ import sys
 
 
 def main():
-    v, chunk, order = 0, 1024, 0
+    v, chunk, order, hot = 0, 1024, 0, 0
     try:
         line = [ln for ln in open(sys.argv[1]).read().splitlines() if ln.startswith("{")][-1]
         ch = json.loads(line)["config"]["spmm_variant"]["forward"]
-        v, chunk, order = int(ch["variant"]), int(ch["chunk"]), int(bool(ch["degree_order"]))
+        v, chunk, order, hot = int(ch["variant"]), int(ch["chunk"]), int(bool(ch["degree_order"])), int(ch.get("hot_rows", 0))
     except Exception as exc:       # fall back to the default plan
         print(f"# pick_winner: {exc!r}", file=sys.stderr)
-    print(f"FWD_V={v} FWD_CHUNK={chunk} FWD_ORDER={order}")
+    print(f"FWD_V={v} FWD_CHUNK={chunk} FWD_ORDER={order} FWD_HOT={hot}")
 
 
 if __name__ == "__main__":
