@@ -245,6 +245,17 @@ int lgb_edge_dot_bwd(const float* zu, const float* zi, const int64_t* row, const
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Weight / bias gradient of a Linear layer over many rows and few features -- the AddmmBackward of SAGEConv's
+ * lin_l / lin_r (model/layers.py:9-24) and of the decoder's Linear layers (model/encoder_decoder.py:55-72):
+ *   dW[o, i] = sum_n dY[n, o] * X[n, i]        db[o] = sum_n dY[n, o]   (db may be NULL)
+ * X [N, in], dY [N, out], dW [out, in] row-major fp32.  Split-K over the rows (fp32 FMA, fixed-order reduction of the
+ * partial tiles: deterministic); ws: lgb_linear_wgrad_ws_bytes(N, in, out).
+ * ------------------------------------------------------------------------------------------- */
+int lgb_linear_wgrad_ws_bytes(int64_t N, int32_t in, int32_t out, size_t* bytes_host);
+int lgb_linear_wgrad(const float* X, const float* dY, int64_t N, int32_t in, int32_t out, float* dW, float* db,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Candidate generation -- make_predictions_for_user (utils/metrics_lightgcn.py:125-142) for a block of
  * users: scores = Wu[u] . Wi^T (fp32 FMA, ascending-d order), seen items masked, top-k by (score desc,
  * id asc).  seen CSR (seen_ptr[n_users_total+1], seen_idx) is indexed by user id (NULL = nothing seen).

@@ -85,6 +85,8 @@ PROTOTYPES = {
     "lgb_edge_concat_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "lgb_edge_dot_fwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_edge_dot_bwd": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "lgb_linear_wgrad_ws_bytes": (C.c_int, [c_i64, c_i32, c_i32, C.POINTER(c_sz)]),
+    "lgb_linear_wgrad": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "lgb_topk_exclude": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "lgb_topk_exclude_tiled": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "lgb_neg_reject_mask": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
@@ -136,6 +138,11 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(t: torch.Tensor) -> bool:
+    """True when ``t`` lives where the kernels run (a gate for OPTIONAL fused paths; mandatory paths use require_cuda)."""
+    return bool(t.is_cuda)
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:

@@ -152,6 +152,53 @@ def aggregate(x_src: torch.Tensor, g: DeviceCSR, aggr: str) -> torch.Tensor:
     return _Aggregate.apply(x_src, g, aggr)
 
 
+# --------------------------------------------------------------------------------------------
+# Linear layers with the split-K weight / bias gradient kernel
+# --------------------------------------------------------------------------------------------
+WGRAD_MIN_ROWS = int(os.environ.get("LGB_WGRAD_MIN_ROWS", "512"))     # below this cuBLAS's own backward is as good
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b with torch's forward (cuBLAS) and input gradient, and lgb_linear_wgrad for dW / db: the [out x N] x [N x in]
+    contraction over the 10^4..10^5 node rows of a batch, for which cuBLAS runs four CTAs (csrc/dense.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy, x = _lib.f32c(gy), _lib.f32c(x)
+        gx = gy @ weight if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            N, n_in = x.shape
+            n_out = gy.shape[1]
+            lib = _lib.load()
+            need = C.c_size_t(0)
+            check(lib.lgb_linear_wgrad_ws_bytes(N, n_in, n_out, C.byref(need)), "linear_wgrad_ws_bytes")
+            ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+            gw = torch.empty(n_out, n_in, dtype=torch.float32, device=x.device)
+            gb = torch.empty(n_out, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            with torch.cuda.device(x.device):
+                check(lib.lgb_linear_wgrad(ptr(x), ptr(gy), N, n_in, n_out, ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream()), "linear_wgrad")
+            _lib.count_launch(3 if gb is not None else 2)
+        return gx, gw, gb
+
+
+def linear(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """module(x) for an nn.Linear (or a materialised LazyLinear) whose backward uses the split-K kernel when the batch has
+    enough rows; anything else (lazy parameters, other dtypes, tiny batches) goes through the module itself."""
+    lazy = isinstance(module, nn.LazyLinear) and module.has_uninitialized_params()
+    if (not lazy and isinstance(module, nn.Linear) and x.dim() == 2 and x.dtype == torch.float32 and x.shape[0] >= WGRAD_MIN_ROWS
+            and _lib.on_device(x) and torch.is_grad_enabled() and module.weight.requires_grad):
+        return _LinearFn.apply(x, module.weight, module.bias)
+    return module(x)
+
+
 class SAGEConv(nn.Module):
     """PyG ``SAGEConv(in_channels, out_channels, aggr, normalize=False, bias=True)`` as the reference builds it
     (model/layers.py:9-24): out = lin_l(aggr_j x_j) + lin_r(x_i); lazy input widths (``-1``)."""
@@ -184,9 +231,9 @@ class SAGEConv(nn.Module):
             if self.lin_l.bias is not None:
                 out = out + self.lin_l.bias
         else:
-            out = self.lin_l(aggregate(x_src, graph, self.aggr))
+            out = linear(self.lin_l, aggregate(x_src, graph, self.aggr))
         if self.root_weight and x_dst is not None:
-            out = out + self.lin_r(x_dst)
+            out = out + linear(self.lin_r, x_dst)
         if self.normalize:
             out = F.normalize(out, p=2.0, dim=-1)
         return out
@@ -422,11 +469,11 @@ class EdgeDecoder(nn.Module):
         z = edge_concat(zu, zi, customer_index, article_index)
         for index, layer in enumerate(self.layers):
             if index == len(self.layers) - 1:
-                z = layer(z)
+                z = linear(layer, z)
             else:
                 if self.p_dropout_features is not None:
                     z = F.dropout(z, p=self.p_dropout_features, training=self.training)
-                z = layer(z).relu()
+                z = linear(layer, z).relu()
         return z.view(-1)
 
 

@@ -59,6 +59,7 @@ def emulated():
         _lib.require_cuda: lambda *tensors: None,
         _lib.stream: lambda: None,
         _lib.load: lambda: lib,
+        _lib.on_device: lambda t: True,
     }
     # the modules did `from ._lib import check, ptr, stream`: rebind those names wherever they were imported
     for modname, mod in list(sys.modules.items()):

@@ -54,6 +54,13 @@ test_encoder_decoder_against_reference_golden = TH.test_encoder_decoder_against_
 test_infer_rebatch_matches_oracle = TH.test_infer_rebatch_matches_oracle
 test_decoder_concat_and_dot = TH.test_decoder_concat_and_dot
 test_hetero_fan_in_three_edge_types = TH.test_hetero_fan_in_three_edge_types
+test_model_gradients_same_with_and_without_wgrad_kernel = TH.test_model_gradients_same_with_and_without_wgrad_kernel
+
+
+@pytest.mark.parametrize("N,n_in,n_out", [(1300, 84, 128), (777, 76, 64), (513, 6, 5), (1, 4, 4), (900, 130, 70)])
+def test_linear_wgrad_vs_torch(cuda_dev, N, n_in, n_out):
+    TH.test_linear_wgrad_vs_torch(cuda_dev, N, n_in, n_out)
+
 # full-size property tests (B = 200 003 BPR triples; a 400 k-edge, 84-wide hetero batch): seconds under the emulator
 test_bpr_full_split_size = TL.test_bpr_full_split_size
 test_batch_sized_aggregation_properties = TH.test_batch_sized_aggregation_properties

@@ -164,3 +164,55 @@ def test_batch_sized_aggregation_properties(cuda_dev):
     close(lg.aggregate(x.detach(), g, "mean"), s.detach() / deg, atol=1e-6)
     ref = torch.zeros(nd, Fw, device=cuda_dev).index_add_(0, ei[1], x.detach()[ei[0]])
     close(s, ref, atol=1e-5)
+
+
+# ------------------------------------------------------------------ split-K weight / bias gradient (csrc/dense.cu)
+@pytest.mark.parametrize("N,n_in,n_out", [(5000, 84, 128), (777, 76, 64), (40000, 128, 1), (513, 6, 5), (1, 4, 4), (3000, 130, 70)])
+def test_linear_wgrad_vs_torch(cuda_dev, N, n_in, n_out):
+    """dW = dY^T X, db = column sums of dY against the float64 evaluation: |err| <= 1e-5*|want| + 1e-6*sum|terms| (the same
+    bound as the SpMM: a sum over N rows in fp32), incl. widths that are not multiples of 4 / 64 and ragged row counts."""
+    from laplace_gnn_recommendation_b200 import hetero
+    gen = torch.Generator().manual_seed(N + n_in)
+    X, dY = torch.randn(N, n_in, generator=gen), torch.randn(N, n_out, generator=gen)
+    lin = torch.nn.Linear(n_in, n_out).to(cuda_dev)
+    x = X.to(cuda_dev).requires_grad_(True)
+    y = hetero._LinearFn.apply(x, lin.weight, lin.bias)
+    torch.testing.assert_close(y.detach().cpu(), torch.nn.functional.linear(X, lin.weight.detach().cpu(), lin.bias.detach().cpu()), rtol=1e-5, atol=1e-5)
+    y.backward(dY.to(cuda_dev))
+    want_w, want_b = dY.double().t() @ X.double(), dY.double().sum(0)
+    mag_w, mag_b = dY.double().abs().t() @ X.double().abs(), dY.double().abs().sum(0)
+    for got, want, mag in ((lin.weight.grad, want_w, mag_w), (lin.bias.grad, want_b, mag_b)):
+        err = (got.detach().cpu().double() - want).abs()
+        assert bool((err <= 1e-5 * want.abs() + 1e-6 * mag + 1e-30).all()), float((err - 1e-5 * want.abs() - 1e-6 * mag).max())
+    torch.testing.assert_close(x.grad.cpu(), dY @ lin.weight.detach().cpu(), rtol=1e-4, atol=1e-4)
+
+
+def test_model_gradients_same_with_and_without_wgrad_kernel(cuda_dev, monkeypatch):
+    """The ranking model on a batch large enough for the split-K path: loss and every parameter gradient agree with the plain
+    nn.Linear backward (rtol 1e-5 of the gradient's magnitude)."""
+    from laplace_gnn_recommendation_b200 import hetero
+    gen = torch.Generator().manual_seed(2)
+    Nc, Na, E, L = 700, 900, 6000, 800
+    x = {"customer": torch.randn(Nc, 20, generator=gen).to(cuda_dev), "article": torch.randn(Na, 12, generator=gen).to(cuda_dev)}
+    e = torch.stack([torch.randint(0, Nc, (E,), generator=gen), torch.randint(0, Na, (E,), generator=gen)]).to(cuda_dev)
+    ei = {hetero.EDGE_KEY: e, hetero.REV_EDGE_KEY: e.flip(0).contiguous()}
+    eli = torch.stack([torch.randint(0, Nc, (L,), generator=gen), torch.randint(0, Na, (L,), generator=gen)]).to(cuda_dev)
+    y = (torch.rand(L, generator=gen) > 0.7).float().to(cuda_dev)
+    metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
+    grads = {}
+    for rows in (512, 10 ** 9):                       # fused backward on / off
+        monkeypatch.setattr(hetero, "WGRAD_MIN_ROWS", rows)
+        torch.manual_seed(0)
+        model = lg.Encoder_Decoder_Model(encoder_layers=lg.get_SAGEConv_layers(2, 32, 16, "mean"), decoder_layers=lg.get_linear_layers(2, 32, 32, 1),
+                                         feature_info={}, metadata=metadata, embedding=False, heterogeneous_prop_agg_type="sum",
+                                         batch_normalize=True, p_dropout_edges=None, p_dropout_features=None).to(cuda_dev)
+        model.initialize_encoder_input_size(type("B", (), {"x_dict": dict(x), "edge_index_dict": ei})())
+        loss = torch.nn.BCEWithLogitsLoss()(model(dict(x), ei, eli), y)
+        loss.backward()
+        grads[rows] = (loss.detach(), {k: p.grad.clone() for k, p in model.named_parameters()})
+    hetero.flush_deferred_checks()
+    (la, ga), (lb, gb) = grads[512], grads[10 ** 9]
+    torch.testing.assert_close(la, lb, rtol=1e-6, atol=1e-7)
+    for k in ga:
+        # (a bias in front of the batch norm has a zero gradient: both backward passes return rounding noise there, hence the floor)
+        torch.testing.assert_close(ga[k], gb[k], rtol=1e-4, atol=1e-5 * float(gb[k].abs().max()) + 1e-7, msg=lambda m: f"{k}: {m}")
