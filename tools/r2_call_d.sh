@@ -27,7 +27,9 @@ echo "[rc=$?] ncu winner captures" >> $O/d_status.log
 unset LGB_SPMM_VARIANT LGB_SPMM_CHUNK LGB_SPMM_HOT
 LGB_SPMM_HOT=256 T 400 python tools/shard_probe.py --world 8 --ranks 0 --variants 0,30 --chunks 1024,256 > $O/d_shard_probe8_h256.log 2>&1
 LGB_SPMM_HOT=512 T 400 python tools/shard_probe.py --world 8 --ranks 0 --variants 31 --chunks 256 > $O/d_shard_probe8_h512.log 2>&1
-for hs in hetero_m hetero_l; do
+for hs in hetero_s hetero_m hetero_l; do
   T 200 python bench.py --workload $hs --steps 20 --warmup 5 --no-cpu-baseline > $O/d_bench_$hs.json 2> $O/d_bench_$hs.err
+  LGB_WGRAD_MIN_ROWS=1000000000 T 200 python bench.py --workload $hs --steps 20 --warmup 5 --no-cpu-baseline > $O/d_bench_${hs}_cublas_wgrad.json 2> $O/d_bench_${hs}_cublas_wgrad.err
 done
+T 200 python tools/hetero_profile.py --workload hetero_l > $O/d_hetero_profile_l.log 2>&1
 cat $O/d_status.log
