@@ -133,7 +133,9 @@ typedef struct lgb_csr {
  *   if (Y)        Y[r,:]       = y
  *   if (acc_out)  acc_out[r,:] = ((acc_in ? acc_in[r,:] : 0) + y) / acc_div
  *
- * X/Y/resid/acc_* are [n, d] row-major.  partial_ws must hold n_tasks*d floats when g->n_tasks > 0.
+ * X/Y/resid/acc_* are [n, d] row-major.  partial_ws must hold n_tasks*d floats when g->n_tasks > 0; the hot-column
+ * variants (30 / 31) need n_tasks*d + 64 floats whose last 64 are ZERO before the first launch (their work counters; every
+ * launch leaves them zero) and a buffer that no concurrent launch shares.
  * ------------------------------------------------------------------------------------------- */
 #define LGB_SPMM_MEAN 1
 /* bits 4..11 of flags pick a kernel variant for A/B measurements (all of them for d in 33..64; 0, 1 and 16 for d <= 32):

@@ -330,12 +330,14 @@ class DeviceCSR:
     def _partial_ws(self, d: int) -> Optional[torch.Tensor]:
         """Partial-sum scratch of the long-row slices: one per (width, STREAM) -- the sharded engine runs the same graph on two
         streams at once (layer k of one chain next to layer k+1 of the other), and launches that overlap must not share it."""
-        if self.n_tasks == 0:
+        if self.n_tasks == 0 and self.n_hot == 0:
             return None
-        key = (d, torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0)
+        key = (d, self.n_tasks, torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0)
         buf = self._partials.get(key)
-        if buf is None or buf.numel() < self.n_tasks * d:
-            buf = torch.empty(self.n_tasks * d, dtype=torch.float32, device=self.device)
+        if buf is None:
+            # + 64 floats behind the partial sums: the work counters of the hot-column kernels (variants 30 / 31), which must
+            # start at zero and are left at zero by every launch
+            buf = torch.zeros(self.n_tasks * d + 64, dtype=torch.float32, device=self.device)
             self._partials[key] = buf
         return buf
 

@@ -847,6 +847,8 @@ static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
 // sub-warp kernel, hence bit-identical results.
 constexpr int HOT_THREADS = 1024;
 constexpr int HOT_WARPS = HOT_THREADS / 32;
+constexpr int HOT_GRAB = 8;        // row groups a warp takes per visit of the work counter
+constexpr int HOT_CTR_FLOATS = 64; // the work counters live in 64 floats behind the n_tasks * d partial sums (caller-zeroed once)
 
 template <int G, int UNROLL, int D4C>
 __device__ __forceinline__ float4 gather_hot(const float4* __restrict__ X4, const float4* hot, int cc, int lig) {
@@ -905,70 +907,93 @@ __global__ void __launch_bounds__(HOT_THREADS, MINB) spmm_hot_kernel(const SpmmP
   const int grp = lane / G, lig = lane % G;
   // 32-bit work-item arithmetic (the launcher checks that the item count fits): keeps the persistent loop inside the register budget
   const int n_tasks = (int)p.n_tasks, n_rows = (int)p.n_rows;
-  const int total = n_tasks + (n_rows + NG - 1) / NG;
-  const int W = (int)gridDim.x * HOT_WARPS;
-  // consecutive work items go to different CTAs (the plan orders them by decreasing size)
-  for (int w = (int)(threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x; w < total; w += W) {
-    if (w < n_tasks) {   // a slice of a long row: whole warp, partial sums
-      float4 acc = f4_zero();
-      accumulate_slice_hot<G, UNROLL, D4C>(p, colh, hot, p.task_start[w], p.task_end[w], lane, acc);
-      if (lane < G) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * D4C + lane, acc);
-      continue;
-    }
-    const int ri = (w - n_tasks) * NG + grp;      // every lane group fetches the bounds of its own row
-    int r = -1, s = 0, e = 0;
-    if (ri < n_rows) {
-      r = p.row_order ? p.row_order[ri] : (int)ri;
-      s = p.rowptr[r];
-      e = p.rowptr[r + 1];
-    }
-    int deg = e - s;
-    const bool is_long = p.chunk > 0 && deg > p.chunk;   // handled by its slices + stage 2
-    if (is_long) deg = 0;
-    if (__all_sync(FULL_MASK, deg <= SUBW_MAX)) {
-      int maxdeg = deg;
-#pragma unroll
-      for (int off = G; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL_MASK, maxdeg, off));
-      float4 acc[1] = {f4_zero()};
-      for (int base = 0; base < maxdeg; base += G) {
-        int c = 0;
-        float wv = 0.f;
-        if (base + lig < deg) {
-          c = ld_stream_i32(colh + s + base + lig);
-          wv = p.val ? ld_stream_f32(p.val + s + base + lig) : 1.f;
-        }
-        const int cnt = min(G, deg - base);
-        const int cntmax = min(G, maxdeg - base);
-        for (int j = 0; j < cntmax; j += UNROLL) {
-          float4 v[UNROLL];
-          float ww[UNROLL];
-          bool ok[UNROLL];
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u) {
-            const int k = j + u;
-            const int cc = __shfl_sync(FULL_MASK, c, k, G);
-            ww[u] = __shfl_sync(FULL_MASK, wv, k, G);
-            ok[u] = k < cnt;
-            if (ok[u]) v[u] = gather_hot<G, UNROLL, D4C>(X4, hot, cc, lig);
-          }
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u)
-            if (ok[u]) f4_fma(acc[0], ww[u], v[u]);
-        }
-      }
-      if (r >= 0 && !is_long) epilogue_row<G, 1>(p, r, e - s, lig, acc);
-      continue;
-    }
-    // mixed / longer rows: the whole warp walks the NG rows one after the other
+  const int row_items = (n_rows + NG - 1) / NG;
+  // Dynamic work distribution (a static round-robin over persistent warps loses 1.5x on a power-law graph: the warp that
+  // draws a 1000-entry row still has its whole share of other rows to walk).  Two global counters behind the partial-sum
+  // scratch: slices are taken one at a time, row groups HOT_GRAB at a time; the last CTA to finish resets them, so a launch
+  // leaves them zero for the next one on the same scratch buffer.
+  int* ctr = reinterpret_cast<int*>(p.partial + (size_t)n_tasks * (D4C * 4));
+  for (;;) {          // ---- phase 1: slices of long rows (whole warp, partial sums) ----
+    int w = 0;
+    if (lane == 0) w = n_tasks > 0 ? atomicAdd(ctr, 1) : 0;
+    w = __shfl_sync(FULL_MASK, w, 0);
+    if (w >= n_tasks) break;
+    float4 acc = f4_zero();
+    accumulate_slice_hot<G, UNROLL, D4C>(p, colh, hot, p.task_start[w], p.task_end[w], lane, acc);
+    if (lane < G) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * D4C + lane, acc);
+  }
+  for (;;) {          // ---- phase 2: row groups ----
+    int base = 0;
+    if (lane == 0) base = atomicAdd(ctr + 1, HOT_GRAB);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (base >= row_items) break;
+    const int last = min(base + HOT_GRAB, row_items);
 #pragma unroll 1
-    for (int g2 = 0; g2 < NG; ++g2) {
-      const int rr = __shfl_sync(FULL_MASK, r, g2 * G);
-      const int ss = __shfl_sync(FULL_MASK, s, g2 * G);
-      const int ee = __shfl_sync(FULL_MASK, e, g2 * G);
-      if (rr < 0 || (p.chunk > 0 && ee - ss > p.chunk)) continue;
-      float4 acc[1] = {f4_zero()};
-      accumulate_slice_hot<G, UNROLL, D4C>(p, colh, hot, ss, ee, lane, acc[0]);
-      if (lane < G) epilogue_row<G, 1>(p, rr, ee - ss, lane, acc);
+    for (int it = base; it < last; ++it) {
+      const int ri = it * NG + grp;      // every lane group fetches the bounds of its own row
+      int r = -1, s = 0, e = 0;
+      if (ri < n_rows) {
+        r = p.row_order ? p.row_order[ri] : ri;
+        s = p.rowptr[r];
+        e = p.rowptr[r + 1];
+      }
+      int deg = e - s;
+      const bool is_long = p.chunk > 0 && deg > p.chunk;   // handled by its slices + stage 2
+      if (is_long) deg = 0;
+      if (__all_sync(FULL_MASK, deg <= SUBW_MAX)) {
+        int maxdeg = deg;
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) maxdeg = max(maxdeg, __shfl_xor_sync(FULL_MASK, maxdeg, off));
+        float4 acc[1] = {f4_zero()};
+        for (int b0 = 0; b0 < maxdeg; b0 += G) {
+          int c = 0;
+          float wv = 0.f;
+          if (b0 + lig < deg) {
+            c = ld_stream_i32(colh + s + b0 + lig);
+            wv = p.val ? ld_stream_f32(p.val + s + b0 + lig) : 1.f;
+          }
+          const int cnt = min(G, deg - b0);
+          const int cntmax = min(G, maxdeg - b0);
+          for (int j = 0; j < cntmax; j += UNROLL) {
+            float4 v[UNROLL];
+            float ww[UNROLL];
+            bool ok[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+              const int k = j + u;
+              const int cc = __shfl_sync(FULL_MASK, c, k, G);
+              ww[u] = __shfl_sync(FULL_MASK, wv, k, G);
+              ok[u] = k < cnt;
+              if (ok[u]) v[u] = gather_hot<G, UNROLL, D4C>(X4, hot, cc, lig);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+              if (ok[u]) f4_fma(acc[0], ww[u], v[u]);
+          }
+        }
+        if (r >= 0 && !is_long) epilogue_row<G, 1>(p, r, e - s, lig, acc);
+        continue;
+      }
+      // mixed / longer rows: the whole warp walks the NG rows one after the other
+#pragma unroll 1
+      for (int g2 = 0; g2 < NG; ++g2) {
+        const int rr = __shfl_sync(FULL_MASK, r, g2 * G);
+        const int ss = __shfl_sync(FULL_MASK, s, g2 * G);
+        const int ee = __shfl_sync(FULL_MASK, e, g2 * G);
+        if (rr < 0 || (p.chunk > 0 && ee - ss > p.chunk)) continue;
+        float4 acc[1] = {f4_zero()};
+        accumulate_slice_hot<G, UNROLL, D4C>(p, colh, hot, ss, ee, lane, acc[0]);
+        if (lane < G) epilogue_row<G, 1>(p, rr, ee - ss, lane, acc);
+      }
+    }
+  }
+  // the last CTA to get here puts the counters back to zero (every warp of every CTA has left both loops by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ctr + 2, 1) == (int)gridDim.x - 1) {
+      ctr[0] = 0; ctr[1] = 0; ctr[2] = 0;
+      __threadfence();
     }
   }
 }
@@ -989,6 +1014,8 @@ static int launch_hot(const SpmmParams& p, const lgb_csr* g, cudaStream_t stream
   }
   const int64_t total = p.n_tasks + (p.n_rows + NG - 1) / NG;
   LGB_REQUIRE(total < (1ll << 31) - (1 << 20), LGB_ERANGE, "lgb_spmm: too many work items for the hot-column kernel");
+  LGB_REQUIRE(p.partial, LGB_EINVAL, "lgb_spmm: variants 30 / 31 need partial_ws of n_tasks*d + %d floats, zero before the first launch "
+              "(the work counters live behind the partial sums)", HOT_CTR_FLOATS);
   if (total > 0) {
     const int64_t resident = (int64_t)sm_count() * MINB;
     const int64_t blocks = std::min<int64_t>(resident, (total + HOT_WARPS - 1) / HOT_WARPS);

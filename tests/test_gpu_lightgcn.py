@@ -437,13 +437,14 @@ def test_hm_shape_epoch_against_fp64(cuda_dev):
     A = sp.diags(dinv) @ A @ sp.diags(dinv)
     absA = abs(A)
 
-    def propagate(x0, resid=None):
-        """-> (layer outputs [Horner form when resid is given], sum_k |A|^k |x0|: the magnitude every fp32 rounding of the
-        K chained products is relative to)"""
-        outs, x, m, mag = [x0], x0, np.abs(x0), np.abs(x0)
+    def propagate(x0, resid=None, m0=None):
+        """-> (layer outputs [Horner form when resid is given], sum_k |A|^k m0: the magnitude every fp32 rounding of the
+        K chained products is relative to; m0 = |x0| unless x0 itself is a difference of larger terms)"""
+        m0 = np.abs(x0) if m0 is None else m0
+        outs, x, m, mag = [x0], x0, m0, m0
         for _ in range(K):
             x = A @ x if resid is None else A @ x + resid
-            m = absA @ m if resid is None else absA @ m + np.abs(resid)
+            m = absA @ m if resid is None else absA @ m + m0
             mag = mag + m
             outs.append(x)
         return outs, mag
@@ -465,7 +466,11 @@ def test_hm_shape_epoch_against_fp64(cuda_dev):
     np.add.at(r, pi, (-sig / B)[:, None] * want[ui])
     np.add.at(r, ni, (sig / B)[:, None] * want[ui])
     r /= (K + 1)
-    outs, mag = propagate(r, resid=r)
+    rmag = np.zeros_like(want)                 # r is built from differences of fp32 embedding rows: its rounding is relative to these
+    np.add.at(rmag, ui, (sig / B)[:, None] * (np.abs(want[pi]) + np.abs(want[ni])) / (K + 1))
+    np.add.at(rmag, pi, (sig / B)[:, None] * np.abs(want[ui]) / (K + 1))
+    np.add.at(rmag, ni, (sig / B)[:, None] * np.abs(want[ui]) / (K + 1))
+    outs, mag = propagate(r, resid=r, m0=rmag)
     gwant = outs[-1]
     for idx in (ui, pi, ni):
         np.add.at(gwant, idx, 2 * lam * E0[idx])
