@@ -119,12 +119,21 @@ class ClockSampler:
         self.index, self.lines, self.proc = index, [], None
 
     def start(self):
+        """Launch the sampler and wait for its first line: nvidia-smi's own start-up (process + NVML initialisation, driver
+        locks) must be over BEFORE the timed region -- it perturbs launch-bound steps by milliseconds otherwise."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region."""
+        self.first = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -136,7 +145,8 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        lines = self.lines[max(getattr(self, "first", 0) - 1, 0):]        # the sample that straddles the start counts too
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -408,12 +418,13 @@ def run_ours(args):
             dist.barrier()
         CUDA.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step()
+    sync()
+    clocks.mark()
     DeviceCSR.spmm = timed_spmm
     graphed = bool(graph_report and graph_report.get("used")) or (world == 1 and args.graph == "on")
     if world > 1 and hasattr(eng.ops, "exchange_events") and not graphed:
@@ -688,12 +699,13 @@ def run_hetero(args):
         e0.record(); out = orig(self, *a, **k); e1.record()
         events.append((e0, e1, self.nnz, self.n_rows, a[0].shape[1]))
         return out
-    for _ in range(args.warmup):
-        step()
-    sync()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step()
+    sync()
+    clocks.mark()
     DeviceCSR.spmm = timed
     launches0 = _lib.LAUNCHES
     sync()

@@ -14,7 +14,7 @@ from .csr import DeviceCSR  # noqa: F401
 from .hetero import (EdgeDecoder, Encoder_Decoder_Model, GNNEncoder, HeteroEncoder, SAGEConv, aggregate,  # noqa: F401
                      build_edge_csr, edge_concat, edge_dot, get_linear_layers, get_SAGEConv_layers, to_hetero)
 from .lightgcn import LightGCN  # noqa: F401
-from .loader import (both_indexes_from_zero, make_lightgcn_splits, sample_mini_batch, split,  # noqa: F401
+from .loader import (DeviceSampler, both_indexes_from_zero, make_lightgcn_splits, sample_mini_batch, sample_mini_batch_device, split,  # noqa: F401
                      structured_negative_sampling)
 from .metrics import evaluation, get_metrics_lightgcn, get_metrics_universal, recall_precision_ndcg  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
@@ -23,7 +23,7 @@ from .topk import SeenItems, make_predictions_for_user, recommend_topk, topk_dic
 
 __all__ = [
     "LightGCN", "bpr_loss", "bpr_indexed", "SparseTensor", "matmul", "gcn_norm", "DeviceCSR",
-    "sample_mini_batch", "structured_negative_sampling", "recommend_topk", "make_predictions_for_user",
+    "sample_mini_batch", "sample_mini_batch_device", "DeviceSampler", "structured_negative_sampling", "recommend_topk", "make_predictions_for_user",
     "SeenItems", "topk_dict", "SAGEConv", "to_hetero", "GNNEncoder", "HeteroEncoder", "EdgeDecoder",
     "Encoder_Decoder_Model", "get_SAGEConv_layers", "get_linear_layers", "aggregate", "build_edge_csr",
     "edge_concat", "edge_dot", "both_indexes_from_zero", "split", "make_lightgcn_splits", "evaluation",

@@ -155,7 +155,9 @@ def aggregate(x_src: torch.Tensor, g: DeviceCSR, aggr: str) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # Linear layers with the split-K weight / bias gradient kernel
 # --------------------------------------------------------------------------------------------
-WGRAD_MIN_ROWS = int(os.environ.get("LGB_WGRAD_MIN_ROWS", "512"))     # below this cuBLAS's own backward is as good
+# rows from which the split-K kernel takes over: below it the step is bound by host-side dispatch, not by the 66 us cuBLAS call,
+# and one more Python-level autograd node costs more than the kernel saves (measured on the S / M batches, profiles/README.md)
+WGRAD_MIN_ROWS = int(os.environ.get("LGB_WGRAD_MIN_ROWS", "65536"))
 
 
 class _LinearFn(torch.autograd.Function):

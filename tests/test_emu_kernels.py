@@ -361,6 +361,7 @@ def test_bench_script_logic_dry_run_two_ranks(tmp_path):
     assert par["eager"]["ok"] and par["eager"]["loss_rel_err"] <= 1e-5 and par["eager"]["grad_max_rel_err"] <= 1e-5, par
     assert line["e2e"]["value"] > 0 and line["roofline"]["launches_timed"] > 0 and line["gpu_launches"] > 0
 test_acceptance_lightgcn_learns = TZ.test_acceptance_lightgcn_learns
+test_device_sampler_distribution_and_validity = TZ.test_device_sampler_distribution_and_validity
 test_acceptance_ranking_model_learns = TZ.test_acceptance_ranking_model_learns
 test_reverse_edge_type_shares_the_transposed_csr = TZ.test_reverse_edge_type_shares_the_transposed_csr
 test_topk_tiled_scoring_is_bit_identical = TZ.test_topk_tiled_scoring_is_bit_identical

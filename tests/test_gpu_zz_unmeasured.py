@@ -386,3 +386,26 @@ def test_topk_tiled_scoring_is_bit_identical(cuda_dev, k, I, d, U):
         finally:
             topk._TOPK_AUTO_MIN_USERS = keep
             topk._TOPK_CHOICE.clear()
+
+
+def test_device_sampler_distribution_and_validity(cuda_dev):
+    """DeviceSampler (opt-in O(B) sampler): every triple is a positive edge with a negative that is NOT an edge of the user and
+    lies in [0, max item id); edges are picked (close to) uniformly.  Not bit-identical to the reference by design."""
+    gen = torch.Generator().manual_seed(4)
+    U, I, E = 50, 40, 900
+    ei = torch.stack([torch.randint(0, U, (E,), generator=gen), torch.randint(0, I, (E,), generator=gen)])
+    ei[0, :400] = 3                                        # a heavy user: most of its negatives must be redrawn
+    ei[1, :400] = torch.randint(0, I - 2, (400,), generator=gen)
+    pos = set((int(a), int(b)) for a, b in ei.t().tolist())
+    s = lg.DeviceSampler(ei.to(cuda_dev))
+    num_nodes = int(ei[1].max())
+    seen_edges = set()
+    for _ in range(20):
+        u, p, n = (t.cpu() for t in s.sample(256))
+        assert u.shape == p.shape == n.shape == (256,)
+        for a, b, c in zip(u.tolist(), p.tolist(), n.tolist()):
+            assert (a, b) in pos and (a, c) not in pos and 0 <= c < num_nodes
+            seen_edges.add((a, b))
+    assert len(seen_edges) > 0.7 * len(pos)                # 5120 uniform draws over <= 900 distinct edges
+    u, p, n = lg.sample_mini_batch_device(64, ei.to(cuda_dev))
+    assert all((a, b) in pos and (a, c) not in pos for a, b, c in zip(u.tolist(), p.tolist(), n.tolist()))

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--k", type=int, default=12)
     ap.add_argument("--eval-every", type=int, default=100)
     ap.add_argument("--lr-decay-every", type=int, default=50)
+    ap.add_argument("--sampler", default="reference", choices=["reference", "device"],
+                    help="reference: bit-exact sample_mini_batch (O(E) CPU draws per iteration); device: DeviceSampler (O(B), same distribution)")
     a = ap.parse_args()
     for style in (["reference", "fused"] if a.style == "both" else [a.style]):
         a.style = style
@@ -66,10 +68,14 @@ def run(a):
 
     t_sample = t_step = t_eval = 0.0
     log = []
+    dsampler = lg.DeviceSampler(train_ei) if a.sampler == "device" else None
     for it in range(a.iters):
         t0 = time.perf_counter()
-        u_idx, p_idx, n_idx = lg.sample_mini_batch(a.batch, train_ei)
-        u_idx, p_idx, n_idx = u_idx.to(dev), p_idx.to(dev), n_idx.to(dev)
+        if dsampler is not None:
+            u_idx, p_idx, n_idx = dsampler.sample(a.batch)
+        else:
+            u_idx, p_idx, n_idx = lg.sample_mini_batch(a.batch, train_ei)
+            u_idx, p_idx, n_idx = u_idx.to(dev), p_idx.to(dev), n_idx.to(dev)
         _common.sync(); t1 = time.perf_counter()
         if a.style == "reference":          # run_pipeline_lightgcn.py:120-158, verbatim call sequence
             users_emb_final, users_emb_0, items_emb_final, items_emb_0 = model.forward(train_sp)
@@ -98,7 +104,7 @@ def run(a):
     seen = lg.SeenItems(edge_index.to(dev), num_users, num_items)
     cands = lg.recommend_topk(model.users_emb.weight.detach(), model.items_emb.weight.detach(),
                               torch.arange(min(num_users, 1024), device=dev), min(256, num_items), seen)
-    print(json.dumps({"workload": a.workload if not _common.DRYRUN else "dryrun", "style": a.style, "iters": a.iters,
+    print(json.dumps({"workload": a.workload if not _common.DRYRUN else "dryrun", "style": a.style, "sampler": a.sampler, "iters": a.iters,
                       "iters_per_s": a.iters / max(t_sample + t_step, 1e-9), "sampler_s": t_sample, "step_s": t_step, "eval_s": t_eval,
                       "test": dict(zip(("loss", "recall", "precision", "ndcg"), [round(float(x), 6) for x in test])),
                       "candidates_shape": list(cands.shape), "log": log}), flush=True)
