@@ -28,7 +28,9 @@ DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
 # 23, 25: with 256-bit loads, d = 64; other widths run the default under those numbers)
 AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13, 20, 22, 23, 25)
 # the hot-column-cache kernels (variants 30 / 31, d in {32, 64}) with the number of operand rows their plan keeps in shared
-# memory (64 KB x two CTAs per SM, 128 / 192 KB x one CTA per SM at d = 64); tried on top of the list above
+# memory (64 KB x two CTAs per SM, 128 / 192 KB x one CTA per SM at d = 64).  A/B'd on the B200 in round 2 and 1.3-1.6x SLOWER
+# than the sub-warp kernel on both halves of the H&M graph (the L1 already keeps the hottest rows; persistent 1024-thread CTAs
+# lose the block scheduler's fine-grained balancing): kept as variants, tried by autotune only with LGB_SPMM_TRY_HOT=1 / hot=
 HOT_CANDIDATES = ((30, 256), (31, 512), (31, 768))
 
 
@@ -169,8 +171,8 @@ class DeviceCSR:
         ``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
         if candidates is None:
             candidates = AUTOTUNE_CANDIDATES if d % 4 == 0 and d <= 64 else ((0, 26, 27) if d == 128 else (0,))
-            if hot is None and d in (32, 64):
-                hot = tuple((v, h * 64 // d) for v, h in HOT_CANDIDATES)
+            if hot is None and d in (32, 64) and os.environ.get("LGB_SPMM_TRY_HOT", "0") == "1":
+                hot = tuple((v, h * 64 // d) for v, h in HOT_CANDIDATES)       # measured slower on B200 (profiles/README.md r2d): opt-in
         # every candidate is a (variant, rows of the hot-column plan) pair; 0 rows = no plan
         candidates = [(v, 0) for v in candidates] + [(int(v), int(h)) for v, h in (hot or ())]
         chunks = tuple(chunks) if chunks else (self.chunk,)

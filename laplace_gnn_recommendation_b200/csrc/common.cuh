@@ -154,6 +154,11 @@ __device__ __forceinline__ float4* dyn_smem_f4() {
   return lgb_dyn_smem;
 }
 
+// Scheduling fence for a batch of independent loads: placed after the LAST load of the batch, once per loaded value.  volatile
+// asm statements keep their program order, so every load of the batch is issued before the first use of any of them -- without
+// it ptxas interleaves each load with the add that consumes the previous one and the in-order issue stalls on the first add.
+__device__ __forceinline__ void pin_f4(float4& v) { asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)); }
+
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 __device__ __forceinline__ void f4_fma(float4& a, float w, const float4& v) {
   a.x = fmaf(w, v.x, a.x);

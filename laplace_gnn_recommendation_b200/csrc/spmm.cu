@@ -578,6 +578,12 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   }
 }
 
+// Threads of one stage-2 CTA: 1024 where the per-group staging fits the static shared memory (a long row of a power-law graph
+// has thousands of partial rows: the parallelism that hides their load latency comes from 32 warps, ptxas serialises a
+// deeper per-thread unroll behind the dependent adds), 256 otherwise.
+template <int G, int VPL>
+constexpr int reduce_threads() { return ((1024 / G) * G * VPL * 16 <= 48 * 1024) ? 1024 : 256; }
+
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
@@ -603,7 +609,7 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
-    spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    { constexpr int RT = reduce_threads<G, VPL>(); spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
     LGB_LAUNCH_CHECK();
   }
   return LGB_OK;
@@ -719,7 +725,7 @@ static int launch_async(const SpmmParams& p, cudaStream_t stream) {
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
-    spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    { constexpr int RT = reduce_threads<G, 1>(); spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
     LGB_LAUNCH_CHECK();
   }
   return LGB_OK;
@@ -727,8 +733,8 @@ static int launch_async(const SpmmParams& p, cudaStream_t stream) {
 
 // Stage 2: one CTA per long row sums that row's partials in a fixed order, then runs the epilogue.
 template <int G, int VPL>
-__global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams p) {
-  constexpr int NGRP = 256 / G;
+__global__ void __launch_bounds__(reduce_threads<G, VPL>()) spmm_long_reduce_kernel(const SpmmParams p) {
+  constexpr int NGRP = reduce_threads<G, VPL>() / G;
   __shared__ float4 sm[NGRP][G * VPL];
   const int L = blockIdx.x;
   const int grp = threadIdx.x / G;
@@ -740,7 +746,7 @@ __global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams 
   for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
   // RU independent loads in flight per lane: the heaviest row of a power-law graph has thousands of partial rows, and a loop
   // with one load in flight made this kernel 85 us (7 % of the launch, ncu r2a) -- the order of the additions stays fixed
-  constexpr int RU = 8;
+  constexpr int RU = 4;
   for (int t = t0 + grp; t < t1; t += NGRP * RU) {
     float4 v[RU][VPL];
 #pragma unroll
@@ -752,6 +758,10 @@ __global__ void __launch_bounds__(256) spmm_long_reduce_kernel(const SpmmParams 
         v[u][q] = (tt < t1 && f < p.d4) ? ld_stream_f4(part + (size_t)tt * p.d4 + f) : f4_zero();
       }
     }
+#pragma unroll
+    for (int u = 0; u < RU; ++u)
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) pin_f4(v[u][q]);       // all RU * VPL loads are in flight before the first add
 #pragma unroll
     for (int u = 0; u < RU; ++u)
 #pragma unroll
@@ -828,7 +838,7 @@ static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
-    spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    { constexpr int RT = reduce_threads<G, VPL>(); spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
     LGB_LAUNCH_CHECK();
   }
   return LGB_OK;
@@ -1023,7 +1033,7 @@ static int launch_hot(const SpmmParams& p, const lgb_csr* g, cudaStream_t stream
     LGB_LAUNCH_CHECK();
   }
   if (p.n_long > 0) {
-    spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, 256, 0, stream>>>(p);
+    { constexpr int RT = reduce_threads<G, 1>(); spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
     LGB_LAUNCH_CHECK();
   }
   return LGB_OK;

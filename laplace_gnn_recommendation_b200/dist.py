@@ -469,7 +469,8 @@ class ShardedLightGCN:
     def autotune(self):
         """Per-rank plan-time choice of the SpMM kernel variant / slice size for each view (DeviceCSR.autotune); ranks may
         choose differently -- the item rows are summed by the exchange, so the replicated blocks stay identical."""
-        chunks = (DEFAULT_CHUNK, 256)      # a rank's launch is bounded below by one slice's serial chain: try shorter slices
+        chunks = (2048, DEFAULT_CHUNK, 512, 256)      # a rank's launch is bounded below by one slice's serial chain: try shorter slices
+        # (and longer ones for the CTA-wide-slice variants, which quarter the partial rows of stage 2)
         out = {}
         for name, g in (("users", self.g_users), ("items", self.g_items)):
             g.autotune(self.d, fused_epilogue=False, chunks=chunks)

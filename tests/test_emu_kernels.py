@@ -197,7 +197,7 @@ def test_autotune_picks_a_checked_variant(cuda_dev, monkeypatch):
     row, col = TL.random_graph(3, 400, 400, 12000, skew=True)
     g = TL.DeviceCSR.from_coo(row, col, 400, 400, chunk=64)
     g = g.with_values(g.gcn_norm()[1])
-    best = g.autotune(64)
+    best = g.autotune(64, hot=csr.HOT_CANDIDATES)
     assert best in csr.AUTOTUNE_CANDIDATES + (30, 31) and g.variant == best
     assert set(g.autotune_report["ms"]) == {f"v{v}" for v in csr.AUTOTUNE_CANDIDATES} | {f"v{v}h{h}" for v, h in csr.HOT_CANDIDATES} \
         and not g.autotune_report["rejected"]

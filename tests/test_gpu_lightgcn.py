@@ -475,5 +475,5 @@ def test_hm_shape_epoch_against_fp64(cuda_dev):
     for idx in (ui, pi, ni):
         np.add.at(gwant, idx, 2 * lam * E0[idx])
     gerr = np.abs(G.numpy() - gwant)
-    gbound = 1e-5 * np.abs(gwant) + 1e-6 * mag + 1e-12
+    gbound = 1e-5 * np.abs(gwant) + 1e-6 * mag + 1e-6 * np.abs(gwant).max()      # + 1e-6 of the largest gradient entry
     assert (gerr <= gbound).all(), f"grad: max excess {(gerr - gbound).max():.3e}"
