@@ -164,12 +164,13 @@ class DeviceSampler:
         pick = torch.randint(self.E, (batch_size,), device=dev, generator=g)
         u, p = self.row[pick], self.col[pick]
         n = torch.randint(hi, (batch_size,), device=dev, generator=g)
-        for _ in range(256):                               # P(redraw) = deg(u) / num_nodes per round: a handful of rounds
+        for _ in range(100000):                            # P(redraw) = deg(u) / num_nodes per round: normally a handful of rounds
             mask = _reject_mask(u, n, self.num_nodes, self.keys, True).bool()
             if not bool(mask.any()):
-                break
+                return u, p, n
             n = torch.where(mask, torch.randint(hi, (batch_size,), device=dev, generator=g), n)
-        return u, p, n
+        raise RuntimeError("DeviceSampler: a user of the batch has (almost) every item as a positive -- no negative found "
+                           "(the reference's structured_negative_sampling loops forever on such a user)")
 
 
 def sample_mini_batch_device(batch_size: int, edge_index: torch.Tensor, generator: Optional[torch.Generator] = None):
