@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 2
+#define LGB_ABI_VERSION 3
 
 enum {
   LGB_OK = 0,
@@ -119,6 +119,14 @@ typedef struct lgb_csr {
   const int32_t* hot_cols;   /* [n_hot] */
   int32_t n_hot;
   int32_t _pad2;
+  /* stage-2 tree plan (optional): the partial rows [long_ptr[L], long_ptr[L+1]) of every long row cut into segments of at
+   * most 32; seg_row[s] = L, [seg_t0[s], seg_t1[s]) = its partial rows, row_seg0[L] = first segment of long row L
+   * ([n_long + 1]).  Used when the call passes LGB_SPMM_TREE_WS (scratch sized for it, see lgb_spmm). */
+  const int32_t* seg_row;
+  const int32_t* seg_t0;
+  const int32_t* seg_t1;
+  const int32_t* row_seg0;
+  int64_t n_seg;
 } lgb_csr;
 
 /* ---------------------------------------------------------------------------------------------
@@ -135,9 +143,13 @@ typedef struct lgb_csr {
  *
  * X/Y/resid/acc_* are [n, d] row-major.  partial_ws must hold n_tasks*d floats when g->n_tasks > 0; the hot-column
  * variants (30 / 31) need n_tasks*d + 64 floats whose last 64 are ZERO before the first launch (their work counters; every
- * launch leaves them zero) and a buffer that no concurrent launch shares.
+ * launch leaves them zero) and a buffer that no concurrent launch shares.  With LGB_SPMM_TREE_WS in flags the caller
+ * declares a scratch of n_tasks*d + 64 + n_seg*d + n_long floats, everything behind the first n_tasks*d ZERO before the
+ * first launch: stage 2 then runs as a tree over the plan's segments (one warp per 32 partial rows, self-resetting
+ * tickets) instead of one CTA per long row.
  * ------------------------------------------------------------------------------------------- */
 #define LGB_SPMM_MEAN 1
+#define LGB_SPMM_TREE_WS 2     /* partial_ws is sized and zeroed for the stage-2 tree (see above) */
 /* bits 4..11 of flags pick a kernel variant for A/B measurements (all of them for d in 33..64; 0, 1 and 16 for d <= 32):
  * 0 = tuned default (sub-warp rows: one lane group per short row, 64 resident warps per SM), 1 = first version (warp per
  * row, unroll 8), 2/3 = software-pipelined persistent warps, 4..6, 12 = warp per row at other unroll / occupancy points,
@@ -147,7 +159,8 @@ typedef struct lgb_csr {
  * policy on those streamed loads, 19 = 16 + 18,
  * 20..22 (d in 33..64) = four rows per warp: 8 lanes x 2 float4 per row, with CTA-wide slices (22: + the prefetches of 18),
  * 23..25 (d = 64) = the same with one 256-bit load per lane and non-zero (LDG.E.256), 26/27 (d = 128) = warp per row with
- * 256-bit gathers (16 lanes x 32 bytes per row; unroll 1 at 64 warps/SM, unroll 2 at 40).  Every variant computes the same operator (rtol 1e-5); summation order inside a row differs between families. */
+ * 256-bit gathers (16 lanes x 32 bytes per row; unroll 1 at 64 warps/SM, unroll 2 at 40), 30/31 = hot-column cache (needs
+ * the plan's colidx_hot / hot_cols; two / one persistent 1024-thread CTAs per SM).  Every variant computes the same operator (rtol 1e-5); summation order inside a row differs between families. */
 #define LGB_SPMM_VARIANT_SHIFT 4
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid,
              const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws,

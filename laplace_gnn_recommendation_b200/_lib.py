@@ -27,6 +27,7 @@ class LgbCsr(C.Structure):
         ("n_long", c_i64), ("n_tasks", c_i64),
         ("long_rows", c_vp), ("long_ptr", c_vp), ("task_row", c_vp), ("task_start", c_vp), ("task_end", c_vp),
         ("colidx_hot", c_vp), ("hot_cols", c_vp), ("n_hot", c_i32), ("_pad2", c_i32),
+        ("seg_row", c_vp), ("seg_t0", c_vp), ("seg_t1", c_vp), ("row_seg0", c_vp), ("n_seg", c_i64),
     ]
 
 
@@ -117,8 +118,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.lgb_abi_version() != 2:
-        raise RuntimeError(f"liblaplace_b200.so ABI {lib.lgb_abi_version()} != 2")
+    if lib.lgb_abi_version() != 3:
+        raise RuntimeError(f"liblaplace_b200.so ABI {lib.lgb_abi_version()} != 3")
     _lib = lib
     return lib
 

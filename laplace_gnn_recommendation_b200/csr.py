@@ -21,6 +21,8 @@ SPMM_VARIANT = int(os.environ.get("LGB_SPMM_VARIANT", "0"))
 # rows with more non-zeros are split into chunk-sized slices (csrc/spmm.cu): bounds the length of any sequential fp32
 # accumulation chain (accuracy) and the work of one warp (load balance)
 DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
+STAGE2_SEG = 32                                                   # partial rows per warp of the stage-2 tree
+STAGE2_TREE = os.environ.get("LGB_SPMM_STAGE2", "tree") != "flat"  # flat = one CTA per long row (the round-1 stage 2), for A/B
 
 
 # candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
@@ -70,6 +72,8 @@ class DeviceCSR:
         self.n_long = 0
         self.n_tasks = 0
         self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
+        self.n_seg = 0
+        self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = None
         self.perm: Optional[torch.Tensor] = None      # COO -> CSR permutation (int64) when built from COO
         self.csr2csc: Optional[torch.Tensor] = None   # set on the TRANSPOSED graph: its entry i is CSR entry csr2csc[i]
         self._t: Optional["DeviceCSR"] = None
@@ -142,7 +146,23 @@ class DeviceCSR:
                                              ptr(self.long_rows), ptr(self.long_ptr), ptr(self.task_row),
                                              ptr(self.task_start), ptr(self.task_end), ptr(ws), ws.numel(), stream()),
                       "spmm_plan_fill")
+                self._build_segments()
         self._struct = None
+
+    def _build_segments(self) -> None:
+        """Stage-2 tree plan: the partial rows of every long row cut into segments of 32 (one warp each, csrc/spmm.cu
+        spmm_long_reduce_tree_kernel).  Plan-time index arithmetic on the device (torch ops)."""
+        lp = self.long_ptr.long()
+        nseg = (lp[1:] - lp[:-1] + STAGE2_SEG - 1) // STAGE2_SEG
+        row_seg0 = torch.zeros(self.n_long + 1, dtype=torch.int64, device=self.device)
+        row_seg0[1:] = torch.cumsum(nseg, 0)
+        self.n_seg = int(row_seg0[-1])
+        seg_row = torch.repeat_interleave(torch.arange(self.n_long, device=self.device), nseg)
+        first = lp[seg_row] + STAGE2_SEG * (torch.arange(self.n_seg, device=self.device) - row_seg0[seg_row])
+        i32 = torch.int32
+        self.seg_row, self.seg_t0 = seg_row.to(i32), first.to(i32)
+        self.seg_t1 = torch.minimum(first + STAGE2_SEG, lp[seg_row + 1]).to(i32)
+        self.row_seg0 = row_seg0.to(i32)
 
     def use_degree_order(self, on: bool = True) -> "DeviceCSR":
         """Process ordinary rows in descending degree-bucket order (better intra-CTA balance on skewed graphs)."""
@@ -233,8 +253,9 @@ class DeviceCSR:
         """Rebuild the long-row plan for another slice size."""
         if int(chunk) != self.chunk:
             self.chunk = int(chunk)
-            self.n_long = self.n_tasks = 0
+            self.n_long = self.n_tasks = self.n_seg = 0
             self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
+            self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = None
             if self.chunk > 0:
                 self._build_plan()
             self._struct = None
@@ -326,6 +347,8 @@ class DeviceCSR:
             s.long_rows, s.long_ptr = ptr(self.long_rows), ptr(self.long_ptr)
             s.task_row, s.task_start, s.task_end = ptr(self.task_row), ptr(self.task_start), ptr(self.task_end)
             s.colidx_hot, s.hot_cols, s.n_hot = ptr(self.colidx_hot), ptr(self.hot_cols), int(self.n_hot)
+            s.seg_row, s.seg_t0, s.seg_t1, s.row_seg0 = ptr(self.seg_row), ptr(self.seg_t0), ptr(self.seg_t1), ptr(self.row_seg0)
+            s.n_seg = int(self.n_seg)
             self._struct = s
         return self._struct
 
@@ -337,9 +360,9 @@ class DeviceCSR:
         key = (d, self.n_tasks, torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0)
         buf = self._partials.get(key)
         if buf is None:
-            # + 64 floats behind the partial sums: the work counters of the hot-column kernels (variants 30 / 31), which must
-            # start at zero and are left at zero by every launch
-            buf = torch.zeros(self.n_tasks * d + 64, dtype=torch.float32, device=self.device)
+            # behind the partial sums: 64 floats for the work counters of the hot-column kernels (variants 30 / 31), the level-2
+            # rows and the tickets of the stage-2 tree; all of it starts at zero and every launch leaves counters / tickets zero
+            buf = torch.zeros(self.n_tasks * d + 64 + self.n_seg * d + self.n_long + 64, dtype=torch.float32, device=self.device)
             self._partials[key] = buf
         return buf
 
@@ -364,7 +387,7 @@ class DeviceCSR:
             variant = SPMM_VARIANT if self.variant is None else self.variant
         if variant in (30, 31) and self.n_hot == 0 and os.environ.get("LGB_SPMM_HOT"):
             self.set_hot(int(os.environ["LGB_SPMM_HOT"]))      # a variant pinned from the environment brings its plan along
-        flags = (1 if mean else 0) | (variant << 4)
+        flags = (1 if mean else 0) | (2 if (STAGE2_TREE and self.n_seg) else 0) | (variant << 4)
         with torch.cuda.device(self.device):
             if y_tail is not None:
                 # split epilogue: rows >= split_row write raw sums to y_tail (see lgb_spmm_split)

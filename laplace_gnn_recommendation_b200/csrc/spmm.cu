@@ -48,6 +48,14 @@ struct SpmmParams {
   float* partial;
   int64_t split_row;   // rows >= split_row skip the epilogue and store their raw sums to y_tail[r - split_row] (0 = off)
   float* y_tail;
+  // stage-2 tree plan (optional): the partial rows of every long row cut into segments of <= 32
+  const int32_t* seg_row;
+  const int32_t* seg_t0;
+  const int32_t* seg_t1;
+  const int32_t* row_seg0;
+  int64_t n_seg;
+  float* part2;        // [n_seg, d] level-2 partial rows
+  int* tickets;        // [n_long], zero between launches
 };
 
 // STEP = distance between the 32-entry batches this warp takes (32: the whole range; 32*SPMM_WARPS: every SPMM_WARPS-th
@@ -578,11 +586,13 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
   }
 }
 
-// Threads of one stage-2 CTA: 1024 where the per-group staging fits the static shared memory (a long row of a power-law graph
-// has thousands of partial rows: the parallelism that hides their load latency comes from 32 warps, ptxas serialises a
-// deeper per-thread unroll behind the dependent adds), 256 otherwise.
+// Threads of one CTA of the flat stage-2 kernel (the fallback of the tree kernel below; 1024-thread CTAs were measured and
+// lose on plans with many short long-rows: their final combine walks 128 groups whatever the row holds).
 template <int G, int VPL>
-constexpr int reduce_threads() { return ((1024 / G) * G * VPL * 16 <= 48 * 1024) ? 1024 : 256; }
+constexpr int reduce_threads() { return 256; }
+
+template <int G, int VPL>
+static int launch_stage2(const SpmmParams& p, cudaStream_t stream);
 
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
@@ -608,10 +618,7 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
     spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL, W256><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
-  if (p.n_long > 0) {
-    { constexpr int RT = reduce_threads<G, VPL>(); spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
-    LGB_LAUNCH_CHECK();
-  }
+  { const int rc2 = launch_stage2<G, VPL>(p, stream); if (rc2) return rc2; }
   return LGB_OK;
 }
 
@@ -724,10 +731,7 @@ static int launch_async(const SpmmParams& p, cudaStream_t stream) {
     spmm_async_kernel<G, S, MINB><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
-  if (p.n_long > 0) {
-    { constexpr int RT = reduce_threads<G, 1>(); spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
-    LGB_LAUNCH_CHECK();
-  }
+  { const int rc2 = launch_stage2<G, 1>(p, stream); if (rc2) return rc2; }
   return LGB_OK;
 }
 
@@ -780,6 +784,123 @@ __global__ void __launch_bounds__(reduce_threads<G, VPL>()) spmm_long_reduce_ker
     const int r = p.long_rows[L];
     epilogue_row<G, VPL>(p, r, p.rowptr[r + 1] - p.rowptr[r], lig, acc);
   }
+}
+
+
+// ---- stage 2 as a tree (default when the plan carries segments) -------------------------------------------------------------
+// The flat kernel above gives one CTA per long row and walks its partial rows with one or two loads in flight: 85-145 us per
+// call on the H&M graph (the most popular item has 4 000-8 000 partial rows), 13-40 us on a 1/8 shard -- 7-13 % of every
+// lgb_spmm call (ncu launch lists r2d / r2f).  Here the partial rows of a long row are cut at plan time into segments of 32;
+// one WARP per segment: lane l loads partial row t0 + l, column by column (16 independent 128-bit loads in flight per lane --
+// no add depends on another load), a shuffle butterfly adds the 32 rows.  A row of one segment goes straight to the
+// epilogue; otherwise the warp stores a level-2 partial row, takes a ticket, and the LAST warp of the row to arrive adds the
+// level-2 rows (same procedure, fixed order) and runs the epilogue.  Deterministic: which warp does the final pass depends on
+// timing, what it computes does not.  Tickets reset themselves.
+__device__ __forceinline__ float4 ld_cg_f4(const float4* p) {    // level-2 rows were written by other SMs: bypass the L1
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int TREE_CB = 16;   // float4 columns handled per pass (64 floats: the whole row at d = 64)
+
+template <bool CG>
+__device__ __forceinline__ void tree_sum32(const float4* __restrict__ rows, int t0, int t1, int d4, int c0, int lane, float4 (&v)[TREE_CB]) {
+  const bool have = t0 + lane < t1;
+  const float4* src = rows + (size_t)(t0 + lane) * d4 + c0;
+#pragma unroll
+  for (int f = 0; f < TREE_CB; ++f)
+    v[f] = (have && c0 + f < d4) ? (CG ? ld_cg_f4(src + f) : ld_stream_f4(src + f)) : f4_zero();
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int f = 0; f < TREE_CB; ++f) v[f] = f4_add(v[f], f4_shfl_xor(v[f], off));
+}
+
+__device__ __forceinline__ float4 pick_col(const float4 (&v)[TREE_CB], int lane) {
+  float4 m = v[0];
+#pragma unroll
+  for (int f = 1; f < TREE_CB; ++f)
+    if ((lane & (TREE_CB - 1)) == f) m = v[f];
+  return m;
+}
+
+// the epilogue of epilogue_row for ONE float4 column f of row r
+__device__ __forceinline__ void epilogue_col(const SpmmParams& p, int r, int deg, int f, float4 y) {
+  if (p.y_tail && r >= p.split_row) {
+    st_f4(reinterpret_cast<float4*>(p.y_tail) + (size_t)(r - p.split_row) * p.d4 + f, y);
+    return;
+  }
+  const size_t o = (size_t)r * p.d4 + f;
+  if (p.mean) {
+    const float c = (float)max(deg, 1);
+    y.x = __fdiv_rn(y.x, c); y.y = __fdiv_rn(y.y, c); y.z = __fdiv_rn(y.z, c); y.w = __fdiv_rn(y.w, c);
+  }
+  if (p.resid) y = f4_add(y, ld_once_f4(reinterpret_cast<const float4*>(p.resid) + o));
+  if (p.Y) st_f4(reinterpret_cast<float4*>(p.Y) + o, y);
+  if (p.acc_out) {
+    float4 a = y;
+    if (p.acc_in) a = f4_add(ld_once_f4(reinterpret_cast<const float4*>(p.acc_in) + o), y);
+    if (p.acc_div != 1.0f) {
+      a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div); a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
+    }
+    st_f4(reinterpret_cast<float4*>(p.acc_out) + o, a);
+  }
+}
+
+__global__ void __launch_bounds__(128) spmm_long_reduce_tree_kernel(const SpmmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t seg = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (seg >= p.n_seg) return;
+  const int L = p.seg_row[seg];
+  const int t0 = p.seg_t0[seg], t1 = p.seg_t1[seg];
+  const int s0 = p.row_seg0[L], nseg = p.row_seg0[L + 1] - s0;
+  const int r = p.long_rows[L];
+  const int deg = p.rowptr[r + 1] - p.rowptr[r];
+  const int d4 = p.d4;
+  const float4* part = reinterpret_cast<const float4*>(p.partial);
+  float4* part2 = reinterpret_cast<float4*>(p.part2);
+  float4 v[TREE_CB];
+  if (nseg == 1) {                                   // the whole row in one segment: sum and finish
+    for (int c0 = 0; c0 < d4; c0 += TREE_CB) {
+      tree_sum32<false>(part, t0, t1, d4, c0, lane, v);
+      if (lane < TREE_CB && c0 + lane < d4) epilogue_col(p, r, deg, c0 + lane, pick_col(v, lane));
+    }
+    return;
+  }
+  for (int c0 = 0; c0 < d4; c0 += TREE_CB) {         // level-2 partial row of this segment
+    tree_sum32<false>(part, t0, t1, d4, c0, lane, v);
+    if (lane < TREE_CB && c0 + lane < d4) st_f4(part2 + (size_t)seg * d4 + c0 + lane, pick_col(v, lane));
+  }
+  __threadfence();
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(p.tickets + L, 1);
+  ticket = __shfl_sync(FULL_MASK, ticket, 0);
+  if (ticket != nseg - 1) return;
+  __threadfence();                                   // every other segment of the row has published its level-2 row
+  for (int c0 = 0; c0 < d4; c0 += TREE_CB) {
+    float4 tot = f4_zero();
+    for (int b = s0; b < s0 + nseg; b += 32) {       // fixed order: segment blocks ascending, butterfly inside a block
+      tree_sum32<true>(part2, b, min(b + 32, s0 + nseg), d4, c0, lane, v);
+      tot = f4_add(tot, pick_col(v, lane));
+    }
+    if (lane < TREE_CB && c0 + lane < d4) epilogue_col(p, r, deg, c0 + lane, tot);
+  }
+  if (lane == 0) p.tickets[L] = 0;
+}
+
+// Stage 2 of every kernel family: the tree when the plan carries segments (and the caller sized the scratch for it), else flat.
+template <int G, int VPL>
+static int launch_stage2(const SpmmParams& p, cudaStream_t stream) {
+  if (p.n_long <= 0) return LGB_OK;
+  if (p.n_seg > 0 && p.seg_row && p.part2 && p.tickets) {
+    spmm_long_reduce_tree_kernel<<<(unsigned)((p.n_seg + 3) / 4), 128, 0, stream>>>(p);
+  } else {
+    constexpr int RT = reduce_threads<G, VPL>();
+    spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, RT, 0, stream>>>(p);
+  }
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
 }
 
 // Scalar path for d % 4 != 0 (tiny test shapes): one warp per row, lane strides over the columns.
@@ -837,10 +958,7 @@ static int launch_vec(const SpmmParams& p, int variant, cudaStream_t stream) {
     }
     LGB_LAUNCH_CHECK();
   }
-  if (p.n_long > 0) {
-    { constexpr int RT = reduce_threads<G, VPL>(); spmm_long_reduce_kernel<G, VPL><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
-    LGB_LAUNCH_CHECK();
-  }
+  { const int rc2 = launch_stage2<G, VPL>(p, stream); if (rc2) return rc2; }
   return LGB_OK;
 }
 
@@ -1032,10 +1150,7 @@ static int launch_hot(const SpmmParams& p, const lgb_csr* g, cudaStream_t stream
     spmm_hot_kernel<G, UNROLL, G, MINB><<<(unsigned)blocks, HOT_THREADS, smem, stream>>>(p, g->colidx_hot, g->hot_cols, g->n_hot);
     LGB_LAUNCH_CHECK();
   }
-  if (p.n_long > 0) {
-    { constexpr int RT = reduce_threads<G, 1>(); spmm_long_reduce_kernel<G, 1><<<(unsigned)p.n_long, RT, 0, stream>>>(p); }
-    LGB_LAUNCH_CHECK();
-  }
+  { const int rc2 = launch_stage2<G, 1>(p, stream); if (rc2) return rc2; }
   return LGB_OK;
 }
 
@@ -1182,6 +1297,11 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   p.X = X; p.Y = Y; p.resid = resid; p.acc_in = acc_in; p.acc_out = acc_out; p.acc_div = acc_div;
   p.mean = (flags & LGB_SPMM_MEAN) ? 1 : 0; p.partial = partial_ws;
   p.split_row = split_row; p.y_tail = y_tail;
+  // stage-2 tree: segments from the plan, level-2 rows and tickets behind the partial sums and the 64 counter floats
+  p.seg_row = g->seg_row; p.seg_t0 = g->seg_t0; p.seg_t1 = g->seg_t1; p.row_seg0 = g->row_seg0;
+  p.n_seg = (g->chunk > 0 && g->seg_row && g->seg_t0 && g->seg_t1 && g->row_seg0 && (flags & LGB_SPMM_TREE_WS)) ? g->n_seg : 0;
+  p.part2 = p.n_seg > 0 && partial_ws ? partial_ws + (size_t)p.n_tasks * d + 64 : nullptr;
+  p.tickets = p.part2 ? reinterpret_cast<int*>(p.part2 + (size_t)p.n_seg * d) : nullptr;
   if (p.n_tasks > 0) {
     LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->task_end && g->long_rows && g->long_ptr, LGB_EINVAL,
                 "lgb_spmm: plan has %lld tasks but plan arrays (task_row/start/end, long_rows/ptr) / partial workspace missing",

@@ -56,6 +56,7 @@ ASM_BODIES = {
     "ld_once_f8": "f4x2 v; v.a = p[0]; v.b = p[1]; return v;",
     "cp_async_commit": "",
     "pin_f4": "",
+    "ld_cg_f4": "return *p;",
     "dyn_smem_f4": "static float4 buf[16384]; return buf;",      # 256 KB: blocks run one at a time
     "cp_async_wait": "",
     # NVSwitch multicast (csrc/peer.cu): the "multicast address" is a key registered with emu_multicast_bind(); a load-reduce
