@@ -311,43 +311,44 @@ class SymmOps(CudaOps):
         return bufs
 
     def _choose_mode(self, buf, grp):
-        """Plan-time choice between the multicast form (in-switch reduction, (G+1)/G of the buffer per link direction) and
-        the peer form ((G-1)/G, but G loads per element): both are run on the largest exchange buffer, timed with CUDA
-        events, max over ranks; every rank takes the same decision.  LGB_EXCHANGE_MODE=multicast|peer pins it."""
+        """Plan-time choice of the exchange kernel's form: multicast (in-switch reduction, (G+1)/G of the buffer per link
+        direction) or peer loads / stores ((G-1)/G, but G loads per element), with 64 or 128 CTAs.  Every candidate is run on
+        the largest exchange buffer and timed with CUDA events, max over ranks; every rank takes the same decision.
+        LGB_EXCHANGE_MODE=multicast|peer and LGB_EXCHANGE_BLOCKS=n pin it."""
         import os
         want = os.environ.get("LGB_EXCHANGE_MODE", "auto")
         blocks = int(os.environ.get("LGB_EXCHANGE_BLOCKS", "0"))
-        self.flags = (blocks & 0xFF) << 8
         self.mode_report = {"multicast_available": self.multicast}
-        if not self.multicast or want == "peer":
-            self.flags |= 2
-            self.mode = "peer"
-            return
-        self.mode = "multicast"
-        if want != "auto":
-            return
-        comm = self.comm[0]
-        times = {}
-        for name, fl in (("multicast", 0), ("peer", 2)):
-            self.flags = (self.flags & ~2) | fl
-            with torch.cuda.stream(comm):
-                for _ in range(2):
-                    self._exchange(buf, 0, comm)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(comm)
-                for _ in range(5):
-                    self._exchange(buf, 0, comm)
-                e1.record(comm)
-            e1.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1) / 5], device=self.device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=grp)
-            times[name] = float(t)
-        self.mode = min(times, key=times.get)
-        self.flags = (self.flags & ~2) | (2 if self.mode == "peer" else 0)
-        self.mode_report.update(ms=times, chosen=self.mode, bytes=buf.numel() * 4)
-        buf.zero_()
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=grp)
+        modes = [m for m in ("multicast", "peer") if (m == "peer" or self.multicast) and want in ("auto", m)] or ["peer"]
+        cands = [(m, b) for m in modes for b in ((blocks,) if blocks else (64, 128))]
+
+        def flags_of(mode, b):
+            return ((b & 0xFF) << 8) | (2 if mode == "peer" else 0)
+        if len(cands) > 1:
+            comm = self.comm[0]
+            times = {}
+            for mode, b in cands:
+                self.flags = flags_of(mode, b)
+                with torch.cuda.stream(comm):
+                    for _ in range(2):
+                        self._exchange(buf, 0, comm)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(comm)
+                    for _ in range(5):
+                        self._exchange(buf, 0, comm)
+                    e1.record(comm)
+                e1.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / 5], device=self.device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=grp)
+                times[f"{mode}/{b}"] = float(t)
+            best = min(times, key=times.get)
+            cands = [c for c in cands if f"{c[0]}/{c[1]}" == best]
+            self.mode_report.update(ms=times, chosen=best, bytes=buf.numel() * 4)
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=grp)
+        self.mode, self.blocks = cands[0]
+        self.flags = flags_of(*cands[0])
 
     def _exchange(self, t, channel, comm):
         off = t.data_ptr() - self._arena.data_ptr() if self._arena is not None else -1
