@@ -302,6 +302,19 @@ int lgb_edge_keys_sorted(const int64_t* row, const int64_t* col, int64_t n, int6
                          int64_t* keys_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Sub-graph batch assembly -- the index-heavy steps of GraphDataset.__getitem__ / fetch_n_hop_neighbourhood
+ * / remap_edges_to_start_from_zero (data/dataset.py:39-182,258-300) for a whole batch of root users at once.
+ *   lgb_segment_expand:      adjacency (ptr[N+1], idx) in int64; frontier nodes[n]; out_off[n+1] = exclusive scan of their
+ *                            degrees; for every adjacency entry j: out_pos[j] = frontier position, out_nbr[j] = neighbour
+ *                            (adjacency order kept).
+ *   lgb_bucketize_segmented: out[j] = torch.bucketize(values[j], buckets[bucket_ptr[seg[j]] : bucket_ptr[seg[j]+1]]).
+ * ------------------------------------------------------------------------------------------- */
+int lgb_segment_expand(const int64_t* ptr, const int64_t* idx, const int64_t* nodes, const int64_t* out_off, int64_t n,
+                       int64_t total, int64_t* out_pos, int64_t* out_nbr, void* stream);
+int lgb_bucketize_segmented(const int64_t* values, const int64_t* seg, int64_t n, const int64_t* buckets,
+                            const int64_t* bucket_ptr, int64_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused Adam step -- optim.Adam(model.parameters(), lr) + optimizer.step() of run_pipeline_lightgcn.py:103,159
  * (betas/eps as given, no weight decay, no amsgrad), torch's single-tensor arithmetic in one streaming pass.
  * `step` is the 1-based step count AFTER the increment (torch's state["step"]).

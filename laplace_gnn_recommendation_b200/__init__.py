@@ -19,6 +19,7 @@ from .loader import (DeviceSampler, both_indexes_from_zero, make_lightgcn_splits
 from .metrics import evaluation, get_metrics_lightgcn, get_metrics_universal, recall_precision_ndcg  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .sparse import SparseTensor, gcn_norm, matmul  # noqa: F401
+from .subgraph import SubgraphSampler  # noqa: F401
 from .topk import SeenItems, make_predictions_for_user, recommend_topk, topk_dict  # noqa: F401
 
 __all__ = [
@@ -28,5 +29,5 @@ __all__ = [
     "Encoder_Decoder_Model", "get_SAGEConv_layers", "get_linear_layers", "aggregate", "build_edge_csr",
     "edge_concat", "edge_dot", "both_indexes_from_zero", "split", "make_lightgcn_splits", "evaluation",
     "get_metrics_lightgcn", "get_metrics_universal", "recall_precision_ndcg", "FusedAdam", "install_aliases", "patch_driver",
-    "HeteroData",
+    "HeteroData", "SubgraphSampler",
 ]

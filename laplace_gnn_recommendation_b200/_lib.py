@@ -93,6 +93,8 @@ PROTOTYPES = {
     "lgb_neg_reject_mask": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_sort_keys_ws_bytes": (C.c_int, [c_i64, C.POINTER(c_sz)]),
     "lgb_edge_keys_sorted": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "lgb_segment_expand": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "lgb_bucketize_segmented": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "lgb_adam_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_vp]),
     "lgb_multimem_allreduce_f32": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp]),
     "lgb_peer_allreduce_f32": (C.c_int, [C.POINTER(C.c_uint64), c_i64, c_i32, c_i32, c_vp]),

@@ -344,13 +344,17 @@ class HeteroEncoder(nn.Module):
 
     reuse_flipped_edge_types = True
 
-    def forward(self, x_dict: Dict[str, torch.Tensor], edge_index_dict) -> Dict[str, torch.Tensor]:
+    def forward(self, x_dict: Dict[str, torch.Tensor], edge_index_dict, graphs: Optional[Dict[tuple, DeviceCSR]] = None
+                ) -> Dict[str, torch.Tensor]:
         x = dict(x_dict)
         flush_deferred_checks()                    # verdicts of the previous batch (index range, flipped edge types)
         # one CSR (+ lazily its transpose) per edge type per batch, shared by all layers and the backward; an edge type
-        # that is the exact flip of another one IS that one's transpose, so the pair costs two sorts instead of four
-        graphs: Dict[tuple, DeviceCSR] = {}
+        # that is the exact flip of another one IS that one's transpose, so the pair costs two sorts instead of four.
+        # ``graphs``: the batch's CSRs when the caller already has them (SubgraphSampler.sample()["graphs"]).
+        graphs = dict(graphs) if graphs else {}
         for et in self.edge_types:
+            if et in graphs:
+                continue
             ei = edge_index_dict[et]
             mate = self._flip_mate(et, graphs, edge_index_dict) if self.reuse_flipped_edge_types else None
             graphs[et] = graphs[mate].transpose() if mate is not None else \
@@ -545,10 +549,10 @@ class Encoder_Decoder_Model(nn.Module):
             x_dict = self._embed(x_dict)
         self.encoder(x_dict, edge_index_dict)
 
-    def forward(self, x_dict, edge_index_dict: dict, edge_label_index: torch.Tensor) -> torch.Tensor:
+    def forward(self, x_dict, edge_index_dict: dict, edge_label_index: torch.Tensor, graphs=None) -> torch.Tensor:
         if self.embedding:
             x_dict = self._embed(x_dict)
-        z_dict = self.encoder(x_dict, edge_index_dict)
+        z_dict = self.encoder(x_dict, edge_index_dict, graphs=graphs) if graphs else self.encoder(x_dict, edge_index_dict)
         if self.batch_normalize:
             z_dict[NODE_USER] = self.encoder_layer_norm_customer(z_dict[NODE_USER])
             z_dict[NODE_ITEM] = self.encoder_layer_norm_article(z_dict[NODE_ITEM])

@@ -54,6 +54,8 @@ test_encoder_decoder_against_reference_golden = TH.test_encoder_decoder_against_
 test_infer_rebatch_matches_oracle = TH.test_infer_rebatch_matches_oracle
 test_decoder_concat_and_dot = TH.test_decoder_concat_and_dot
 test_hetero_fan_in_three_edge_types = TH.test_hetero_fan_in_three_edge_types
+test_subgraph_sampler_against_reference_golden = TH.test_subgraph_sampler_against_reference_golden
+test_subgraph_sampler_random_mode_and_model_step = TH.test_subgraph_sampler_random_mode_and_model_step
 test_model_gradients_same_with_and_without_wgrad_kernel = TH.test_model_gradients_same_with_and_without_wgrad_kernel
 
 

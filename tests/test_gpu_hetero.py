@@ -216,3 +216,87 @@ def test_model_gradients_same_with_and_without_wgrad_kernel(cuda_dev, monkeypatc
     for k in ga:
         # (a bias in front of the batch norm has a zero gradient: both backward passes return rounding noise there, hence the floor)
         torch.testing.assert_close(ga[k], gb[k], rtol=1e-4, atol=1e-5 * float(gb[k].abs().max()) + 1e-7, msg=lambda m: f"{k}: {m}")
+
+
+# ------------------------------------------------------------------ device-side sub-graph batch assembly
+def _lex_sorted(e):
+    order = torch.argsort(e[0] * (int(e[1].max()) + 1 if e.numel() else 1) + e[1], stable=True)
+    return e[:, order]
+
+
+def test_subgraph_sampler_against_reference_golden(cuda_dev):
+    """SubgraphSampler.sample(roots) against GraphDataset.__getitem__ of the REAL reference (tests/golden/make_golden_subgraph.py:
+    randomization=False, the reference's own test mode) on its manual test graphs and a random one, 1-3 hops: node features
+    and label edges identical entry for entry, sub-graph edges identical as multisets (the reference walks Python sets), the
+    batch = the disjoint union with PyG-style offsets."""
+    import os
+    golden = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_subgraph.pt"))
+    for name, gcase in golden.items():
+        c, cfg = gcase["inputs"], gcase["config"]
+        s = lg.SubgraphSampler(c["edge_index"].to(cuda_dev), c["x_user"].to(cuda_dev), c["x_article"].to(cuda_dev),
+                               n_hop_neighbors=cfg["n_hops"], num_neighbors=cfg["num_neighbors"], positive_edges_ratio=cfg["pos_ratio"],
+                               negative_edges_ratio=cfg["neg_ratio"], k=cfg["k"], randomization=False)
+        batch = s.sample(torch.tensor(c["roots"]).to(cuda_dev))
+        uptr, aptr = batch["ptr"]["customer"].cpu(), batch["ptr"]["article"].cpu()
+        ei, eli, lab = batch["edge_index_dict"][("customer", "buys", "article")].cpu(), batch["edge_label_index"].cpu(), batch["edge_label"].cpu()
+        rev = batch["edge_index_dict"][("article", "rev_buys", "customer")].cpu()
+        assert torch.equal(rev, ei.flip(0))
+        xu, xa = batch["x_dict"]["customer"].cpu(), batch["x_dict"]["article"].cpu()
+        for b, want in enumerate(gcase["items"]):
+            what = f"{name} root #{b}"
+            u0, u1, a0, a1 = int(uptr[b]), int(uptr[b + 1]), int(aptr[b]), int(aptr[b + 1])
+            assert torch.equal(xu[u0:u1], want["x_user"]) and torch.equal(xa[a0:a1], want["x_article"]), what
+            mine = (ei[0] >= u0) & (ei[0] < u1)
+            assert bool(((ei[1][mine] >= a0) & (ei[1][mine] < a1)).all()), what            # block diagonal
+            local = torch.stack([ei[0][mine] - u0, ei[1][mine] - a0])
+            assert torch.equal(_lex_sorted(local), _lex_sorted(want["edge_index"])), what
+            lm = (eli[0] >= u0) & (eli[0] < u1)
+            assert torch.equal(torch.stack([eli[0][lm] - u0, eli[1][lm] - a0]), want["edge_label_index"]), what
+            assert torch.equal(lab[lm], want["edge_label"]), what
+        # the prebuilt CSR pair describes the same edges as the COO lists
+        g = batch["graphs"][("customer", "buys", "article")]
+        assert g.n_rows == int(aptr[-1]) and g.n_cols == int(uptr[-1]) and g.nnz == ei.shape[1]
+        from laplace_gnn_recommendation_b200 import hetero
+        hetero.flush_deferred_checks()
+
+
+def test_subgraph_sampler_random_mode_and_model_step(cuda_dev):
+    """Random mode (device generator): sampled positives are the root's own articles, the cheap-branch negatives lie in
+    [0, id_max), fan-out cuts bound every frontier, every edge of the batch is a real edge -- and the batch (with its prebuilt
+    CSR pair) drives a training step of the ranking model that equals the step on the same batch without the prebuilt graphs."""
+    from laplace_gnn_recommendation_b200 import hetero
+    gen = torch.Generator().manual_seed(8)
+    U, A, E = 300, 200, 40000
+    e = torch.stack([torch.randint(0, U, (E,), generator=gen), torch.randint(0, A, (E,), generator=gen)])
+    e[0, :U] = torch.arange(U)
+    pos = set(map(tuple, e.t().tolist()))
+    xu, xa = torch.randn(U, 6, generator=gen), torch.randn(A, 5, generator=gen)
+    s = lg.SubgraphSampler(e.to(cuda_dev), xu.to(cuda_dev), xa.to(cuda_dev), n_hop_neighbors=3, num_neighbors=7, randomization=True)
+    roots = torch.randint(0, U, (16,), generator=gen)
+    batch = s.sample(roots.to(cuda_dev))
+    uid, aid = batch["n_id"]["customer"].cpu(), batch["n_id"]["article"].cpu()
+    ei = batch["edge_index_dict"][hetero.EDGE_KEY].cpu()
+    assert all((int(uid[a]), int(aid[b])) in pos for a, b in ei.t().tolist())            # remapped ids point at real edges
+    eli, lab = batch["edge_label_index"].cpu(), batch["edge_label"].cpu()
+    uptr = batch["ptr"]["customer"].cpu()
+    for b, r in enumerate(roots.tolist()):
+        m = (eli[0] >= uptr[b]) & (eli[0] < uptr[b + 1])
+        assert bool((uid[eli[0][m]] == r).all())                                           # label edges start at the root
+        assert all((r, int(aid[x])) in pos for x in eli[1][m & (lab == 1)].tolist())       # sampled positives are its articles
+        n_pos_r, n_s = int((e[0] == r).sum()), int((m & (lab == 1)).sum())
+        assert n_s == max(1, int(n_pos_r * 0.5)) and int((m & (lab == 0)).sum()) == int((11 if n_s <= 1 else 3.0) * n_s)
+        # hop structure: 1 + <= 7 + <= 7 users (frontiers are cut to num_neighbors), besides the root's own row
+        assert int(uptr[b + 1] - uptr[b]) <= 1 + 7 + 7
+    metadata = (["customer", "article"], [hetero.EDGE_KEY, hetero.REV_EDGE_KEY])
+    losses = []
+    for use_graphs in (True, False):
+        torch.manual_seed(0)
+        model = lg.Encoder_Decoder_Model(encoder_layers=lg.get_SAGEConv_layers(2, 16, 8, "mean"), decoder_layers=lg.get_linear_layers(2, 16, 16, 1),
+                                         feature_info={}, metadata=metadata, embedding=False, heterogeneous_prop_agg_type="sum",
+                                         batch_normalize=True, p_dropout_edges=None, p_dropout_features=None).to(cuda_dev)
+        out = model(dict(batch["x_dict"]), batch["edge_index_dict"], batch["edge_label_index"], graphs=batch["graphs"] if use_graphs else None)
+        loss = torch.nn.BCEWithLogitsLoss()(out, batch["edge_label"].float())
+        loss.backward()
+        losses.append(float(loss))
+    hetero.flush_deferred_checks()
+    assert losses[0] == pytest.approx(losses[1], rel=1e-6)
