@@ -201,6 +201,74 @@ def linear(module: nn.Module, x: torch.Tensor) -> torch.Tensor:
     return module(x)
 
 
+class _SageFn(torch.autograd.Function):
+    """One SAGEConv (add / mean) as ONE autograd node: out = (aggr_j x_j) Wl^T + bl + x_dst Wr^T.  The S / M batches of the
+    ranking step are bound by host dispatch (profiles/README.md r2c): the composition aggregate -> Linear -> Linear -> add
+    costs seven autograd nodes and a dozen op dispatches per layer and edge type, this one costs one node, one library call
+    and two GEMM calls forward; backward: the transposed aggregation, three GEMM calls and the two weight gradients (split-K
+    kernel from WGRAD_MIN_ROWS rows, cuBLAS below).  Same arithmetic as the composition (the second GEMM accumulates onto the
+    first one's fp32 result exactly like the separate add)."""
+
+    @staticmethod
+    def forward(ctx, x_src, x_dst, w_l, b_l, w_r, g: DeviceCSR, mean: bool):
+        x_src = _lib.f32c(x_src)
+        agg = g.spmm(x_src, mean=mean)
+        out = torch.addmm(b_l, agg, w_l.t()) if b_l is not None else agg @ w_l.t()
+        if w_r is not None:
+            out.addmm_(x_dst, w_r.t())
+        ctx.save_for_backward(agg, x_dst if w_r is not None else None, w_l, w_r)
+        ctx.g, ctx.mean, ctx.has_bias = g, mean, b_l is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        agg, x_dst, w_l, w_r = ctx.saved_tensors
+        g: DeviceCSR = ctx.g
+        gout = _lib.f32c(gout)
+        need = ctx.needs_input_grad
+        gx_src = gx_dst = gw_l = gb_l = gw_r = None
+        if need[0]:
+            d_agg = gout @ w_l
+            if ctx.mean:
+                scaled = torch.empty_like(d_agg)
+                with torch.cuda.device(gout.device):
+                    check(_lib.load().lgb_row_div_by_degree(ptr(d_agg), ptr(g.rowptr), g.n_rows, d_agg.shape[1], ptr(scaled), stream()),
+                          "row_div_by_degree")
+                _lib.count_launch()
+                d_agg = scaled
+            gx_src = g.transpose().spmm(d_agg)
+        if need[2] or (ctx.has_bias and need[3]):
+            gw_l, gb_l = _wgrad(agg, gout, ctx.has_bias)
+        if w_r is not None:
+            if need[1]:
+                gx_dst = gout @ w_r
+            if need[4]:
+                gw_r, _ = _wgrad(x_dst, gout, False)
+        return gx_src, gx_dst, gw_l, gb_l, gw_r, None, None
+
+
+def _wgrad(x: torch.Tensor, gy: torch.Tensor, want_bias: bool):
+    """(dW [out, in], db [out] or None) of y = x W^T + b: split-K kernel for many rows, cuBLAS + a column sum otherwise."""
+    x = _lib.f32c(x)
+    N, n_in = x.shape
+    n_out = gy.shape[1]
+    if N < WGRAD_MIN_ROWS:
+        return gy.t() @ x, (gy.sum(0) if want_bias else None)
+    lib = _lib.load()
+    need = C.c_size_t(0)
+    check(lib.lgb_linear_wgrad_ws_bytes(N, n_in, n_out, C.byref(need)), "linear_wgrad_ws_bytes")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+    gw = torch.empty(n_out, n_in, dtype=torch.float32, device=x.device)
+    gb = torch.empty(n_out, dtype=torch.float32, device=x.device) if want_bias else None
+    with torch.cuda.device(x.device):
+        check(lib.lgb_linear_wgrad(ptr(x), ptr(gy), N, n_in, n_out, ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream()), "linear_wgrad")
+    _lib.count_launch(3 if gb is not None else 2)
+    return gw, gb
+
+
+FUSED_SAGE = os.environ.get("LGB_SAGE_FUSED", "1") == "1"
+
+
 class SAGEConv(nn.Module):
     """PyG ``SAGEConv(in_channels, out_channels, aggr, normalize=False, bias=True)`` as the reference builds it
     (model/layers.py:9-24): out = lin_l(aggr_j x_j) + lin_r(x_i); lazy input widths (``-1``)."""
@@ -226,7 +294,12 @@ class SAGEConv(nn.Module):
         x_src, x_dst = (x, x) if isinstance(x, torch.Tensor) else x
         if graph is None:
             graph = build_edge_csr(edge_index, x_src.shape[0], x_dst.shape[0])
-        lazy = isinstance(self.lin_l, nn.LazyLinear) and self.lin_l.has_uninitialized_params()
+        lazy = (isinstance(self.lin_l, nn.LazyLinear) and self.lin_l.has_uninitialized_params()) or \
+            (self.root_weight and isinstance(self.lin_r, nn.LazyLinear) and self.lin_r.has_uninitialized_params())
+        if (FUSED_SAGE and not lazy and not self.project_first and not self.normalize and self.aggr in ("add", "sum", "mean")
+                and x_src.dtype == torch.float32 and _lib.on_device(x_src) and (not self.root_weight or x_dst is not None)):
+            return _SageFn.apply(x_src, x_dst if self.root_weight else None, self.lin_l.weight, self.lin_l.bias,
+                                 self.lin_r.weight if self.root_weight else None, graph, self.aggr == "mean")
         if (self.project_first and not lazy and self.aggr in ("add", "sum", "mean")
                 and self.lin_l.out_features < self.lin_l.in_features):
             out = aggregate(F.linear(x_src, self.lin_l.weight), graph, self.aggr)
