@@ -110,17 +110,48 @@ def epoch_bytes(nnz: int, N: int, d: int, K: int, B: int) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock, power and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  Read through NVML from a
+    thread of this process (pynvml, one query every 25 ms, ~0.1 ms each): an `nvidia-smi -lms` child process was measured to
+    slow launch-bound steps down by up to 2x while it polls (its start-up and every poll take driver locks) -- it remains the
+    fallback when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.samples, self.first, self._stop, self.smax = index, [], None, [], 0, False, None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                                   # CUDA_VISIBLE_DEVICES may renumber: address the device by its PCI bus id
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
-        """Launch the sampler and wait for its first line: nvidia-smi's own start-up (process + NVML initialisation, driver
-        locks) must be over BEFORE the timed region -- it perturbs launch-bound steps by milliseconds otherwise."""
+        try:
+            nv, h = self._nvml_handle()
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+
+            def loop():
+                while not self._stop:
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), [n for b, n in names.items() if mask & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.025)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.mode = "nvml"
+            return
+        except Exception:
+            self.mode = "nvidia-smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -133,19 +164,26 @@ class ClockSampler:
 
     def mark(self):
         """Samples taken from here on belong to the timed region."""
-        self.first = len(self.lines)
+        self.first = len(self.samples) if getattr(self, "mode", "") == "nvml" else len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "mode", "") == "nvml":
+            time.sleep(0.03)
+            self._stop = True
+            got = self.samples[max(self.first - 1, 0):]             # the sample that straddles the start counts too
+            sm = [c for c, _ in got]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted({r for _, rs in got for r in rs}), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        lines = self.lines[max(getattr(self, "first", 0) - 1, 0):]        # the sample that straddles the start counts too
+        lines = self.lines[max(self.first - 1, 0):]
         for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -158,7 +196,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
