@@ -43,6 +43,44 @@ class CUDA:
         return torch.device("cuda", local)
 
 
+_ORIG_AFFINITY = None
+
+
+def unpin_cpus():
+    """Give the process all its CPUs back (before the CPU baseline, which uses every host core)."""
+    if _ORIG_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _ORIG_AFFINITY)
+        except Exception:
+            pass
+
+
+def pin_to_gpu_cpus(local: int):
+    """Run this process on the CPUs that are local to its GPU (sysfs `local_cpulist` of the PCI device, intersected with the
+    CPUs the container may use).  The launch-bound steps (ranking model on small batches, ML-1M-sized graphs) are host-dispatch
+    bound: on a two-socket box a process that lands on the far socket pays every kernel launch across the socket link.
+    Returns a short description for the JSON line; never raises."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        global _ORIG_AFFINITY
+        _ORIG_AFFINITY = set(allowed)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return {"gpu_local_cpus": txt, "allowed": len(allowed), "pinned_to": len(use)}
+        return {"gpu_local_cpus": txt, "allowed": len(allowed), "pinned_to": None if use else "no local CPU is available to this process"}
+    except Exception as exc:
+        return {"error": repr(exc)[:120]}
+
+
 WORKLOADS = {
     # name: (U, I, E)  -- BASELINE.json configs[2] (H&M-shaped) and configs[1] (MovieLens-1M-shaped)
     "hm": (1_371_980, 105_542, 31_788_324),
@@ -348,6 +386,7 @@ def run_ours(args):
     if not CUDA.available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     dev = CUDA.device(local)
+    affinity = pin_to_gpu_cpus(local) if dev.type == "cuda" else None
     if world > 1:
         dist.init_process_group(CUDA.backend, **({"device_id": dev} if CUDA.backend == "nccl" else {}))
     if world != args.gpus:
@@ -601,6 +640,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        unpin_cpus()
         torch.set_num_threads(os.cpu_count() or 1)
         Us, Is, Es = (x // CPU_SAMPLE_SCALE for x in WORKLOADS[args.workload])
         cstep, cnnz = cpu_epoch_runner(Us, Is, Es, d, K, B, args.degree, 1234)
@@ -617,6 +657,7 @@ def run_ours(args):
 
     if rank == 0:
         line = base_line(args, value, ms, nnz)
+        line["config"]["cpu_affinity"] = affinity
         line["config"]["spmm_variant"] = tuned if tuned is not None else "default (autotune off)"
         if exchange is not None:
             line["exchange"] = exchange
@@ -707,6 +748,7 @@ def run_hetero(args):
     if not CUDA.available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     dev = CUDA.device(local)
+    affinity = pin_to_gpu_cpus(local) if dev.type == "cuda" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus:
@@ -750,13 +792,18 @@ def run_hetero(args):
     launches0 = _lib.LAUNCHES
     sync()
     t0, t1 = CUDA.event(), CUDA.event()
+    marks = [CUDA.event() for _ in range(args.steps)]          # one event per step: median / max next to the contract's mean
     t0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         loss = step()
-    t1.record()
+        marks[i].record()
+    t1 = marks[-1] if marks else t1
+    if not marks:
+        t1.record()
     sync()
     DeviceCSR.spmm = orig
     launches = _lib.LAUNCHES - launches0
+    per_step = [a.elapsed_time(b) for a, b in zip([t0] + marks[:-1], marks)]
     clk = clocks.stop() if rank == 0 else None
     ms = torch.tensor([t0.elapsed_time(t1) / max(args.steps, 1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -806,6 +853,7 @@ def run_hetero(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        unpin_cpus()
         torch.set_num_threads(os.cpu_count() or 1)
         csize = "hetero_s"                                   # bounded sample: the S batch whatever size the GPU arm ran
         cstep = hetero_cpu_step_runner(csize, args.hetero_aggr, model.state_dict(), metadata)
@@ -820,8 +868,12 @@ def run_hetero(args):
                                                               "warm-up; oracle port (index_add scatter, torch Linear, autograd)"}
     if rank == 0:
         line = hetero_line(args, value, ms)
+        line["config"]["cpu_affinity"] = affinity
         line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                     "loss": float(loss.detach())})
+                     "loss": float(loss.detach()),
+                     "per_step_ms": {"median": statistics.median(per_step), "min": min(per_step), "max": max(per_step),
+                                     "note": "this step is bound by host dispatch on the S / M batches: the mean (ms_per_step, the "
+                                             "contract's number) moves with the host, the median is the steadier figure"} if per_step else None})
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
