@@ -136,8 +136,9 @@ def lookup_traffic(workload, degree, d, n_gpus, plan):
         return None
     for c in caps:
         if (c["workload"], c["degree"], c["d"], c["n_gpus"]) == (workload, degree, d, n_gpus) and plan is not None and \
-                (c["variant"], c["chunk"], bool(c["degree_order"]), int(c.get("hot_rows", 0))) == \
-                (plan.get("variant"), plan.get("chunk"), bool(plan.get("degree_order")), int(plan.get("hot_rows", 0))):
+                (c["variant"], c["chunk"], bool(c["degree_order"]), int(c.get("hot_rows", 0)), bool(c.get("sweep", False))) == \
+                (plan.get("variant"), plan.get("chunk"), bool(plan.get("degree_order")), int(plan.get("hot_rows", 0)),
+                 bool(plan.get("sweep", False))):
             return c
     return None
 
@@ -416,8 +417,9 @@ def run_ours(args):
             try:
                 # slice sizes: the CTA-wide-slice variants (16, 19, 20-25) walk a slice with four warps, so plan slices of
                 # 2048 / 4096 entries keep their per-warp chain at 512 / 1024 while quartering the partial rows of stage 2
-                g.autotune(d, chunks=(4096, 2048, 1024, 512), degree_orders=(False, True))
-                gt.autotune(d, chunks=(4096, 2048, 1024, 512), degree_orders=(False, True))
+                # sweeps: long-row slices in plan order or sorted by first column (csr.py use_sweep_order)
+                g.autotune(d, chunks=(4096, 2048, 1024, 512), degree_orders=(False, True), sweeps=(False, True))
+                gt.autotune(d, chunks=(4096, 2048, 1024, 512), degree_orders=(False, True), sweeps=(False, True))
                 tuned = {"forward": g.autotune_report.get("chosen"), "backward": gt.autotune_report.get("chosen"),
                          "forward_ms": g.autotune_report["ms"], "backward_ms": gt.autotune_report["ms"],
                          "rejected": {**g.autotune_report["rejected"], **gt.autotune_report["rejected"]}}
@@ -570,7 +572,8 @@ def run_ours(args):
     plan = None
     if world == 1:        # the plan the forward launches ran with (autotune's choice, or the env / flag defaults)
         plan = {"variant": g.variant if g.variant is not None else int(os.environ.get("LGB_SPMM_VARIANT", "0")),
-                "chunk": g.chunk, "degree_order": g.row_order is not None, "hot_rows": int(getattr(g, "n_hot", 0))}
+                "chunk": g.chunk, "degree_order": g.row_order is not None, "hot_rows": int(getattr(g, "n_hot", 0)),
+                "sweep": bool(getattr(g, "sweep", False))}
     cap = lookup_traffic(args.workload, args.degree, d, world, plan)
     traffic = cap["dram_bytes_per_call"] if cap else None
     floor = spmm_floor_bytes(spmm_events[0][2], spmm_events[0][3], d) if spmm_events else None
@@ -794,7 +797,15 @@ def run_hetero(args):
     t0, t1 = CUDA.event(), CUDA.event()
     marks = [CUDA.event() for _ in range(args.steps)]          # one event per step: median / max next to the contract's mean
     import gc
-    gc.collect(); gc.disable()                                  # no cyclic-GC pause inside the timed region of a host-bound step
+    # A full (generation-2) collection walks every object torch and the bench have alive -- tens of ms for a 2 ms host-bound
+    # step.  gc.freeze() moves what exists now out of the collector's reach (the production recipe for long-running servers);
+    # the collector itself stays ON, so garbage the steps create is still collected.  LGB_BENCH_GC=default|disable to compare.
+    gc_mode = os.environ.get("LGB_BENCH_GC", "freeze")
+    gc.collect()
+    if gc_mode == "freeze":
+        gc.freeze()
+    elif gc_mode == "disable":
+        gc.disable()
     t0.record()
     for i in range(args.steps):
         loss = step()
@@ -804,6 +815,8 @@ def run_hetero(args):
         t1.record()
     sync()
     gc.enable()
+    if gc_mode == "freeze":
+        gc.unfreeze()
     DeviceCSR.spmm = orig
     launches = _lib.LAUNCHES - launches0
     per_step = [a.elapsed_time(b) for a, b in zip([t0] + marks[:-1], marks)]
@@ -872,9 +885,11 @@ def run_hetero(args):
     if rank == 0:
         line = hetero_line(args, value, ms)
         line["config"]["cpu_affinity"] = affinity
+        line["config"]["gc"] = gc_mode
         line.update({"clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                      "loss": float(loss.detach()),
                      "per_step_ms": {"median": statistics.median(per_step), "min": min(per_step), "max": max(per_step),
+                                     "steps_over_5x_median": sum(1 for x in per_step if x > 5 * statistics.median(per_step)),
                                      "note": "this step is bound by host dispatch on the S / M batches: the mean (ms_per_step, the "
                                              "contract's number) moves with the host, the median is the steadier figure"} if per_step else None})
         print(json.dumps(line), flush=True)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LGB_ABI_VERSION 3
+#define LGB_ABI_VERSION 4
 
 enum {
   LGB_OK = 0,
@@ -127,6 +127,11 @@ typedef struct lgb_csr {
   const int32_t* seg_t1;
   const int32_t* row_seg0;
   int64_t n_seg;
+  /* execution order of the long-row slices (optional): the CTA / warp with slice slot i runs slice task_exec[i] (a permutation of
+   * 0..n_tasks-1); NULL = plan order (row by row).  Partial sums stay indexed by slice id, so stage 2 and the summation order of
+   * every row -- hence the result, bit for bit -- do not depend on it.  The host plan sorts the slices by their first column
+   * ("column sweep"): slices of different long rows that gather the same operand rows run next to each other and find them in L2. */
+  const int32_t* task_exec;  /* [n_tasks] */
 } lgb_csr;
 
 /* ---------------------------------------------------------------------------------------------

@@ -21,6 +21,8 @@ SPMM_VARIANT = int(os.environ.get("LGB_SPMM_VARIANT", "0"))
 # rows with more non-zeros are split into chunk-sized slices (csrc/spmm.cu): bounds the length of any sequential fp32
 # accumulation chain (accuracy) and the work of one warp (load balance)
 DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
+# execute long-row slices in column-sweep order by default (DeviceCSR.use_sweep_order; autotune decides per graph when it runs)
+DEFAULT_SWEEP = os.environ.get("LGB_SPMM_SWEEP", "0") == "1"
 STAGE2_SEG = 32                                                   # partial rows per warp of the stage-2 tree
 STAGE2_TREE = os.environ.get("LGB_SPMM_STAGE2", "tree") != "flat"  # flat = one CTA per long row (the round-1 stage 2), for A/B
 
@@ -74,6 +76,8 @@ class DeviceCSR:
         self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
         self.n_seg = 0
         self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = None
+        self.sweep = DEFAULT_SWEEP                         # execute the long-row slices in column-sweep order: use_sweep_order()
+        self.task_exec: Optional[torch.Tensor] = None
         self.perm: Optional[torch.Tensor] = None      # COO -> CSR permutation (int64) when built from COO
         self.csr2csc: Optional[torch.Tensor] = None   # set on the TRANSPOSED graph: its entry i is CSR entry csr2csc[i]
         self._t: Optional["DeviceCSR"] = None
@@ -147,7 +151,25 @@ class DeviceCSR:
                                              ptr(self.task_start), ptr(self.task_end), ptr(ws), ws.numel(), stream()),
                       "spmm_plan_fill")
                 self._build_segments()
+        self._build_sweep()
         self._struct = None
+
+    def use_sweep_order(self, on: bool = True) -> "DeviceCSR":
+        """Execute the long-row slices sorted by their first column instead of row by row.  Rows are stored with ascending
+        columns, so a slice covers a narrow column range; in sweep order the slices of ALL long rows that gather the same band
+        of operand rows run next to each other, and the band is fetched from DRAM once instead of once per long row (the
+        351 MB user table of the H&M-shaped item rows does not fit the 126 MB L2).  Results are bit-identical: partial sums
+        stay indexed by slice id."""
+        self.sweep = bool(on)
+        self._build_sweep()
+        self._struct = None
+        return self
+
+    def _build_sweep(self) -> None:
+        self.task_exec = None
+        if self.sweep and self.n_tasks > 1:
+            first = self.colidx[self.task_start.long()]
+            self.task_exec = torch.argsort(first, stable=True).to(torch.int32)
 
     def _build_segments(self) -> None:
         """Stage-2 tree plan: the partial rows of every long row cut into segments of 32 (one warp each, csrc/spmm.cu
@@ -182,10 +204,10 @@ class DeviceCSR:
 
     # ---- plan-time kernel selection --------------------------------------------------------
     def autotune(self, d: int, candidates=None, reps: int = 5, fused_epilogue: bool = True, chunks=None,
-                 degree_orders=(False,), hot=None) -> int:
+                 degree_orders=(False,), hot=None, sweeps=(False,)) -> int:
         """Pick the fastest lgb_spmm configuration for THIS graph and width on THIS device (one-off, like an FFT plan):
         kernel variant x slice size of the long-row plan (``chunks``, default: the current one) x row processing order
-        (``degree_orders``).  Every configuration is first checked against the first one's result on random data (one that
+        (``degree_orders``) x slice execution order (``sweeps``, see use_sweep_order).  Every configuration is first checked against the first one's result on random data (one that
         disagrees beyond fp32 summation-order noise is dropped and reported), then timed with CUDA events over the call
         shape the LightGCN layers use (Y + fused accumulate).  The winner is installed on the graph (plan, row order,
         ``self.variant``) and used by every later ``spmm`` that does not name a variant.  Returns the chosen variant."""
@@ -200,11 +222,14 @@ class DeviceCSR:
             chunks = (self.chunk,)
         dev = self.device
         report = {"d": d, "ms": {}, "rejected": {}}
-        n_configs = len(candidates) * len(chunks) * len(degree_orders)
+        sweeps = tuple(bool(x) for x in sweeps) or (False,)
+        n_configs = len(candidates) * len(chunks) * len(degree_orders) * len(sweeps)
         if self.n_rows == 0 or self.nnz == 0 or n_configs <= 1:
             self.variant = candidates[0][0] if candidates else None
             self.set_hot(candidates[0][1] if candidates else 0)
-            report["chosen"] = {"variant": self.variant, "chunk": self.chunk, "degree_order": self.row_order is not None}
+            self.use_sweep_order(sweeps[0])
+            report["chosen"] = {"variant": self.variant, "chunk": self.chunk, "degree_order": self.row_order is not None,
+                                "sweep": self.sweep}
             self.autotune_report = report
             return self.variant
         gen = torch.Generator(device=dev).manual_seed(1234)
@@ -213,38 +238,44 @@ class DeviceCSR:
         Y = torch.empty(self.n_rows, d, device=dev)
         out = torch.empty(self.n_rows, d, device=dev) if fused_epilogue else None
         ref = ref_mag = None
-        best, best_ms = (chunks[0], bool(degree_orders[0]), candidates[0]), float("inf")
+        best, best_ms = (chunks[0], bool(degree_orders[0]), candidates[0], sweeps[0]), float("inf")
         for chunk in chunks:
             self._set_chunk(chunk)
             for order in degree_orders:
                 self.use_degree_order(bool(order))
-                for cand in candidates:
-                    v, n_hot = cand
-                    key = f"v{v}" + (f"h{n_hot}" if n_hot else "") + (f"/chunk{chunk}" if len(chunks) > 1 else "") + ("/degree-order" if order else "")
-                    try:
-                        self.set_hot(n_hot)
-                        run = (lambda: self.spmm(X, Y=Y, acc_in=acc, acc_out=out, variant=v)) if fused_epilogue else (lambda: self.spmm(X, Y=Y, variant=v))   # noqa: E731
-                        run()
-                        if ref is None:
-                            ref = Y.clone()
-                            ref_mag = float(ref.abs().max()) + 1e-30
-                        else:
-                            err = float((Y - ref).abs().max())
-                            if not err <= 1e-4 * ref_mag:            # also catches NaN
-                                report["rejected"][key] = f"max |diff| {err:.3e} vs magnitude {ref_mag:.3e}"
-                                continue
-                        ms = _time_ms(run, reps, dev)
-                    except RuntimeError as exc:                       # a variant that is not available for this shape
-                        report["rejected"][key] = str(exc)[:200]
-                        continue
-                    report["ms"][key] = ms
-                    if ms < best_ms:
-                        best, best_ms = (chunk, bool(order), cand), ms
+                for sweep in sweeps:
+                    if sweep and self.n_tasks <= 1 and len(sweeps) > 1:
+                        continue                                          # nothing to reorder: same launch as sweep off
+                    self.use_sweep_order(sweep)
+                    for cand in candidates:
+                        v, n_hot = cand
+                        key = (f"v{v}" + (f"h{n_hot}" if n_hot else "") + (f"/chunk{chunk}" if len(chunks) > 1 else "")
+                               + ("/degree-order" if order else "") + ("/sweep" if sweep else ""))
+                        try:
+                            self.set_hot(n_hot)
+                            run = (lambda: self.spmm(X, Y=Y, acc_in=acc, acc_out=out, variant=v)) if fused_epilogue else (lambda: self.spmm(X, Y=Y, variant=v))   # noqa: E731
+                            run()
+                            if ref is None:
+                                ref = Y.clone()
+                                ref_mag = float(ref.abs().max()) + 1e-30
+                            else:
+                                err = float((Y - ref).abs().max())
+                                if not err <= 1e-4 * ref_mag:            # also catches NaN
+                                    report["rejected"][key] = f"max |diff| {err:.3e} vs magnitude {ref_mag:.3e}"
+                                    continue
+                            ms = _time_ms(run, reps, dev)
+                        except RuntimeError as exc:                       # a variant that is not available for this shape
+                            report["rejected"][key] = str(exc)[:200]
+                            continue
+                        report["ms"][key] = ms
+                        if ms < best_ms:
+                            best, best_ms = (chunk, bool(order), cand, sweep), ms
         self._set_chunk(best[0])
         self.use_degree_order(best[1])
+        self.use_sweep_order(best[3])
         self.set_hot(best[2][1])
         self.variant, self.autotune_report = best[2][0], report
-        report["chosen"] = {"variant": best[2][0], "chunk": best[0], "degree_order": best[1]}
+        report["chosen"] = {"variant": best[2][0], "chunk": best[0], "degree_order": best[1], "sweep": best[3]}
         if best[2][1]:
             report["chosen"].update(hot_rows=best[2][1], hot_share=round(getattr(self, "hot_share", 0.0), 4))
         return self.variant
@@ -254,7 +285,7 @@ class DeviceCSR:
         if int(chunk) != self.chunk:
             self.chunk = int(chunk)
             self.n_long = self.n_tasks = self.n_seg = 0
-            self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
+            self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = self.task_exec = None
             self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = None
             if self.chunk > 0:
                 self._build_plan()
@@ -318,6 +349,8 @@ class DeviceCSR:
         t.csr2csc = csr2csc
         if self.row_order is not None:
             t.use_degree_order()
+        if self.sweep:
+            t.use_sweep_order()
         t._t = self
         self._t = t
         return t
@@ -349,6 +382,7 @@ class DeviceCSR:
             s.colidx_hot, s.hot_cols, s.n_hot = ptr(self.colidx_hot), ptr(self.hot_cols), int(self.n_hot)
             s.seg_row, s.seg_t0, s.seg_t1, s.row_seg0 = ptr(self.seg_row), ptr(self.seg_t0), ptr(self.seg_t1), ptr(self.row_seg0)
             s.n_seg = int(self.n_seg)
+            s.task_exec = ptr(self.task_exec)
             self._struct = s
         return self._struct
 

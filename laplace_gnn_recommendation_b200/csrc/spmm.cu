@@ -56,6 +56,7 @@ struct SpmmParams {
   int64_t n_seg;
   float* part2;        // [n_seg, d] level-2 partial rows
   int* tickets;        // [n_long], zero between launches
+  const int32_t* task_exec;   // [n_tasks] execution order of the slices (NULL = plan order); partial rows stay indexed by slice id
 };
 
 // STEP = distance between the 32-entry batches this warp takes (32: the whole range; 32*SPMM_WARPS: every SPMM_WARPS-th
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     if ((int64_t)blockIdx.x < p.n_tasks) {   // one CTA per slice
       __shared__ float4 wsum[SPMM_WARPS][G * VPL];
       const int wi = threadIdx.x >> 5;
-      const int64_t t = blockIdx.x;
+      const int64_t t = p.task_exec ? p.task_exec[blockIdx.x] : (int64_t)blockIdx.x;
       const int s = p.task_start[t], e = p.task_end[t];
       float4 acc[VPL];
 #pragma unroll
@@ -467,13 +468,14 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     float4 acc[VPL];
 #pragma unroll
     for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
-    const int s = p.task_start[w], e = p.task_end[w];
+    const int64_t t = p.task_exec ? p.task_exec[w] : w;
+    const int s = p.task_start[t], e = p.task_end[t];
     accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256>(p, s, e, lane, acc);
     if (lane < G) {
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
         const int f = W256 ? lane * VPL + q : lane + q * G;
-        if (f < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)w * d4 + f, acc[q]);
+        if (f < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)t * d4 + f, acc[q]);
       }
     }
     return;
@@ -1302,6 +1304,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   p.n_seg = (g->chunk > 0 && g->seg_row && g->seg_t0 && g->seg_t1 && g->row_seg0 && (flags & LGB_SPMM_TREE_WS)) ? g->n_seg : 0;
   p.part2 = p.n_seg > 0 && partial_ws ? partial_ws + (size_t)p.n_tasks * d + 64 : nullptr;
   p.tickets = p.part2 ? reinterpret_cast<int*>(p.part2 + (size_t)p.n_seg * d) : nullptr;
+  p.task_exec = p.n_tasks > 0 ? g->task_exec : nullptr;
   if (p.n_tasks > 0) {
     LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->task_end && g->long_rows && g->long_ptr, LGB_EINVAL,
                 "lgb_spmm: plan has %lld tasks but plan arrays (task_row/start/end, long_rows/ptr) / partial workspace missing",

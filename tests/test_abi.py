@@ -36,12 +36,12 @@ def test_header_symbols_exported(lib):
 def test_ctypes_table_matches_header(lib):
     from laplace_gnn_recommendation_b200 import _lib
     assert sorted(_lib.PROTOTYPES) == declared_functions()
-    assert lib.lgb_abi_version() == 3
+    assert lib.lgb_abi_version() == 4
 
 
 def test_struct_layouts():
     from laplace_gnn_recommendation_b200._lib import LgbBprArgs, LgbCsr
-    assert C.sizeof(LgbCsr) == 3 * 8 + 4 * 8 + 8 + 2 * 8 + 5 * 8 + 2 * 8 + 8 + 4 * 8 + 8      # mirrors struct lgb_csr (ABI 2: + hot-column plan, ABI 3: + stage-2 segments)
+    assert C.sizeof(LgbCsr) == 3 * 8 + 4 * 8 + 8 + 2 * 8 + 5 * 8 + 2 * 8 + 8 + 4 * 8 + 8 + 8  # mirrors struct lgb_csr (ABI 2: + hot-column plan, ABI 3: + stage-2 segments, ABI 4: + task_exec)
     assert C.sizeof(LgbBprArgs) == 9 * 8 + 8 + 8 + 4 * 4 + 2 * 8 + 8 + 6 * 8 + 2 * 8            # mirrors struct lgb_bpr_args
 
 

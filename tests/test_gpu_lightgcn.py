@@ -116,6 +116,31 @@ def test_spmm_vs_oracle(cuda_dev, d, chunk, variant=None):
     spmm_close(gt.spmm(X.to(cuda_dev), variant=variant), colptr, r, val.cpu()[csr2csc], X, sequential=seq)
 
 
+@pytest.mark.parametrize("variant", [0, 16, 20, 23])
+def test_spmm_sweep_order_bit_identical(cuda_dev, variant):
+    """Long-row slices executed in column-sweep order (lgb_csr.task_exec) give the same bits as plan order: partial sums are
+    indexed by slice id, only the CTA -> slice assignment changes."""
+    n, nnz, d = 400, 30000, 64
+    row, col = random_graph(11, n, n, nnz, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
+    _, val = g.gcn_norm()
+    g = g.with_values(val)
+    assert g.n_tasks > 10
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(2)).to(cuda_dev)
+    y0 = g.spmm(X, variant=variant)
+    g.use_sweep_order(True)
+    ex = g.task_exec.long().cpu()
+    assert torch.equal(torch.sort(ex).values, torch.arange(g.n_tasks))          # a permutation ...
+    first = g.colidx.cpu()[g.task_start.cpu().long()][ex]
+    assert bool((first[1:] >= first[:-1]).all()) and not torch.equal(ex, torch.arange(g.n_tasks))   # ... sorted by first column
+    y1 = g.spmm(X, variant=variant)
+    assert torch.equal(y0, y1)
+    gt = g.transpose()                                                           # the transposed plan inherits the order
+    assert gt.sweep and gt.task_exec is not None
+    g.use_sweep_order(False)
+    assert g.task_exec is None and torch.equal(g.spmm(X, variant=variant), y0)
+
+
 def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
     n, nnz, d = 500, 20000, 64
     row, col = random_graph(5, n, n, nnz, skew=True)

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--variants", default="1,3,6")
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--workload", default="hm")
+    ap.add_argument("--chunks", default="", help="slice sizes of the long-row plan to walk (default: the library default)")
+    ap.add_argument("--sweep", default="0", help="comma list of 0/1: long-row slices in plan order / column-sweep order")
     a = ap.parse_args()
     dev = _common.device()
     U, I, E = WORKLOADS[a.workload]
@@ -35,15 +37,22 @@ def main():
     X = torch.randn(N, d, device=dev); Y = torch.empty(N, d, device=dev); acc = torch.randn(N, d, device=dev)
     print(f"graph: nnz={g.nnz} n_long={g.n_long} n_tasks={g.n_tasks} | users view nnz={gu.nnz} long={gu.n_long} tasks={gu.n_tasks}"
           f" | items view nnz={gi.nnz} long={gi.n_long} tasks={gi.n_tasks}")
-    for v in [int(x) for x in a.variants.split(",")]:
-        t_full = timeit(lambda: g.spmm(X, Y=Y, acc_in=acc, acc_out=acc, variant=v))
-        t_plain = timeit(lambda: g.spmm(X, Y=Y, variant=v))
-        t_u = timeit(lambda: gu.spmm(X, Y=Y[:U], variant=v))
-        t_i = timeit(lambda: gi.spmm(X, Y=Y[U:], variant=v))
-        gb = spmm_bytes(g.nnz, N, d) / 1e9
-        print(f"variant {v}: full+acc {t_full:.3f} ms | plain {t_plain:.3f} ms ({gb / t_plain:.0f} GB/s alg) | "
-              f"user rows {t_u:.3f} ms ({spmm_bytes(gu.nnz, U, d) / 1e6 / t_u:.0f} GB/s) | "
-              f"item rows {t_i:.3f} ms ({spmm_bytes(gi.nnz, I, d) / 1e6 / t_i:.0f} GB/s)")
+    chunks = [int(x) for x in a.chunks.split(",")] if a.chunks else [g.chunk]
+    for chunk in chunks:
+        for sweep in [bool(int(x)) for x in a.sweep.split(",")]:
+            for h in (g, gu, gi):
+                h._set_chunk(chunk)
+                h.use_sweep_order(sweep)
+            tag = f"chunk {chunk} sweep {int(sweep)} (item-view tasks {gi.n_tasks})"
+            for v in [int(x) for x in a.variants.split(",")]:
+                t_full = timeit(lambda: g.spmm(X, Y=Y, acc_in=acc, acc_out=acc, variant=v))
+                t_plain = timeit(lambda: g.spmm(X, Y=Y, variant=v))
+                t_u = timeit(lambda: gu.spmm(X, Y=Y[:U], variant=v))
+                t_i = timeit(lambda: gi.spmm(X, Y=Y[U:], variant=v))
+                gb = spmm_bytes(g.nnz, N, d) / 1e9
+                print(f"{tag} variant {v}: full+acc {t_full:.3f} ms | plain {t_plain:.3f} ms ({gb / t_plain:.0f} GB/s alg) | "
+                      f"user rows {t_u:.3f} ms ({spmm_bytes(gu.nnz, U, d) / 1e6 / t_u:.0f} GB/s) | "
+                      f"item rows {t_i:.3f} ms ({spmm_bytes(gi.nnz, I, d) / 1e6 / t_i:.0f} GB/s)", flush=True)
 
 
 if __name__ == "__main__":
