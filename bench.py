@@ -800,7 +800,7 @@ def run_hetero(args):
     # A full (generation-2) collection walks every object torch and the bench have alive -- tens of ms for a 2 ms host-bound
     # step.  gc.freeze() moves what exists now out of the collector's reach (the production recipe for long-running servers);
     # the collector itself stays ON, so garbage the steps create is still collected.  LGB_BENCH_GC=default|disable to compare.
-    gc_mode = os.environ.get("LGB_BENCH_GC", "freeze")
+    gc_mode = os.environ.get("LGB_BENCH_GC", "default")
     gc.collect()
     if gc_mode == "freeze":
         gc.freeze()

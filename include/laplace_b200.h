@@ -263,6 +263,14 @@ int lgb_edge_dot_fwd(const float* zu, const float* zi, const int64_t* row, const
 int lgb_edge_dot_bwd(const float* zu, const float* zi, const int64_t* row, const int64_t* col,
                      const float* gout, int64_t L, int32_t d, float* dzu_zeroed, float* dzi_zeroed,
                      void* stream);
+/* Inference form of the reference's two-layer decoder (model/encoder_decoder.py:55-72 with the default layers of
+ * model/layers.py:35-56: Linear(du+di -> H), relu, Linear(H -> 1)) when dropout is off: because the first Linear acts on a
+ * concatenation, W1 [zu[r] ; zi[c]] + b1 = pu[r] + pi[c] with the per-NODE projections pu = zu W1[:, :du]^T + b1 and
+ * pi = zi W1[:, du:]^T (two library GEMMs over the nodes instead of one over the label edges), and
+ *   out[e] = b2 + sum_h w2[h] * relu(pu[row[e], h] + pi[col[e], h]).
+ * Forward only (training-mode dropout acts on the per-edge concatenation, so the training step keeps the concat form). */
+int lgb_edge_mlp2_fwd(const float* pu, const float* pi, const int64_t* row, const int64_t* col, int64_t L, int32_t H,
+                      const float* w2, const float* b2, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Weight / bias gradient of a Linear layer over many rows and few features -- the AddmmBackward of SAGEConv's

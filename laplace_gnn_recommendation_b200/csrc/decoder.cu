@@ -96,6 +96,36 @@ edge_dot_bwd_kernel(const float* __restrict__ zu, const float* __restrict__ zi, 
   }
 }
 
+// Inference form of the two-layer concat-MLP decoder: out[e] = b2 + sum_h w2[h] * relu(pu[row[e], h] + pi[col[e], h]), pu / pi
+// the per-node halves of the first Linear (bias folded into pu by the caller).  One warp per label edge, one 128-bit load per
+// lane and 32 * 4 hidden units per step (H = 128: exactly one step), shuffle butterfly for the final sum.
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+edge_mlp2_fwd_kernel(const float* __restrict__ pu, const float* __restrict__ pi, const int64_t* __restrict__ row,
+                     const int64_t* __restrict__ col, int64_t L, int H, const float* __restrict__ w2,
+                     const float* __restrict__ b2, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * DEC_WARPS + (threadIdx.x >> 5);
+  if (e >= L) return;
+  const int64_t r = row[e], c = col[e];
+  float acc = 0.f;
+  if ((H & 3) == 0) {
+    const float4* a = (const float4*)(pu + r * H);
+    const float4* b = (const float4*)(pi + c * H);
+    const float4* w = (const float4*)w2;
+    for (int f = lane; f < H / 4; f += 32) {
+      const float4 x = ld_gather_f4(a + f), y = ld_gather_f4(b + f), ww = w[f];
+      acc = fmaf(ww.x, fmaxf(x.x + y.x, 0.f), acc);
+      acc = fmaf(ww.y, fmaxf(x.y + y.y, 0.f), acc);
+      acc = fmaf(ww.z, fmaxf(x.z + y.z, 0.f), acc);
+      acc = fmaf(ww.w, fmaxf(x.w + y.w, 0.f), acc);
+    }
+  } else {
+    for (int f = lane; f < H; f += 32) acc = fmaf(w2[f], fmaxf(pu[r * H + f] + pi[c * H + f], 0.f), acc);
+  }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, off);
+  if (lane == 0) out[e] = acc + (b2 ? b2[0] : 0.f);
+}
+
 static inline unsigned edge_blocks(int64_t L) { return (unsigned)((L + DEC_WARPS - 1) / DEC_WARPS); }
 
 }  // namespace lgb
@@ -138,6 +168,17 @@ int lgb_edge_dot_bwd(const float* zu, const float* zi, const int64_t* row, const
   LGB_REQUIRE(L >= 0 && d > 0 && (L == 0 || (zu && zi && row && col && gout)), LGB_EINVAL, "lgb_edge_dot_bwd: bad argument");
   if (L == 0 || (!dzu && !dzi)) return LGB_OK;
   edge_dot_bwd_kernel<<<edge_blocks(L), DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(zu, zi, row, col, gout, L, d, dzu, dzi);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
+int lgb_edge_mlp2_fwd(const float* pu, const float* pi, const int64_t* row, const int64_t* col, int64_t L, int32_t H,
+                      const float* w2, const float* b2, float* out, void* stream) {
+  LGB_REQUIRE(L >= 0 && H > 0 && (L == 0 || (pu && pi && row && col && w2 && out)), LGB_EINVAL, "lgb_edge_mlp2_fwd: bad argument");
+  LGB_REQUIRE((H & 3) != 0 || ((((uintptr_t)pu | (uintptr_t)pi | (uintptr_t)w2) & 15) == 0), LGB_EINVAL,
+              "lgb_edge_mlp2_fwd: pu / pi / w2 must be 16-byte aligned when H %% 4 == 0");
+  if (L == 0) return LGB_OK;
+  edge_mlp2_fwd_kernel<<<edge_blocks(L), DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(pu, pi, row, col, L, H, w2, b2, out);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
 }

@@ -530,21 +530,65 @@ def edge_dot(zu, zi, row, col):
     return _EdgeDot.apply(zu, zi, row, col)
 
 
+def edge_mlp2_inference(zu, zi, row, col, lin1, lin2) -> torch.Tensor:
+    """Two-layer concat-MLP decoder without the per-edge concatenation (forward only, dropout off): the first Linear is applied
+    to the NODES (``pu = zu W1[:, :du]^T + b1``, ``pi = zi W1[:, du:]^T``, two cuBLAS GEMMs), then lgb_edge_mlp2_fwd evaluates
+    ``b2 + w2 . relu(pu[row] + pi[col])`` per label edge.  Same function as model/encoder_decoder.py:55-72 in eval mode, other
+    fp32 summation order (rtol 1e-5 against the concat form, tests)."""
+    zu, zi, row, col = _lib.f32c(zu), _lib.f32c(zi), _lib.i64c(row), _lib.i64c(col)
+    _lib.require_cuda(zu, zi, row, col)
+    du = zu.shape[1]
+    W1, b1 = lin1.weight.detach(), lin1.bias
+    pu = torch.addmm(b1.detach(), zu, W1[:, :du].t()) if b1 is not None else zu @ W1[:, :du].t()
+    pi = zi @ W1[:, du:].t()
+    L, H = row.numel(), W1.shape[0]
+    out = torch.empty(L, dtype=torch.float32, device=zu.device)
+    w2 = lin2.weight.detach().reshape(-1).contiguous()
+    b2 = lin2.bias.detach() if lin2.bias is not None else None
+    with torch.cuda.device(zu.device):
+        check(_lib.load().lgb_edge_mlp2_fwd(ptr(pu), ptr(pi), ptr(row), ptr(col), L, H, ptr(w2), ptr(b2), ptr(out), stream()),
+              "edge_mlp2_fwd")
+    _lib.count_launch()
+    return out
+
+
 class EdgeDecoder(nn.Module):
     """model/encoder_decoder.py:49-72.  ``mode="mlp"`` is the reference (concat -> [dropout -> Linear -> relu]* ->
     Linear -> view(-1)); ``mode="dot"`` is the dot-product decoder of north_star (layers unused)."""
 
-    def __init__(self, layers: ModuleList, p_dropout_features: Optional[float], mode: str = "mlp"):
+    def __init__(self, layers: ModuleList, p_dropout_features: Optional[float], mode: str = "mlp",
+                 node_projection: str = "auto"):
         super().__init__()
         self.layers = layers
         self.p_dropout_features = p_dropout_features
         self.mode = mode
+        # "auto": without autograd and without active dropout, a two-layer decoder whose label edges outnumber the nodes they
+        # touch is evaluated through per-node projections (edge_mlp2_inference); "off": always the per-edge concat form
+        self.node_projection = node_projection
+
+    def _use_node_projection(self, zu, zi, L: int) -> bool:
+        if self.node_projection == "off" or len(self.layers) != 2 or self.layers[1].out_features != 1:
+            return False
+        if any(isinstance(m, nn.LazyLinear) and m.has_uninitialized_params() for m in self.layers):
+            return False
+        if self.layers[0].in_features != zu.shape[1] + zi.shape[1] or not _lib.on_device(zu):
+            return False
+        if torch.is_grad_enabled() and (zu.requires_grad or zi.requires_grad or self.layers[0].weight.requires_grad):
+            return False
+        if self.training and self.p_dropout_features:
+            return False
+        if self.node_projection == "on":
+            return True
+        du, di = zu.shape[1], zi.shape[1]
+        return L * (du + di) > zu.shape[0] * du + zi.shape[0] * di      # rows through the first GEMM: edges vs nodes
 
     def forward(self, z_dict: dict, edge_label_index) -> torch.Tensor:
         customer_index, article_index = edge_label_index
         zu, zi = z_dict[NODE_USER], z_dict[NODE_ITEM]
         if self.mode == "dot":
             return edge_dot(zu, zi, customer_index, article_index)
+        if self._use_node_projection(zu, zi, customer_index.numel()):
+            return edge_mlp2_inference(zu, zi, customer_index, article_index, self.layers[0], self.layers[1])
         z = edge_concat(zu, zi, customer_index, article_index)
         for index, layer in enumerate(self.layers):
             if index == len(self.layers) - 1:
@@ -633,5 +677,6 @@ class Encoder_Decoder_Model(nn.Module):
 
     def infer(self, x_dict, edge_index_dict: dict, edge_label_index: torch.Tensor) -> torch.Tensor:
         self.eval()
-        out = self.forward(x_dict, edge_index_dict, edge_label_index).detach()
+        with torch.no_grad():           # the reference detaches the scores; without a tape the decoder may use its inference form
+            out = self.forward(x_dict, edge_index_dict, edge_label_index)
         return rebatch_by_user(out, edge_label_index[0], value=-(1 << 50))

@@ -54,6 +54,7 @@ test_aggregate_fwd_bwd_vs_oracle = TH.test_aggregate_fwd_bwd_vs_oracle
 test_encoder_decoder_against_reference_golden = TH.test_encoder_decoder_against_reference_golden
 test_infer_rebatch_matches_oracle = TH.test_infer_rebatch_matches_oracle
 test_decoder_concat_and_dot = TH.test_decoder_concat_and_dot
+test_decoder_node_projection_inference_form = TH.test_decoder_node_projection_inference_form
 test_hetero_fan_in_three_edge_types = TH.test_hetero_fan_in_three_edge_types
 test_subgraph_sampler_against_reference_golden = TH.test_subgraph_sampler_against_reference_golden
 test_subgraph_sampler_random_mode_and_model_step = TH.test_subgraph_sampler_random_mode_and_model_step

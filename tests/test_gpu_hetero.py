@@ -120,6 +120,53 @@ def test_decoder_concat_and_dot(cuda_dev, golden):
     close(dot_model({"customer": zu, "article": zi}, eli), ho.edge_decoder_dot(d["z_user"], d["z_item"], d["eli"]))
 
 
+def test_decoder_node_projection_inference_form(cuda_dev, golden):
+    """Dropout-off inference form of the two-layer decoder (per-node projections + lgb_edge_mlp2_fwd): equals the REAL reference
+    EdgeDecoder output of the golden fixture and the per-edge concat form at the production widths; never used under autograd
+    or with active dropout."""
+    d = golden["decoder"]
+    zu, zi, eli = d["z_user"].to(cuda_dev), d["z_item"].to(cuda_dev), d["eli"].to(cuda_dev)
+    layers = lg.get_linear_layers(2, 16, 16, 1).to(cuda_dev)
+    with torch.no_grad():
+        for l, (w, b) in zip(layers, d["linears"]):
+            l.weight.copy_(w); l.bias.copy_(b)
+    z = {"customer": zu, "article": zi}
+    from laplace_gnn_recommendation_b200 import _lib
+    dec = lg.EdgeDecoder(layers, None, node_projection="on")
+    n0 = _lib.LAUNCHES
+    with torch.no_grad():
+        got = dec(z, eli)
+    assert _lib.LAUNCHES - n0 == 1                                   # one lgb_edge_mlp2_fwd, no concat launch
+    close(got, d["out"], rtol=1e-5, atol=1e-6)
+    # under autograd the reference form runs (the inference kernel has no backward)
+    out = dec(z, eli)
+    assert out.requires_grad
+    close(out, d["out"], rtol=1e-5, atol=1e-6)
+    # production widths (64 + 64 -> 128 -> 1), a non-multiple-of-4 hidden width, label edges outnumbering the nodes
+    for H, du, di, nu, ni, L in ((128, 64, 64, 300, 200, 5000), (6, 8, 4, 30, 20, 400), (132, 64, 64, 50, 40, 1000)):
+        gen = torch.Generator().manual_seed(H)
+        a, b = torch.randn(nu, du, generator=gen).to(cuda_dev), torch.randn(ni, di, generator=gen).to(cuda_dev)
+        idx = torch.stack([torch.randint(0, nu, (L,), generator=gen), torch.randint(0, ni, (L,), generator=gen)]).to(cuda_dev)
+        torch.manual_seed(H)
+        ls = lg.get_linear_layers(2, du + di, H, 1).to(cuda_dev)
+        auto, off = lg.EdgeDecoder(ls, 0.5), lg.EdgeDecoder(ls, 0.5, node_projection="off")
+        auto.eval(); off.eval()
+        zz = {"customer": a, "article": b}
+        with torch.no_grad():
+            assert auto._use_node_projection(a, b, L)
+            fast, ref = auto(zz, idx), off(zz, idx)
+        close(fast, ref, rtol=1e-5, atol=2e-6)
+        want = ho.edge_decoder_mlp(a.cpu(), b.cpu(), idx.cpu(), [(l.weight.detach().cpu(), l.bias.detach().cpu()) for l in ls])
+        close(fast, want, rtol=1e-5, atol=2e-6)
+        auto.train()                                                  # active dropout acts on the per-edge concatenation
+        with torch.no_grad():
+            assert not auto._use_node_projection(a, b, L)
+        auto.eval()
+        with torch.no_grad():                                         # few label edges, many nodes: the concat form is cheaper
+            assert not auto._use_node_projection(a, b, 3)
+    # Encoder_Decoder_Model.infer goes through it (golden infer test covers the values)
+
+
 @pytest.mark.parametrize("hetero_aggr", ["sum", "mean", "max"])
 def test_hetero_fan_in_three_edge_types(cuda_dev, hetero_aggr):
     """Two edge types into the same destination + one reverse type: exercises the pairwise fan-in."""
