@@ -415,11 +415,8 @@ def run_ours(args):
         if not args.no_autotune:     # plan-time choice of the SpMM kernel variant for this graph (result-checked, see csr.py)
             gt = g.transpose()
             try:
-                # slice sizes: the CTA-wide-slice variants (16, 19, 20-25) walk a slice with four warps, so plan slices of
-                # 2048 / 4096 entries keep their per-warp chain at 512 / 1024 while quartering the partial rows of stage 2
-                # sweeps: long-row slices in plan order or sorted by first column (csr.py use_sweep_order)
-                g.autotune(d, chunks=(4096, 2048, 1024, 512), degree_orders=(False, True), sweeps=(False, True))
-                gt.autotune(d, chunks=(4096, 2048, 1024, 512), degree_orders=(False, True), sweeps=(False, True))
+                # the public plan-time call (variant x slice size x row order x slice order, lightgcn.AUTOTUNE_SPACE)
+                model.autotune(adj, thorough=True)
                 tuned = {"forward": g.autotune_report.get("chosen"), "backward": gt.autotune_report.get("chosen"),
                          "forward_ms": g.autotune_report["ms"], "backward_ms": gt.autotune_report["ms"],
                          "rejected": {**g.autotune_report["rejected"], **gt.autotune_report["rejected"]}}

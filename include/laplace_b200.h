@@ -177,6 +177,18 @@ int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float*
 int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
                    float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
                    void* stream);
+/* lgb_spmm for an operand X that is ZERO outside a known set of rows: bit c of x_row_bitmap ([ceil(n_cols / 32)] words) set
+ * <=> row c of X may be non-zero.  Same result as lgb_spmm (entries that multiply a zero row contribute nothing), but such
+ * entries are never gathered: the kernel streams colidx, tests the bitmap and fetches the flagged rows only.  Use: the FIRST
+ * layer of the LightGCN backward -- dE_f is non-zero on the <= 3*B rows of the BPR batch (utils/metrics_lightgcn.py:9-45 through
+ * the six gathers of run_pipeline_lightgcn.py:133-144), so A^T dE_f touches 3*B of the N operand rows (B = 128: 384 of 1.48 M).
+ * d <= 64 with d % 4 == 0 uses the filtered kernels; other widths run lgb_spmm's dense kernels.  lgb_rows_bitmap builds the bitmap. */
+int lgb_spmm_rowsparse(const lgb_csr* g, const float* X, const uint32_t* x_row_bitmap, int32_t d, float* Y,
+                       const float* resid, const float* acc_in, float* acc_out, float acc_div, int32_t flags,
+                       float* partial_ws, void* stream);
+/* bitmap[(idx[i] + offset) / 32] |= 1 << ((idx[i] + offset) % 32) for i < n (atomicOr; the caller zeroes the bitmap once per
+ * batch, lgb_zero).  Indices outside [0, n_bits) are ignored. */
+int lgb_rows_bitmap(const int64_t* idx, int64_t n, int64_t offset, int64_t n_bits, uint32_t* bitmap, void* stream);
 
 /* scatter-max per destination (PyG aggr="max"): Y[r,:] = max_e X[colidx[e],:] (0 for empty rows),
  * argmax[r,:] = the winning source row (or -1), used by the backward. */

@@ -10,7 +10,8 @@ There is no CPU fallback: the kernels fail loudly when the shared library or a C
 from . import _lib  # noqa: F401
 from .aliases import HeteroData, install_aliases, patch_driver  # noqa: F401
 from .bpr import bpr_indexed, bpr_loss  # noqa: F401
-from .csr import DeviceCSR  # noqa: F401
+from . import csr, lightgcn  # noqa: F401
+from .csr import DeviceCSR, rows_bitmap  # noqa: F401
 from .hetero import (EdgeDecoder, Encoder_Decoder_Model, GNNEncoder, HeteroEncoder, SAGEConv, aggregate,  # noqa: F401
                      build_edge_csr, edge_concat, edge_dot, get_linear_layers, get_SAGEConv_layers, to_hetero)
 from .lightgcn import LightGCN  # noqa: F401
@@ -29,5 +30,5 @@ __all__ = [
     "Encoder_Decoder_Model", "get_SAGEConv_layers", "get_linear_layers", "aggregate", "build_edge_csr",
     "edge_concat", "edge_dot", "both_indexes_from_zero", "split", "make_lightgcn_splits", "evaluation",
     "get_metrics_lightgcn", "get_metrics_universal", "recall_precision_ndcg", "FusedAdam", "install_aliases", "patch_driver",
-    "HeteroData", "SubgraphSampler",
+    "HeteroData", "SubgraphSampler", "rows_bitmap",
 ]

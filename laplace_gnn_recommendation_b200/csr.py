@@ -59,6 +59,23 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def rows_bitmap(n_rows: int, index_lists, device, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Bitmap of row ids for ``DeviceCSR.spmm(x_rows=)``: bit r set for every r = idx + offset of the ``(idx int64, offset)``
+    pairs in ``index_lists`` (ids outside [0, n_rows) are ignored).  One memset + one tiny launch per list (lgb_rows_bitmap)."""
+    lib = _lib.load()
+    words = (int(n_rows) + 31) // 32
+    if out is None:
+        out = torch.empty(max(words, 1), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(lib.lgb_zero(ptr(out), out.numel() * 4, stream()), "zero")
+        for idx, offset in index_lists:
+            idx = _lib.i64c(idx)
+            _lib.require_cuda(idx)
+            check(lib.lgb_rows_bitmap(ptr(idx), idx.numel(), int(offset), int(n_rows), ptr(out), stream()), "rows_bitmap")
+            _lib.count_launch()
+    return out
+
+
 class DeviceCSR:
     """An [n_rows, n_cols] sparse matrix in CSR form living in HBM."""
 
@@ -404,8 +421,10 @@ class DeviceCSR:
     def spmm(self, X: torch.Tensor, Y: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
              acc_in: Optional[torch.Tensor] = None, acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0,
              mean: bool = False, want_y: bool = True, variant: Optional[int] = None, split_row: Optional[int] = None,
-             y_tail: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
-        """Y = A @ X with the fused epilogue of lgb_spmm.  Allocates Y when want_y and Y is None."""
+             y_tail: Optional[torch.Tensor] = None, x_rows: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """Y = A @ X with the fused epilogue of lgb_spmm.  Allocates Y when want_y and Y is None.
+        ``x_rows``: bitmap (int32 words, ``rows_bitmap``) of the rows of X that may be non-zero -- lgb_spmm_rowsparse: same
+        result, entries that multiply a zero row are never gathered."""
         _lib.require_cuda(X)
         if X.dim() != 2 or X.shape[0] != self.n_cols:
             raise RuntimeError(f"spmm: X has shape {tuple(X.shape)}, expected [{self.n_cols}, d]")
@@ -430,6 +449,13 @@ class DeviceCSR:
                 check(lib.lgb_spmm_split(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
                                          float(acc_div), flags, ptr(self._partial_ws(d)), int(split_row), ptr(y_tail),
                                          stream()), "spmm_split")
+            elif x_rows is not None:
+                if x_rows.dtype != torch.int32 or x_rows.numel() * 32 < self.n_cols or not x_rows.is_contiguous():
+                    raise RuntimeError(f"spmm: x_rows must be a contiguous int32 bitmap of >= {self.n_cols} bits")
+                _lib.require_cuda(x_rows)
+                check(lib.lgb_spmm_rowsparse(C.byref(self.struct), ptr(X), ptr(x_rows), d, ptr(Y), ptr(resid), ptr(acc_in),
+                                             ptr(acc_out), float(acc_div), flags, ptr(self._partial_ws(d)), stream()),
+                      "spmm_rowsparse")
             else:
                 check(lib.lgb_spmm(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
                                    float(acc_div), flags, ptr(self._partial_ws(d)), stream()), "spmm")

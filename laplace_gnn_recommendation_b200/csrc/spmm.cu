@@ -57,7 +57,13 @@ struct SpmmParams {
   float* part2;        // [n_seg, d] level-2 partial rows
   int* tickets;        // [n_long], zero between launches
   const int32_t* task_exec;   // [n_tasks] execution order of the slices (NULL = plan order); partial rows stay indexed by slice id
+  const uint32_t* filter;     // row-sparse operand (lgb_spmm_rowsparse): bit c set <=> row c of X may be non-zero; NULL = dense X
 };
+
+// bit test of the row-sparse operand's bitmap (n_cols bits, L1-resident: 185 KB for the H&M-shaped table)
+__device__ __forceinline__ bool filter_hit(const uint32_t* __restrict__ filter, int c) {
+  return (__ldg(filter + ((uint32_t)c >> 5)) >> ((uint32_t)c & 31u)) & 1u;
+}
 
 // STEP = distance between the 32-entry batches this warp takes (32: the whole range; 32*SPMM_WARPS: every SPMM_WARPS-th
 // batch, when the warps of a CTA share one slice).
@@ -68,7 +74,10 @@ struct SpmmParams {
 // D4C = d/4 when it is known at compile time (the row is exactly one float4 per lane of the group: d = 4*G*VPL, e.g. d = 64
 // with G = 16): the column-bound predicates disappear and the row offset becomes a shift; 0 = read it from the parameters.
 // W256: a lane holds two ADJACENT float4 of the row (2*lig, 2*lig+1) and fetches them with one 256-bit load (LDG.E.256).
-template <int G, int VPL, int UNROLL, int STEP = 32, typename IT = uint32_t, int D4C = 0, bool W256 = false>
+// FILTER (lgb_spmm_rowsparse): X is zero outside the rows flagged in p.filter.  Every lane tests the column it loaded; a batch
+// without a hit costs one ballot, and the hits of a batch are taken NG at a time straight from the ballot mask (group g pops the
+// g-th lowest set bit) -- entries that multiply a zero row are never gathered.  Order per group: ascending, fixed.
+template <int G, int VPL, int UNROLL, int STEP = 32, typename IT = uint32_t, int D4C = 0, bool W256 = false, bool FILTER = false>
 __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int e, int lane, float4 (&acc)[VPL]) {
   constexpr int NG = 32 / G;
   static_assert(32 % (NG * UNROLL) == 0, "a batch of 32 entries must be a whole number of unrolled steps");
@@ -81,11 +90,41 @@ __device__ __forceinline__ void accumulate_slice(const SpmmParams& p, int s, int
   const IT d4i = (IT)d4;
   for (int base = s; base < e; base += STEP) {
     const int idx = base + lane;
-    int c = 0;
+    int c = FILTER ? -1 : 0;
     float w = 0.f;
     if (idx < e) {
       c = ld_stream_i32(p.colidx + idx);
-      w = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+      if (FILTER && !filter_hit(p.filter, c)) c = -1;
+      if (!FILTER || c >= 0) w = p.val ? ld_stream_f32(p.val + idx) : 1.f;
+    }
+    if (FILTER) {
+      unsigned m = __ballot_sync(FULL_MASK, c >= 0);
+      while (m) {                                   // warp-uniform: every lane holds the same mask
+        int k = -1;
+#pragma unroll
+        for (int g2 = 0; g2 < NG; ++g2) {
+          const int b = m ? __ffs((int)m) - 1 : -1;
+          if (g2 == grp) k = b;
+          m &= m - 1u;                              // 0 stays 0
+        }
+        const int cc = __shfl_sync(FULL_MASK, c, k & 31);
+        const float wk = __shfl_sync(FULL_MASK, w, k & 31);
+        if (k >= 0) {
+          const IT row = (IT)cc * d4i;
+          if (W256) {
+            const f4x2 t = ld_gather_f8(X4 + (row + (IT)(lig * 2)));
+            f4_fma(acc[0], wk, t.a);
+            f4_fma(acc[VPL - 1], wk, t.b);
+          } else {
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) {
+              const int f = lig + q * G;
+              if (f < d4) f4_fma(acc[q], wk, ld_gather_f4(X4 + (row + (IT)f)));
+            }
+          }
+        }
+      }
+      continue;
     }
     const int cnt = min(32, e - base);
     for (int j = 0; j < cnt; j += NG * UNROLL) {
@@ -420,7 +459,7 @@ constexpr int SUBW_MAX = 64;
 // arithmetic per non-zero).
 // W256 (variants 23-25, d = 64 only, measurement pending): the short-row path fetches a lane's two float4 with ONE 256-bit
 // load (sm_100's LDG.E.256) -- a 256-byte row = one load instruction of 8 lanes, four rows per warp-level load.
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false>
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false, bool FILTER = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
   static_assert(G % UNROLL == 0, "the unrolled gather step must divide the lane-group width");
   static_assert(D4C == 0 || D4C == G * VPL, "a compile-time d/4 must fill the lane group exactly");
@@ -440,7 +479,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
       float4 acc[VPL];
 #pragma unroll
       for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
-      accumulate_slice<G, VPL, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C, W256>(p, s + 32 * wi, e, lane, acc);
+      accumulate_slice<G, VPL, UNROLL, 32 * SPMM_WARPS, uint32_t, D4C, W256, FILTER>(p, s + 32 * wi, e, lane, acc);
       if (lane < G) {
 #pragma unroll
         for (int q = 0; q < VPL; ++q) wsum[wi][W256 ? lane * VPL + q : lane + q * G] = acc[q];   // indexed by float4 of the row
@@ -470,7 +509,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
     const int64_t t = p.task_exec ? p.task_exec[w] : w;
     const int s = p.task_start[t], e = p.task_end[t];
-    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256>(p, s, e, lane, acc);
+    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256, FILTER>(p, s, e, lane, acc);
     if (lane < G) {
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
@@ -521,7 +560,37 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
       c = ld_stream_i32_hint(p.colidx + s + lig, pol);
       wv = p.val ? ld_stream_f32_hint(p.val + s + lig, pol) : 1.f;
     }
-    for (int base = 0; base < maxdeg; base += G) {
+    for (int base = 0; FILTER && base < maxdeg; base += G) {
+      // row-sparse operand: every lane tests its own column; the groups pop their hits from the ballot mask, one per step
+      c = -1; wv = 0.f;
+      if (base + lig < deg) {
+        c = ld_stream_i32(p.colidx + s + base + lig);
+        if (!filter_hit(p.filter, c)) c = -1;
+        else wv = p.val ? ld_stream_f32(p.val + s + base + lig) : 1.f;
+      }
+      unsigned gm = (__ballot_sync(FULL_MASK, c >= 0) >> (grp * G)) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+      while (__any_sync(FULL_MASK, gm != 0)) {
+        const int k = gm ? __ffs((int)gm) - 1 : -1;
+        gm &= gm - 1u;
+        const int cc = __shfl_sync(FULL_MASK, c, k & (G - 1), G);
+        const float wk = __shfl_sync(FULL_MASK, wv, k & (G - 1), G);
+        if (k >= 0) {
+          const uint32_t row = (uint32_t)cc * d4u;
+          if (W256) {
+            const f4x2 t = ld_gather_f8(X4 + (row + (uint32_t)(lig * 2)));
+            f4_fma(acc[0], wk, t.a);
+            f4_fma(acc[VPL - 1], wk, t.b);
+          } else {
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) {
+              const int f = lig + q * G;
+              if (f < d4) f4_fma(acc[q], wk, ld_gather_f4(X4 + (row + (uint32_t)f)));
+            }
+          }
+        }
+      }
+    }
+    for (int base = 0; !FILTER && base < maxdeg; base += G) {
       if (PF) {                                    // the NEXT batch is requested before this one is consumed
         cn = 0; wn = 0.f;
         if (base + G + lig < deg) {
@@ -583,7 +652,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
     float4 acc[VPL];
 #pragma unroll
     for (int q = 0; q < VPL; ++q) acc[q] = f4_zero();
-    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256>(p, ss, ee, lane, acc);
+    accumulate_slice<G, VPL, UNROLL, 32, uint32_t, D4C, W256, FILTER>(p, ss, ee, lane, acc);
     if (lane < G) epilogue_row<G, VPL, false, W256>(p, rr, ee - ss, lane, acc);
   }
 }
@@ -599,7 +668,7 @@ static int launch_stage2(const SpmmParams& p, cudaStream_t stream);
 template <int G, int VPL>
 __global__ void spmm_long_reduce_kernel(const SpmmParams p);
 
-template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false>
+template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false, bool FILTER = false>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream);
 
 // d/4 == G*VPL (d = 64 with G = 16, d = 32 with G = 8) gets the kernel specialised on that constant
@@ -609,7 +678,7 @@ static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
                          : launch_subwarp_impl<G, UNROLL, MINB, WIDE, 0, PF, VPL>(p, stream);
 }
 
-template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF, int VPL, bool W256>
+template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF, int VPL, bool W256, bool FILTER>
 static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   constexpr int NG = 32 / G;
   const int64_t row_warps = (p.n_rows + NG - 1) / NG;
@@ -617,7 +686,7 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
   if (warps > 0) {
     const int64_t blocks = WIDE ? p.n_tasks + (row_warps + SPMM_WARPS - 1) / SPMM_WARPS : (warps + SPMM_WARPS - 1) / SPMM_WARPS;
     LGB_REQUIRE(blocks < (1ll << 31), LGB_ERANGE, "lgb_spmm: grid too large");
-    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL, W256><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
+    spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL, W256, FILTER><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
   { const int rc2 = launch_stage2<G, VPL>(p, stream); if (rc2) return rc2; }
@@ -1253,13 +1322,37 @@ __global__ void scale_concat_scalar_kernel(const float* __restrict__ a, int64_t 
 
 }  // namespace lgb
 
+namespace lgb {
+__global__ void __launch_bounds__(256) rows_bitmap_kernel(const int64_t* __restrict__ idx, int64_t n, int64_t offset, int64_t n_bits,
+                                                          uint32_t* __restrict__ bitmap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = idx[i] + offset;
+  if (c >= 0 && c < n_bits) atomicOr(bitmap + (c >> 5), 1u << (c & 31));
+}
+}  // namespace lgb
+
 using namespace lgb;
 
 extern "C" {
 
+int lgb_rows_bitmap(const int64_t* idx, int64_t n, int64_t offset, int64_t n_bits, uint32_t* bitmap, void* stream_) {
+  LGB_REQUIRE(n >= 0 && n_bits >= 0 && (n == 0 || (idx && bitmap)), LGB_EINVAL, "lgb_rows_bitmap: bad argument");
+  if (n == 0) return LGB_OK;
+  rows_bitmap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(idx, n, offset, n_bits, bitmap);
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
 static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
                      float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
-                     void* stream_);
+                     void* stream_, const uint32_t* filter = nullptr);
+
+int lgb_spmm_rowsparse(const lgb_csr* g, const float* X, const uint32_t* x_row_bitmap, int32_t d, float* Y, const float* resid,
+                       const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws, void* stream_) {
+  LGB_REQUIRE(x_row_bitmap, LGB_EINVAL, "lgb_spmm_rowsparse: null bitmap");
+  return spmm_impl(g, X, d, Y, resid, acc_in, acc_out, acc_div, flags, partial_ws, 0, nullptr, stream_, x_row_bitmap);
+}
 
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
              float* acc_out, float acc_div, int32_t flags, float* partial_ws, void* stream_) {
@@ -1281,7 +1374,7 @@ int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const 
 
 static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
                      float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
-                     void* stream_) {
+                     void* stream_, const uint32_t* filter) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LGB_REQUIRE(g && g->rowptr && X && d > 0, LGB_EINVAL, "lgb_spmm: null graph/X or d <= 0");
   LGB_REQUIRE(g->nnz == 0 || g->colidx, LGB_EINVAL, "lgb_spmm: null colidx");
@@ -1305,6 +1398,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   p.part2 = p.n_seg > 0 && partial_ws ? partial_ws + (size_t)p.n_tasks * d + 64 : nullptr;
   p.tickets = p.part2 ? reinterpret_cast<int*>(p.part2 + (size_t)p.n_seg * d) : nullptr;
   p.task_exec = p.n_tasks > 0 ? g->task_exec : nullptr;
+  p.filter = nullptr;
   if (p.n_tasks > 0) {
     LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->task_end && g->long_rows && g->long_ptr, LGB_EINVAL,
                 "lgb_spmm: plan has %lld tasks but plan arrays (task_row/start/end, long_rows/ptr) / partial workspace missing",
@@ -1339,6 +1433,14 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
     if (d4 <= 128) return launch_vec<32, 4, 1, 8, size_t>(p, 1, stream);
     set_error("lgb_spmm: d=%d > 512 not supported", d);
     return LGB_EINVAL;
+  }
+  if (filter && d4 <= 16) {
+    // row-sparse operand (lgb_spmm_rowsparse): the filtered forms of the sub-warp kernel with CTA-wide slices; other widths run
+    // the dense kernels below (same result: the flagged rows are the only non-zero ones)
+    p.filter = filter;
+    if (d4 == 16 && (all_ptrs & 31) == 0) return launch_subwarp_impl<8, 1, 16, true, 16, false, 2, true, true>(p, stream);
+    if (d4 <= 8) return launch_subwarp_impl<8, 2, 16, true, 0, false, 1, false, true>(p, stream);
+    return launch_subwarp_impl<16, 2, 16, true, 0, false, 1, false, true>(p, stream);
   }
   if (variant == 30 || variant == 31) {   // hot-column cache: needs the plan's recoded column array and an exact one-float4-per-lane width
     if (g->colidx_hot && g->hot_cols && g->n_hot > 0 && (d4 == 8 || d4 == 16) && !y_tail) {

@@ -33,6 +33,7 @@ otherwise).
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes as C
 from typing import List, Optional, Tuple
 
@@ -42,7 +43,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import LgbBprArgs, LgbExchange, check, ptr, stream
 from .bpr import _launch as _bpr_launch, _ws as _bpr_ws
-from .csr import DEFAULT_CHUNK, DeviceCSR
+from .csr import DEFAULT_CHUNK, DeviceCSR, rows_bitmap
 
 N_CHANNELS = 3          # exchange channels: one per layer chain + the BPR batch rows
 
@@ -146,13 +147,24 @@ class CudaOps:
         return [torch.zeros(*s, dtype=torch.float32, device=self.device) for s in shapes]
 
     # kernels --------------------------------------------------------------------------------------
-    def spmm(self, g, X, Y, resid=None):
+    def spmm(self, g, X, Y, resid=None, x_rows=None):
         if g.n_rows == 0:
             return
         if g.n_cols == 0:                       # a rank without users (world > #users): its partial sums are zero
             Y.zero_() if resid is None else Y.copy_(resid)
             return
-        g.spmm(X, Y=Y, resid=resid)
+        g.spmm(X, Y=Y, resid=resid, x_rows=x_rows)
+
+    def rows_bitmap(self, n, index_lists, key):
+        """Bitmap of the rows idx + offset (``(idx, offset)`` pairs; ids outside [0, n) ignored) for ``spmm(x_rows=)``; one
+        persistent buffer per ``key`` (graph capture)."""
+        if n <= 0:
+            return None
+        bufs = self.__dict__.setdefault("_bitmaps", {})
+        buf = bufs.get(key)
+        if buf is None or buf.numel() * 32 < n:
+            buf = bufs[key] = torch.empty((n + 31) // 32, dtype=torch.int32, device=self.device)
+        return rows_bitmap(n, index_lists, self.device, out=buf)
 
     def row_view(self, g: DeviceCSR, lo: int, hi: int) -> DeviceCSR:
         """Rows [lo, hi) of g as a CSR of its own (rowptr slice; colidx/val shared, offsets stay absolute) -- probes."""
@@ -434,6 +446,8 @@ class ShardedLightGCN:
             gen_i = torch.Generator(device=self.device).manual_seed(999)
             self.table[Ug:].normal_(0, 0.1, generator=gen_i)
         self.max_batch = int(max_batch)
+        self.rowsparse_backward = os.environ.get("LGB_ROWSPARSE_BACKWARD", "1") != "0"   # first backward layer: lgb_spmm_rowsparse ...
+        self.rowsparse_ratio = 8                                                          # ... while the table has >= 8 rows per batch row
         # layer outputs: user rows in plain HBM, item rows in exchange buffers (+ the 2*B*d batch-row buffer of the BPR section)
         self._yu = [torch.empty(Ug, d, **f32) for _ in range(K)]
         bufs = self.ops.alloc_exchange([(I, d)] * max(K, 1) + [(2, self.max_batch, d)])
@@ -543,10 +557,11 @@ class ShardedLightGCN:
         return report
 
     # ---- K propagation layers as two independent chains ---------------------------------------------------------------
-    def _propagate(self, xu, xi, resid_u=None, resid_i=None, last_u=None):
+    def _propagate(self, xu, xi, resid_u=None, resid_i=None, last_u=None, rows_u=None, rows_i=None):
         """(xu, xi) -> K layers of  yu = G_users xi (+resid_u),  yi = exchange(G_items xu (+resid_i on rank 0)).
         Returns ([yu_0..yu_{K-1}], [yi_0..yi_{K-1}]); on return everything is ordered on the current stream.
-        last_u: buffer that receives yu_{K-1} instead of the internal one."""
+        last_u: buffer that receives yu_{K-1} instead of the internal one.  rows_u / rows_i: bitmaps of the rows of the INPUT
+        xu / xi that may be non-zero (the backward's batch rows): layer 0 gathers from them as lgb_spmm_rowsparse."""
         K, ops = self.K, self.ops
         two = self.schedule == "chains"
         ctx = ops.fork(two)
@@ -557,12 +572,12 @@ class ShardedLightGCN:
             yi = self._yi[k]
             yu = last_u if (k == K - 1 and last_u is not None) else self._yu[k]
             with ctx[ci]:
-                ops.spmm(self.g_items, xu, yi, resid=ri)                       # partial item rows <- owned users
+                ops.spmm(self.g_items, xu, yi, resid=ri, x_rows=rows_u if k == 0 else None)   # partial item rows <- owned users
                 h = ops.exchange_async(yi, channel=ci)                           # ... summed over ranks
             with ctx[cu]:
                 if pending is not None:
                     pending.wait()                                               # xi = yi_{k-1} must be complete (same chain)
-                ops.spmm(self.g_users, xi, yu, resid=resid_u)                   # owned user rows <- all items
+                ops.spmm(self.g_users, xi, yu, resid=resid_u, x_rows=rows_i if k == 0 else None)   # owned user rows <- all items
             yus.append(yu); yis.append(yi)
             xu, xi, pending = yu, yi, h
         ops.join(two)
@@ -583,13 +598,14 @@ class ShardedLightGCN:
         ops.mean_rows([Wi] + yis, float(K + 1), self.E_f_items)
         return self.E_f_users, self.E_f_items
 
-    def backward(self, ru: torch.Tensor, ri: torch.Tensor):
+    def backward(self, ru: torch.Tensor, ri: torch.Tensor, rows_u=None, rows_i=None):
         """grad = sum_k (A^T)^k r with r = dE_f/(K+1) (Horner: g <- A g + r; the local block is symmetric).  ri must be the
-        complete item-row residual (identical on every rank)."""
+        complete item-row residual (identical on every rank).  rows_u / rows_i: optional bitmaps (ops.rows_bitmap) of the rows
+        of ru / ri that may be non-zero."""
         if self.K == 0:
             self.grad_users.copy_(ru); self.grad_items.copy_(ri)
             return self.grad_users, self.grad_items
-        self._propagate(ru, ri, resid_u=ru, resid_i=ri, last_u=self.grad_users)
+        self._propagate(ru, ri, resid_u=ru, resid_i=ri, last_u=self.grad_users, rows_u=rows_u, rows_i=rows_i)
         return self.grad_users, self.grad_items
 
     @torch.no_grad()
@@ -617,7 +633,14 @@ class ShardedLightGCN:
         loss = self._loss
         ops.bpr(stage[0], stage[1], Efi, Wi, self._iota[:B], p, n, lambda_val, B, gscale=1.0 / (K + 1), loss=loss, duf=dst, dpf=ri)
         ops.scatter_add_owned(dst, u, self.lo, self.hi, ru)
-        Gu, Gi = self.backward(ru, ri)
+        # ru / ri are non-zero on the batch rows only: the first backward layer skips every entry that multiplies a zero row
+        rows_u = rows_i = None
+        if self.rowsparse_backward and d % 4 == 0 and d <= 64:
+            if self.rowsparse_ratio * B <= Ug:
+                rows_u = ops.rows_bitmap(Ug, ((u, -self.lo),), "users")
+            if self.rowsparse_ratio * 2 * B <= self.I:
+                rows_i = ops.rows_bitmap(self.I, ((p, 0), (n, 0)), "items")
+        Gu, Gi = self.backward(ru, ri, rows_u=rows_u, rows_i=rows_i)
         # + 2*lambda*E0 on the batch rows: owned users locally, item rows redundantly (identical) on every rank
         ops.bpr(Efu, Wu, Efi, Wi, u, p, n, lambda_val, B, user_lo=self.lo, user_hi=self.hi, user_rows_only=True, du0=Gu, dp0=Gi)
         self.loss = loss

@@ -26,11 +26,21 @@ from torch import nn
 from . import _lib
 from ._lib import check, ptr, stream
 from .bpr import bpr_indexed
-from .csr import DeviceCSR
+from .csr import DeviceCSR, rows_bitmap
 from .sparse import SparseTensor, gcn_norm, matmul
 
 
 _AUTOTUNE = os.environ.get("LGB_SPMM_AUTOTUNE", "0") == "1"   # tune the SpMM variant per graph on first use
+
+
+# plan space of LightGCN.autotune(thorough=True) and bench.py: slice sizes (the CTA-wide-slice variants walk a slice with four warps,
+# so 2048 / 4096 keep their per-warp chain at 512 / 1024 while quartering the partial rows of stage 2), row order, slice order
+AUTOTUNE_SPACE = dict(chunks=(4096, 2048, 1024, 512), degree_orders=(False, True), sweeps=(False, True))
+
+
+# first backward layer as lgb_spmm_rowsparse while the batch rows are at most 1 / ROWSPARSE_MAX_SHARE of the table
+ROWSPARSE_BACKWARD = os.environ.get("LGB_ROWSPARSE_BACKWARD", "1") != "0"
+ROWSPARSE_MAX_SHARE = 8
 
 
 def _scale_concat(a: Optional[torch.Tensor], b: Optional[torch.Tensor], na: int, nb: int, d: int, scale: float,
@@ -61,8 +71,11 @@ def propagate_forward(g: DeviceCSR, E0: torch.Tensor, K: int) -> torch.Tensor:
     return E_f
 
 
-def propagate_backward(gt: DeviceCSR, r: torch.Tensor, K: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dE0 = sum_{k=0..K} (A^T)^k r  via Horner: g <- A^T g + r, K times (r already holds dE_f/(K+1))."""
+def propagate_backward(gt: DeviceCSR, r: torch.Tensor, K: int, out: Optional[torch.Tensor] = None,
+                       r_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dE0 = sum_{k=0..K} (A^T)^k r  via Horner: g <- A^T g + r, K times (r already holds dE_f/(K+1)).
+    ``r_rows``: bitmap of the rows of r that may be non-zero (the BPR batch): the first layer gathers from r itself and runs as
+    lgb_spmm_rowsparse -- of the nnz entries only those whose column is a batch row are fetched."""
     if K == 0:
         return r
     g = r
@@ -74,7 +87,7 @@ def propagate_backward(gt: DeviceCSR, r: torch.Tensor, K: int, out: Optional[tor
             dst = torch.empty_like(r)
             if not last:
                 bufs[k % 2] = dst
-        gt.spmm(g, Y=dst, resid=r)
+        gt.spmm(g, Y=dst, resid=r, x_rows=r_rows if k == 0 else None)
         g = dst
     return g
 
@@ -142,14 +155,25 @@ class LightGCN(nn.Module):
             self._fuse_tables()
         return out
 
+    def _rows_bitmap_buf(self, n: int, device) -> torch.Tensor:
+        buf = getattr(self, "_bitmap", None)
+        if buf is None or buf.numel() * 32 < n or buf.device != device:
+            buf = self._bitmap = torch.empty((n + 31) // 32, dtype=torch.int32, device=device)
+        return buf
+
     # ---- plan-time kernel selection (optional) ------------------------------------------------
-    def autotune(self, edge_index: SparseTensor):
+    def autotune(self, edge_index: SparseTensor, thorough: Optional[bool] = None):
         """Time the SpMM kernel variants on THIS graph (and its transpose, for the backward) at this embedding width and
-        keep the fastest for all later calls (``DeviceCSR.autotune``).  One-off per graph, ~tens of launches; also run
-        automatically on first use when LGB_SPMM_AUTOTUNE=1.  Returns (forward variant, backward variant)."""
+        keep the fastest for all later calls (``DeviceCSR.autotune``).  One-off per graph; also run automatically on first use
+        when LGB_SPMM_AUTOTUNE=1.  ``thorough`` (default: graphs of a million entries and more) also walks the slice size of
+        the long-row plan, the degree-bucketed row order and the column-sweep order of the slices -- on the H&M-shaped graph
+        that search is what takes the epoch from 8.1 to 6.9 ms (profiles/README.md r2l).  Returns (forward, backward variant)."""
         g = gcn_norm(edge_index, add_self_loops=self.add_self_loops).csr()
         d = self.users_emb.weight.shape[1]
-        return g.autotune(d), g.transpose().autotune(d)
+        if thorough is None:
+            thorough = g.nnz >= 1_000_000
+        space = AUTOTUNE_SPACE if thorough else {}
+        return g.autotune(d, **space), g.transpose().autotune(d, **space)
 
     # ---- reference API ------------------------------------------------------------------------
     def forward(self, edge_index: SparseTensor):
@@ -238,7 +262,12 @@ class LightGCN(nn.Module):
         if K == 0:
             G = r
         else:
-            G = propagate_backward(g.transpose(), r, K)
+            # dE_f is non-zero on the batch rows only: while they are a small part of the table, say so to the first layer
+            r_rows = None
+            if ROWSPARSE_BACKWARD and 3 * user_indices.numel() * ROWSPARSE_MAX_SHARE <= N and d % 4 == 0 and d <= 64:
+                r_rows = rows_bitmap(N, ((user_indices, 0), (pos_item_indices, U), (neg_item_indices, U)), E0.device,
+                                     out=self._rows_bitmap_buf(N, E0.device))
+            G = propagate_backward(g.transpose(), r, K, r_rows=r_rows)
         # + 2*lambda*E0[rows] on the layer-0 rows of the batch
         bpr_indexed(E_f, E0, U, user_indices, pos_item_indices, neg_item_indices, lambda_val, dE_0=G)
         Wu.grad, Wi.grad = G[:U], G[U:]

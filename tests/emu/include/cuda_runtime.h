@@ -148,6 +148,8 @@ template <class T, class U>
 static inline T atomicMin(T* p, U v) { T old = *p; if ((T)v < old) *p = (T)v; return old; }
 template <class T, class U>
 static inline T atomicExch(T* p, U v) { T old = *p; *p = (T)v; return old; }
+template <typename T, typename U>
+static inline T atomicOr(T* p, U v) { T old = *p; *p = (T)(old | (T)v); return old; }
 template <class T, class U, class V>
 static inline T atomicCAS(T* p, U cmp, V v) { T old = *p; if (old == (T)cmp) *p = (T)v; return old; }
 

@@ -40,9 +40,21 @@ class CpuOracleOps:
     def alloc_exchange(self, shapes):
         return [torch.zeros(*sh) for sh in shapes]
 
-    def spmm(self, g, X, Y, resid=None):
+    def spmm(self, g, X, Y, resid=None, x_rows=None):
+        if x_rows is not None:       # the engine's promise behind lgb_spmm_rowsparse: X is zero outside the flagged rows
+            assert x_rows.numel() == X.shape[0] and not bool(X[~x_rows].any())
+            self.rowsparse_calls = getattr(self, "rowsparse_calls", 0) + 1
         y = lo.spmm(g["rowptr"], g["col"], g["val"], X) if X.shape[0] else torch.zeros(g["n"], X.shape[1])
         Y.copy_(y if resid is None else y + resid)
+
+    def rows_bitmap(self, n, index_lists, key):
+        if n <= 0:
+            return None
+        m = torch.zeros(n, dtype=torch.bool)
+        for idx, off in index_lists:
+            r = idx.long() + off
+            m[r[(r >= 0) & (r < n)]] = True
+        return m
 
     def mean_rows(self, srcs, div, out):
         acc = srcs[0]
@@ -197,7 +209,11 @@ def _worker(rank, world, port, cases, out_dir):
                 ops = make_emu_ops() if ops_kind == "emu" else CpuOracleOps()
                 eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], pb["K"], pb["users"], pb["items"], "cpu", ops=ops,
                                       init_tables=(pb["Wu"], pb["Wi"]), schedule=schedule, max_batch=128)
+                if ci % 2 == 1:                  # every other case: the first backward layer as lgb_spmm_rowsparse whatever the sizes
+                    eng.rowsparse_ratio = 0
                 loss = eng.fused_step(pb["u"], pb["p"], pb["n"], pb["lam"])
+                if ci % 2 == 1 and ops_kind == "oracle" and K > 0 and d <= 64:
+                    assert ops.rowsparse_calls >= 1   # (CpuOracleOps.spmm also asserts the operand is zero outside the bitmap)
                 tuned = None
                 if ops_kind == "emu" and ci == len(cases) - 1:      # plan-time choice of the step form, once per world size
                     import time

@@ -141,6 +141,45 @@ def test_spmm_sweep_order_bit_identical(cuda_dev, variant):
     assert g.task_exec is None and torch.equal(g.spmm(X, variant=variant), y0)
 
 
+@pytest.mark.parametrize("d", [64, 32, 48, 20, 128, 6])
+def test_spmm_rowsparse_matches_dense(cuda_dev, d):
+    """lgb_spmm_rowsparse (operand zero outside the rows of a bitmap: entries that multiply a zero row are never gathered)
+    against lgb_spmm on the same operand, and against the fp64 oracle -- long rows (slices + stage 2), short rows, fused
+    residual / accumulate epilogue, every kernel shape (d = 64: 256-bit form; d4 <= 8; d4 <= 16; wider / scalar: dense fallback)."""
+    n, nnz = 700, 40000
+    row, col = random_graph(21, n, n, nnz, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=64)
+    _, val = g.gcn_norm()
+    g = g.with_values(val).use_sweep_order(True)
+    gen = torch.Generator().manual_seed(d)
+    for n_hot in (0, 1, 37, n):
+        hot = torch.randperm(n, generator=gen)[:n_hot]
+        X = torch.zeros(n, d)
+        X[hot] = torch.randn(n_hot, d, generator=gen)
+        R, A = torch.randn(n, d, generator=gen), torch.randn(n, d, generator=gen)
+        # ids outside [0, n) and duplicates are ignored / harmless; the second list uses an offset
+        lists = ((torch.cat([hot[: n_hot // 2], hot[: n_hot // 2], torch.tensor([-5, n + 3])]).to(cuda_dev), 0),
+                 ((hot[n_hot // 2:] - 11).to(cuda_dev), 11))
+        bm = lg.rows_bitmap(n, lists, cuda_dev)
+        bits = torch.zeros(bm.numel() * 32, dtype=torch.bool)
+        bits[hot] = True
+        words = bm.cpu().to(torch.int64) & 0xFFFFFFFF
+        got_bits = ((words[:, None] >> torch.arange(32)[None, :]) & 1).bool().view(-1)
+        assert torch.equal(got_bits, bits)
+        Xd, Rd, Ad = X.to(cuda_dev), R.to(cuda_dev), A.to(cuda_dev)
+        dense = g.spmm(Xd, resid=Rd)
+        sparse = g.spmm(Xd, resid=Rd, x_rows=bm)
+        close(sparse, dense, rtol=1e-5, atol=1e-6)
+        base = lo.spmm(g.rowptr.cpu().long(), g.colidx.cpu().long(), val.cpu().double(), X.double()).float()
+        close(sparse, base + R, rtol=1e-5, atol=1e-6)
+        acc = torch.empty(n, d, device=cuda_dev)
+        g.spmm(Xd, want_y=False, acc_in=Ad, acc_out=acc, acc_div=3.0, x_rows=bm)
+        close(acc, (A + base) / 3.0, rtol=1e-5, atol=1e-6)
+        assert torch.equal(g.spmm(Xd, x_rows=bm), g.spmm(Xd, x_rows=bm))          # deterministic
+    with pytest.raises(RuntimeError):
+        g.spmm(Xd, x_rows=bm[:2])                                                  # bitmap shorter than the operand
+
+
 def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
     n, nnz, d = 500, 20000, 64
     row, col = random_graph(5, n, n, nnz, skew=True)
@@ -226,6 +265,7 @@ def test_spmm_large_properties(cuda_dev):
 
 # ------------------------------------------------------------------ LightGCN forward/backward + BPR
 def run_case(c, dev, fused):
+    fused = bool(fused)
     U, I, d, K = c["U"], c["I"], c["d"], c["K"]
     model = lg.LightGCN(U, I, d, K)
     with torch.no_grad():
@@ -245,8 +285,10 @@ def run_case(c, dev, fused):
     return loss, u_f, i_f, model.users_emb.weight.grad, model.items_emb.weight.grad
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_lightgcn_against_reference_golden(cuda_dev, golden, fused):
+@pytest.mark.parametrize("fused", [False, True, "rowsparse"])
+def test_lightgcn_against_reference_golden(cuda_dev, golden, fused, monkeypatch):
+    if fused == "rowsparse":      # first backward layer through lgb_spmm_rowsparse whatever the table / batch sizes
+        monkeypatch.setattr(lg.lightgcn, "ROWSPARSE_MAX_SHARE", 0)
     for c in golden["lightgcn"]:
         loss, u_f, i_f, gu, gi = run_case(c, cuda_dev, fused)
         close(u_f, c["u_final"]); close(i_f, c["i_final"])

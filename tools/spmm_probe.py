@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--d", type=int, default=64)
     ap.add_argument("--workload", default="hm")
     ap.add_argument("--chunks", default="", help="slice sizes of the long-row plan to walk (default: the library default)")
+    ap.add_argument("--rowsparse", type=int, default=0, help="B > 0: also time lgb_spmm_rowsparse on an operand that is zero outside the 3B rows of a BPR batch")
     ap.add_argument("--sweep", default="0", help="comma list of 0/1: long-row slices in plan order / column-sweep order")
     a = ap.parse_args()
     dev = _common.device()
@@ -37,6 +38,18 @@ def main():
     X = torch.randn(N, d, device=dev); Y = torch.empty(N, d, device=dev); acc = torch.randn(N, d, device=dev)
     print(f"graph: nnz={g.nnz} n_long={g.n_long} n_tasks={g.n_tasks} | users view nnz={gu.nnz} long={gu.n_long} tasks={gu.n_tasks}"
           f" | items view nnz={gi.nnz} long={gi.n_long} tasks={gi.n_tasks}")
+    Xs = bm = None
+    if a.rowsparse > 0:          # a BPR batch: B edges drawn uniformly (user, positive item) + B uniform negatives
+        gen = torch.Generator(device=dev).manual_seed(7)
+        pick = torch.randint(0, users.numel(), (a.rowsparse,), generator=gen, device=dev)
+        ub, pb = users[pick], items[pick]
+        nb = torch.randint(0, I, (a.rowsparse,), generator=gen, device=dev)
+        bm = lg.rows_bitmap(N, ((ub, 0), (pb, U), (nb, U)), dev)
+        Xs = torch.zeros(N, d, device=dev)
+        rows = torch.cat([ub, pb + U, nb + U])
+        Xs[rows] = torch.randn(rows.numel(), d, device=dev)
+        deg = (g.rowptr[1:] - g.rowptr[:-1]).long()
+        print(f"rowsparse: {torch.unique(rows).numel()} operand rows flagged; entries that hit them: {int(deg[torch.unique(rows)].sum())} of {g.nnz}")
     chunks = [int(x) for x in a.chunks.split(",")] if a.chunks else [g.chunk]
     for chunk in chunks:
         for sweep in [bool(int(x)) for x in a.sweep.split(",")]:
@@ -53,6 +66,15 @@ def main():
                 print(f"{tag} variant {v}: full+acc {t_full:.3f} ms | plain {t_plain:.3f} ms ({gb / t_plain:.0f} GB/s alg) | "
                       f"user rows {t_u:.3f} ms ({spmm_bytes(gu.nnz, U, d) / 1e6 / t_u:.0f} GB/s) | "
                       f"item rows {t_i:.3f} ms ({spmm_bytes(gi.nnz, I, d) / 1e6 / t_i:.0f} GB/s)", flush=True)
+            if bm is not None:
+                t_d = timeit(lambda: g.spmm(Xs, Y=Y, resid=Xs))
+                t_s = timeit(lambda: g.spmm(Xs, Y=Y, resid=Xs, x_rows=bm))
+                t_su = timeit(lambda: gu.spmm(Xs, Y=Y[:U], x_rows=bm))
+                t_si = timeit(lambda: gi.spmm(Xs, Y=Y[U:], x_rows=bm))
+                Yd = g.spmm(Xs, resid=Xs); Ys = g.spmm(Xs, resid=Xs, x_rows=bm)
+                err = float((Yd - Ys).abs().max()) / (float(Yd.abs().max()) + 1e-30)
+                print(f"{tag} rowsparse B={a.rowsparse}: dense kernel on the sparse operand {t_d:.3f} ms | rowsparse {t_s:.3f} ms "
+                      f"(user rows {t_su:.3f}, item rows {t_si:.3f}) | max rel diff {err:.2e}", flush=True)
 
 
 if __name__ == "__main__":

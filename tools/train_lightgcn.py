@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--lr-decay-every", type=int, default=50)
     ap.add_argument("--sampler", default="reference", choices=["reference", "device"],
                     help="reference: bit-exact sample_mini_batch (O(E) CPU draws per iteration); device: DeviceSampler (O(B), same distribution)")
+    ap.add_argument("--autotune", action="store_true", help="plan-time kernel / plan selection on the training graph (LightGCN.autotune)")
     a = ap.parse_args()
     for style in (["reference", "fused"] if a.style == "both" else [a.style]):
         a.style = style
@@ -68,6 +69,13 @@ def run(a):
 
     t_sample = t_step = t_eval = 0.0
     log = []
+    t_tune, plan = 0.0, None
+    if getattr(a, "autotune", False):
+        _common.sync(); t0 = time.perf_counter()
+        model.autotune(train_sp)
+        _common.sync(); t_tune = time.perf_counter() - t0
+        g = lg.gcn_norm(train_sp, add_self_loops=False).csr()
+        plan = {"forward": g.autotune_report.get("chosen"), "backward": g.transpose().autotune_report.get("chosen")}
     dsampler = lg.DeviceSampler(train_ei) if a.sampler == "device" else None
     for it in range(a.iters):
         t0 = time.perf_counter()
@@ -106,6 +114,7 @@ def run(a):
                               torch.arange(min(num_users, 1024), device=dev), min(256, num_items), seen)
     print(json.dumps({"workload": a.workload if not _common.DRYRUN else "dryrun", "style": a.style, "sampler": a.sampler, "iters": a.iters,
                       "iters_per_s": a.iters / max(t_sample + t_step, 1e-9), "sampler_s": t_sample, "step_s": t_step, "eval_s": t_eval,
+                      "autotune_s": t_tune, "plan": plan,
                       "test": dict(zip(("loss", "recall", "precision", "ndcg"), [round(float(x), 6) for x in test])),
                       "candidates_shape": list(cands.shape), "log": log}), flush=True)
 
