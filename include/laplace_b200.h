@@ -182,13 +182,21 @@ int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const 
  * entries are never gathered: the kernel streams colidx, tests the bitmap and fetches the flagged rows only.  Use: the FIRST
  * layer of the LightGCN backward -- dE_f is non-zero on the <= 3*B rows of the BPR batch (utils/metrics_lightgcn.py:9-45 through
  * the six gathers of run_pipeline_lightgcn.py:133-144), so A^T dE_f touches 3*B of the N operand rows (B = 128: 384 of 1.48 M).
+ * resid_row_bitmap (optional, [ceil(n_rows / 32)] words): the same promise for resid -- rows that are not flagged are not read
+ * (in that backward layer resid is dE_f itself: 351 MB of zeros not fetched, one dependent load less per output row).
  * d <= 64 with d % 4 == 0 uses the filtered kernels; other widths run lgb_spmm's dense kernels.  lgb_rows_bitmap builds the bitmap. */
 int lgb_spmm_rowsparse(const lgb_csr* g, const float* X, const uint32_t* x_row_bitmap, int32_t d, float* Y,
-                       const float* resid, const float* acc_in, float* acc_out, float acc_div, int32_t flags,
-                       float* partial_ws, void* stream);
+                       const float* resid, const uint32_t* resid_row_bitmap, const float* acc_in, float* acc_out,
+                       float acc_div, int32_t flags, float* partial_ws, void* stream);
 /* bitmap[(idx[i] + offset) / 32] |= 1 << ((idx[i] + offset) % 32) for i < n (atomicOr; the caller zeroes the bitmap once per
  * batch, lgb_zero).  Indices outside [0, n_bits) are ignored. */
 int lgb_rows_bitmap(const int64_t* idx, int64_t n, int64_t offset, int64_t n_bits, uint32_t* bitmap, void* stream);
+/* out = scale * a ([n_rows, d]) and, in the same pass, WHICH rows of a hold a non-zero: bit row_offset + r of bitmap is set and
+ * count[0] incremented for each such row r (caller zeroes bitmap and count).  The autograd backward of LightGCN.forward receives dE_f as
+ * a dense tensor (model/lightgcn.py:46-80 under torch autograd: the six row gathers of run_pipeline_lightgcn.py:133-144 scatter
+ * into zeros); this finds its batch rows for lgb_spmm_rowsparse without another pass.  d in {4, 8, 16, 32, 64, 128}. */
+int lgb_scale_rows_nonzero(const float* a, int64_t n_rows, int32_t d, float scale, float* out, int64_t row_offset,
+                           uint32_t* bitmap, int32_t* count, void* stream);
 
 /* scatter-max per destination (PyG aggr="max"): Y[r,:] = max_e X[colidx[e],:] (0 for empty rows),
  * argmax[r,:] = the winning source row (or -1), used by the backward. */

@@ -71,8 +71,9 @@ PROTOTYPES = {
     "lgb_degree_order": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "lgb_spmm": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp]),
     "lgb_spmm_split": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_i64, c_vp, c_vp]),
-    "lgb_spmm_rowsparse": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp]),
+    "lgb_spmm_rowsparse": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp]),
     "lgb_rows_bitmap": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "lgb_scale_rows_nonzero": (C.c_int, [c_vp, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "lgb_segment_max": (C.c_int, [C.POINTER(LgbCsr), c_vp, c_i32, c_vp, c_vp, c_vp]),
     "lgb_segment_max_bwd": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "lgb_row_div_by_degree": (C.c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),

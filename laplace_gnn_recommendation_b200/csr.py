@@ -421,10 +421,12 @@ class DeviceCSR:
     def spmm(self, X: torch.Tensor, Y: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
              acc_in: Optional[torch.Tensor] = None, acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0,
              mean: bool = False, want_y: bool = True, variant: Optional[int] = None, split_row: Optional[int] = None,
-             y_tail: Optional[torch.Tensor] = None, x_rows: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+             y_tail: Optional[torch.Tensor] = None, x_rows: Optional[torch.Tensor] = None,
+             resid_rows: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Y = A @ X with the fused epilogue of lgb_spmm.  Allocates Y when want_y and Y is None.
         ``x_rows``: bitmap (int32 words, ``rows_bitmap``) of the rows of X that may be non-zero -- lgb_spmm_rowsparse: same
-        result, entries that multiply a zero row are never gathered."""
+        result, entries that multiply a zero row are never gathered.  ``resid_rows``: the same kind of bitmap for ``resid`` (used
+        with ``x_rows`` only): rows that are not flagged are not read."""
         _lib.require_cuda(X)
         if X.dim() != 2 or X.shape[0] != self.n_cols:
             raise RuntimeError(f"spmm: X has shape {tuple(X.shape)}, expected [{self.n_cols}, d]")
@@ -453,7 +455,10 @@ class DeviceCSR:
                 if x_rows.dtype != torch.int32 or x_rows.numel() * 32 < self.n_cols or not x_rows.is_contiguous():
                     raise RuntimeError(f"spmm: x_rows must be a contiguous int32 bitmap of >= {self.n_cols} bits")
                 _lib.require_cuda(x_rows)
-                check(lib.lgb_spmm_rowsparse(C.byref(self.struct), ptr(X), ptr(x_rows), d, ptr(Y), ptr(resid), ptr(acc_in),
+                if resid_rows is not None and (resid_rows.dtype != torch.int32 or resid_rows.numel() * 32 < self.n_rows
+                                               or not resid_rows.is_contiguous()):
+                    raise RuntimeError(f"spmm: resid_rows must be a contiguous int32 bitmap of >= {self.n_rows} bits")
+                check(lib.lgb_spmm_rowsparse(C.byref(self.struct), ptr(X), ptr(x_rows), d, ptr(Y), ptr(resid), ptr(resid_rows), ptr(acc_in),
                                              ptr(acc_out), float(acc_div), flags, ptr(self._partial_ws(d)), stream()),
                       "spmm_rowsparse")
             else:

@@ -58,6 +58,7 @@ struct SpmmParams {
   int* tickets;        // [n_long], zero between launches
   const int32_t* task_exec;   // [n_tasks] execution order of the slices (NULL = plan order); partial rows stay indexed by slice id
   const uint32_t* filter;     // row-sparse operand (lgb_spmm_rowsparse): bit c set <=> row c of X may be non-zero; NULL = dense X
+  const uint32_t* resid_filter;   // same for the rows of resid (NULL = dense): a row that is not flagged is not read
 };
 
 // bit test of the row-sparse operand's bitmap (n_cols bits, L1-resident: 185 KB for the H&M-shaped table)
@@ -182,6 +183,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
     return;
   }
   const size_t rowoff = (size_t)r * p.d4;
+  const bool has_resid = p.resid && (!p.resid_filter || filter_hit(p.resid_filter, r));
   if (CONTIG && VPL == 2) {
     // the 256-bit layout (callers guarantee d/4 == 2*G): both float4 of the lane move with ONE load / store each
     const size_t o = rowoff + (size_t)lig * 2;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
       y0.x = __fdiv_rn(y0.x, c); y0.y = __fdiv_rn(y0.y, c); y0.z = __fdiv_rn(y0.z, c); y0.w = __fdiv_rn(y0.w, c);
       y1.x = __fdiv_rn(y1.x, c); y1.y = __fdiv_rn(y1.y, c); y1.z = __fdiv_rn(y1.z, c); y1.w = __fdiv_rn(y1.w, c);
     }
-    if (p.resid) {
+    if (has_resid) {
       const f4x2 t = ld_once_f8(reinterpret_cast<const float4*>(p.resid) + o);
       y0 = f4_add(y0, t.a); y1 = f4_add(y1, t.b);
     }
@@ -219,7 +221,7 @@ __device__ __forceinline__ void epilogue_row(const SpmmParams& p, int r, int deg
       const float c = (float)max(deg, 1);
       y.x = __fdiv_rn(y.x, c); y.y = __fdiv_rn(y.y, c); y.z = __fdiv_rn(y.z, c); y.w = __fdiv_rn(y.w, c);
     }
-    if (p.resid) {
+    if (has_resid) {
       const float4* src = reinterpret_cast<const float4*>(p.resid) + rowoff + f;
       y = f4_add(y, EF ? ld_once_f4_hint(src, pol) : ld_once_f4(src));
     }
@@ -1320,6 +1322,33 @@ __global__ void scale_concat_scalar_kernel(const float* __restrict__ a, int64_t 
   }
 }
 
+// out = scale * a, and which rows of a hold a non-zero: bit r of bitmap, count[0] += rows flagged.  G = d/4 lanes per row (a
+// power of two <= 32), so a warp covers 32/G whole rows per step and one ballot finds them.
+template <int G>
+__global__ void __launch_bounds__(256) scale_rows_nonzero_kernel(const float4* __restrict__ a, int64_t n4, float scale,
+                                                                 float4* __restrict__ out, int64_t row_offset,
+                                                                 uint32_t* __restrict__ bitmap, int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4_up = (n4 + 31) / 32 * 32;                      // warp-uniform trip count (256-thread CTAs, 32-aligned starts)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_up; i += stride) {
+    bool nz = false;
+    if (i < n4) {
+      float4 v = ld_stream_f4(a + i);
+      nz = v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      st_f4(out + i, v);
+    }
+    const unsigned m = __ballot_sync(FULL_MASK, nz);
+    const unsigned gm = (m >> ((lane / G) * G)) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+    if (gm != 0 && lane % G == 0) {
+      const int64_t row = row_offset + i / G;
+      atomicOr(bitmap + (row >> 5), 1u << (row & 31));
+      atomicAdd(count, 1);
+    }
+  }
+}
+
 }  // namespace lgb
 
 namespace lgb {
@@ -1344,14 +1373,40 @@ int lgb_rows_bitmap(const int64_t* idx, int64_t n, int64_t offset, int64_t n_bit
   return LGB_OK;
 }
 
+int lgb_scale_rows_nonzero(const float* a, int64_t n_rows, int32_t d, float scale, float* out, int64_t row_offset, uint32_t* bitmap,
+                           int32_t* count, void* stream_) {
+  LGB_REQUIRE(n_rows >= 0 && d > 0 && row_offset >= 0 && (n_rows == 0 || (a && out && bitmap && count)), LGB_EINVAL, "lgb_scale_rows_nonzero: bad argument");
+  const int d4 = d / 4;
+  LGB_REQUIRE(d % 4 == 0 && d4 <= 32 && (d4 & (d4 - 1)) == 0 && ((((uintptr_t)a | (uintptr_t)out) & 15) == 0), LGB_EINVAL,
+              "lgb_scale_rows_nonzero: d must be 4, 8, 16, 32, 64 or 128 and the rows 16-byte aligned");
+  if (n_rows == 0) return LGB_OK;
+  const int64_t n4 = n_rows * d4;
+  const unsigned blocks = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 16);
+  cudaStream_t st = (cudaStream_t)stream_;
+  const float4* a4 = (const float4*)a;
+  float4* o4 = (float4*)out;
+  int* cnt = (int*)count;
+  switch (d4) {
+    case 1: scale_rows_nonzero_kernel<1><<<blocks, 256, 0, st>>>(a4, n4, scale, o4, row_offset, bitmap, cnt); break;
+    case 2: scale_rows_nonzero_kernel<2><<<blocks, 256, 0, st>>>(a4, n4, scale, o4, row_offset, bitmap, cnt); break;
+    case 4: scale_rows_nonzero_kernel<4><<<blocks, 256, 0, st>>>(a4, n4, scale, o4, row_offset, bitmap, cnt); break;
+    case 8: scale_rows_nonzero_kernel<8><<<blocks, 256, 0, st>>>(a4, n4, scale, o4, row_offset, bitmap, cnt); break;
+    case 16: scale_rows_nonzero_kernel<16><<<blocks, 256, 0, st>>>(a4, n4, scale, o4, row_offset, bitmap, cnt); break;
+    default: scale_rows_nonzero_kernel<32><<<blocks, 256, 0, st>>>(a4, n4, scale, o4, row_offset, bitmap, cnt); break;
+  }
+  LGB_LAUNCH_CHECK();
+  return LGB_OK;
+}
+
 static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
                      float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
-                     void* stream_, const uint32_t* filter = nullptr);
+                     void* stream_, const uint32_t* filter = nullptr, const uint32_t* resid_filter = nullptr);
 
 int lgb_spmm_rowsparse(const lgb_csr* g, const float* X, const uint32_t* x_row_bitmap, int32_t d, float* Y, const float* resid,
-                       const float* acc_in, float* acc_out, float acc_div, int32_t flags, float* partial_ws, void* stream_) {
+                       const uint32_t* resid_row_bitmap, const float* acc_in, float* acc_out, float acc_div, int32_t flags,
+                       float* partial_ws, void* stream_) {
   LGB_REQUIRE(x_row_bitmap, LGB_EINVAL, "lgb_spmm_rowsparse: null bitmap");
-  return spmm_impl(g, X, d, Y, resid, acc_in, acc_out, acc_div, flags, partial_ws, 0, nullptr, stream_, x_row_bitmap);
+  return spmm_impl(g, X, d, Y, resid, acc_in, acc_out, acc_div, flags, partial_ws, 0, nullptr, stream_, x_row_bitmap, resid_row_bitmap);
 }
 
 int lgb_spmm(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
@@ -1374,7 +1429,7 @@ int lgb_spmm_split(const lgb_csr* g, const float* X, int32_t d, float* Y, const 
 
 static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, const float* resid, const float* acc_in,
                      float* acc_out, float acc_div, int32_t flags, float* partial_ws, int64_t split_row, float* y_tail,
-                     void* stream_, const uint32_t* filter) {
+                     void* stream_, const uint32_t* filter, const uint32_t* resid_filter) {
   cudaStream_t stream = (cudaStream_t)stream_;
   LGB_REQUIRE(g && g->rowptr && X && d > 0, LGB_EINVAL, "lgb_spmm: null graph/X or d <= 0");
   LGB_REQUIRE(g->nnz == 0 || g->colidx, LGB_EINVAL, "lgb_spmm: null colidx");
@@ -1398,7 +1453,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   p.part2 = p.n_seg > 0 && partial_ws ? partial_ws + (size_t)p.n_tasks * d + 64 : nullptr;
   p.tickets = p.part2 ? reinterpret_cast<int*>(p.part2 + (size_t)p.n_seg * d) : nullptr;
   p.task_exec = p.n_tasks > 0 ? g->task_exec : nullptr;
-  p.filter = nullptr;
+  p.filter = nullptr; p.resid_filter = nullptr;
   if (p.n_tasks > 0) {
     LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->task_end && g->long_rows && g->long_ptr, LGB_EINVAL,
                 "lgb_spmm: plan has %lld tasks but plan arrays (task_row/start/end, long_rows/ptr) / partial workspace missing",
@@ -1438,6 +1493,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
     // row-sparse operand (lgb_spmm_rowsparse): the filtered forms of the sub-warp kernel with CTA-wide slices; other widths run
     // the dense kernels below (same result: the flagged rows are the only non-zero ones)
     p.filter = filter;
+    p.resid_filter = resid ? resid_filter : nullptr;
     if (d4 == 16 && (all_ptrs & 31) == 0) return launch_subwarp_impl<8, 1, 16, true, 16, false, 2, true, true>(p, stream);
     if (d4 <= 8) return launch_subwarp_impl<8, 2, 16, true, 0, false, 1, false, true>(p, stream);
     return launch_subwarp_impl<16, 2, 16, true, 0, false, 1, false, true>(p, stream);

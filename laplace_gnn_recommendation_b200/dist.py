@@ -147,13 +147,13 @@ class CudaOps:
         return [torch.zeros(*s, dtype=torch.float32, device=self.device) for s in shapes]
 
     # kernels --------------------------------------------------------------------------------------
-    def spmm(self, g, X, Y, resid=None, x_rows=None):
+    def spmm(self, g, X, Y, resid=None, x_rows=None, resid_rows=None):
         if g.n_rows == 0:
             return
         if g.n_cols == 0:                       # a rank without users (world > #users): its partial sums are zero
             Y.zero_() if resid is None else Y.copy_(resid)
             return
-        g.spmm(X, Y=Y, resid=resid, x_rows=x_rows)
+        g.spmm(X, Y=Y, resid=resid, x_rows=x_rows, resid_rows=resid_rows if (x_rows is not None and resid is not None) else None)
 
     def rows_bitmap(self, n, index_lists, key):
         """Bitmap of the rows idx + offset (``(idx, offset)`` pairs; ids outside [0, n) ignored) for ``spmm(x_rows=)``; one
@@ -572,12 +572,14 @@ class ShardedLightGCN:
             yi = self._yi[k]
             yu = last_u if (k == K - 1 and last_u is not None) else self._yu[k]
             with ctx[ci]:
-                ops.spmm(self.g_items, xu, yi, resid=ri, x_rows=rows_u if k == 0 else None)   # partial item rows <- owned users
+                ops.spmm(self.g_items, xu, yi, resid=ri, x_rows=rows_u if k == 0 else None,
+                         resid_rows=rows_i if k == 0 else None)                 # partial item rows <- owned users
                 h = ops.exchange_async(yi, channel=ci)                           # ... summed over ranks
             with ctx[cu]:
                 if pending is not None:
                     pending.wait()                                               # xi = yi_{k-1} must be complete (same chain)
-                ops.spmm(self.g_users, xi, yu, resid=resid_u, x_rows=rows_i if k == 0 else None)   # owned user rows <- all items
+                ops.spmm(self.g_users, xi, yu, resid=resid_u, x_rows=rows_i if k == 0 else None,
+                         resid_rows=rows_u if k == 0 else None)                 # owned user rows <- all items
             yus.append(yu); yis.append(yi)
             xu, xi, pending = yu, yi, h
         ops.join(two)

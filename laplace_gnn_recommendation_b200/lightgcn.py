@@ -87,25 +87,38 @@ def propagate_backward(gt: DeviceCSR, r: torch.Tensor, K: int, out: Optional[tor
             dst = torch.empty_like(r)
             if not last:
                 bufs[k % 2] = dst
-        gt.spmm(g, Y=dst, resid=r, x_rows=r_rows if k == 0 else None)
+        gt.spmm(g, Y=dst, resid=r, x_rows=r_rows if k == 0 else None, resid_rows=r_rows if k == 0 else None)
         g = dst
     return g
 
 
 class _Propagate(torch.autograd.Function):
+    """E_f = mean_k A^k [Wu; Wi], returned as its user and item blocks (two views of one buffer): the backward then receives
+    the two gradient blocks as they are and scales / concatenates them in ONE pass, instead of autograd's cat for a split."""
+
     @staticmethod
     def forward(ctx, Wu, Wi, model: "LightGCN", g: DeviceCSR, K: int):
         E0 = model._table_for(Wu, Wi)
-        ctx.g, ctx.K, ctx.U = g, K, Wu.shape[0]
-        return propagate_forward(g, E0, K)
+        ctx.g, ctx.K, ctx.U, ctx.model = g, K, Wu.shape[0], model
+        ctx.shape = tuple(E0.shape)
+        E_f = propagate_forward(g, E0, K)
+        return E_f[: ctx.U], E_f[ctx.U:]
 
     @staticmethod
-    def backward(ctx, gE):
+    def backward(ctx, gU, gI):
         K, U = ctx.K, ctx.U
-        gE = _lib.f32c(gE)
-        N, d = gE.shape
-        r = _scale_concat(gE, None, N, 0, d, 1.0 / (K + 1), torch.empty_like(gE))
-        G = propagate_backward(ctx.g.transpose(), r, K)
+        N, d = ctx.shape
+        gU = _lib.f32c(gU) if gU is not None else None
+        gI = _lib.f32c(gI) if gI is not None else None
+        dev = (gU if gU is not None else gI).device
+        r = torch.empty(N, d, dtype=torch.float32, device=dev)
+        r_rows = None
+        if ROWSPARSE_BACKWARD and K > 0 and d in (16, 32, 64):
+            # dE_f arrives dense, but under mini-batch BPR only the batch rows are non-zero: the scaling pass notes which
+            r_rows = ctx.model._scale_and_find_rows(gU, gI, U, N - U, d, 1.0 / (K + 1), r)
+        else:
+            _scale_concat(gU, gI, U, N - U, d, 1.0 / (K + 1), r)
+        G = propagate_backward(ctx.g.transpose(), r, K, r_rows=r_rows)
         return G[:U], G[U:], None, None, None
 
 
@@ -161,6 +174,37 @@ class LightGCN(nn.Module):
             buf = self._bitmap = torch.empty((n + 31) // 32, dtype=torch.int32, device=device)
         return buf
 
+    def _scale_and_find_rows(self, gU, gI, U: int, I: int, d: int, scale: float, r: torch.Tensor):
+        """r = scale * [gU; gI] (None = zeros) plus the bitmap of its non-zero rows (lgb_scale_rows_nonzero, one pass per block).
+        Whether the bitmap is worth using (few rows flagged) is a host decision: the row count is read back on the first call and
+        every 64th after it (one small synchronisation each), in between the last answer stands -- a stale answer costs speed,
+        never correctness.  Returns the bitmap, or None when the gradient is (taken to be) dense."""
+        N = U + I
+        dev = r.device
+        bm = self._rows_bitmap_buf(N, dev)
+        cnt = getattr(self, "_rows_count", None)
+        if cnt is None or cnt.device != dev:
+            cnt = self._rows_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            check(lib.lgb_zero(ptr(bm), bm.numel() * 4, stream()), "zero")
+            check(lib.lgb_zero(ptr(cnt), 4, stream()), "zero")
+            for g_blk, lo, n in ((gU, 0, U), (gI, U, I)):
+                if n == 0:
+                    continue
+                if g_blk is None:
+                    check(lib.lgb_zero(ptr(r[lo:lo + n]), n * d * 4, stream()), "zero")
+                else:
+                    check(lib.lgb_scale_rows_nonzero(ptr(g_blk), n, d, float(scale), ptr(r[lo:lo + n]), lo, ptr(bm), ptr(cnt), stream()),
+                          "scale_rows_nonzero")
+                    _lib.count_launch()
+        st = self.__dict__.setdefault("_rows_state", {"calls": 0, "sparse": False})
+        capturing = dev.type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if st["calls"] % 64 == 0 and not capturing:
+            st["sparse"] = int(cnt.item()) * ROWSPARSE_MAX_SHARE <= N
+        st["calls"] += 1
+        return bm if st["sparse"] else None
+
     # ---- plan-time kernel selection (optional) ------------------------------------------------
     def autotune(self, edge_index: SparseTensor, thorough: Optional[bool] = None):
         """Time the SpMM kernel variants on THIS graph (and its transpose, for the backward) at this embedding width and
@@ -187,8 +231,7 @@ class LightGCN(nn.Module):
         if g.n_rows != self.num_users + self.num_items or g.n_cols != g.n_rows:
             raise RuntimeError(f"adjacency is {g.n_rows}x{g.n_cols}, expected a square matrix of "
                                f"{self.num_users + self.num_items} nodes")
-        emb_final = _Propagate.apply(Wu, Wi, self, g, self.num_iterations)
-        users_emb_final, items_emb_final = torch.split(emb_final, [self.num_users, self.num_items])
+        users_emb_final, items_emb_final = _Propagate.apply(Wu, Wi, self, g, self.num_iterations)
         return users_emb_final, Wu, items_emb_final, Wi
 
     def propagate(self, edge_index: SparseTensor, x: torch.Tensor, **kwargs) -> torch.Tensor:

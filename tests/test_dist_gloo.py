@@ -40,9 +40,11 @@ class CpuOracleOps:
     def alloc_exchange(self, shapes):
         return [torch.zeros(*sh) for sh in shapes]
 
-    def spmm(self, g, X, Y, resid=None, x_rows=None):
+    def spmm(self, g, X, Y, resid=None, x_rows=None, resid_rows=None):
         if x_rows is not None:       # the engine's promise behind lgb_spmm_rowsparse: X is zero outside the flagged rows
             assert x_rows.numel() == X.shape[0] and not bool(X[~x_rows].any())
+            if resid_rows is not None and resid is not None:
+                assert resid_rows.numel() == resid.shape[0] and not bool(resid[~resid_rows].any())
             self.rowsparse_calls = getattr(self, "rowsparse_calls", 0) + 1
         y = lo.spmm(g["rowptr"], g["col"], g["val"], X) if X.shape[0] else torch.zeros(g["n"], X.shape[1])
         Y.copy_(y if resid is None else y + resid)

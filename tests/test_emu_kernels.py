@@ -38,6 +38,7 @@ test_spmm_256bit_gathers_d128_vs_oracle = TZ.test_spmm_256bit_gathers_d128_vs_or
 test_spmm_fused_epilogue_and_degree_order = TL.test_spmm_fused_epilogue_and_degree_order
 test_spmm_sweep_order_bit_identical = TL.test_spmm_sweep_order_bit_identical
 test_spmm_rowsparse_matches_dense = TL.test_spmm_rowsparse_matches_dense
+test_lightgcn_small_batch_rowsparse_backward = TL.test_lightgcn_small_batch_rowsparse_backward
 test_lightgcn_against_reference_golden = TL.test_lightgcn_against_reference_golden
 test_lightgcn_against_oracle = TL.test_lightgcn_against_oracle
 test_bpr_against_reference_golden = TL.test_bpr_against_reference_golden

@@ -170,6 +170,8 @@ def test_spmm_rowsparse_matches_dense(cuda_dev, d):
         dense = g.spmm(Xd, resid=Rd)
         sparse = g.spmm(Xd, resid=Rd, x_rows=bm)
         close(sparse, dense, rtol=1e-5, atol=1e-6)
+        # the backward's call shape: resid is the row-sparse operand itself, and its bitmap says which rows to read
+        close(g.spmm(Xd, resid=Xd, x_rows=bm, resid_rows=bm), g.spmm(Xd, resid=Xd), rtol=1e-5, atol=1e-6)
         base = lo.spmm(g.rowptr.cpu().long(), g.colidx.cpu().long(), val.cpu().double(), X.double()).float()
         close(sparse, base + R, rtol=1e-5, atol=1e-6)
         acc = torch.empty(n, d, device=cuda_dev)
@@ -265,7 +267,7 @@ def test_spmm_large_properties(cuda_dev):
 
 # ------------------------------------------------------------------ LightGCN forward/backward + BPR
 def run_case(c, dev, fused):
-    fused = bool(fused)
+    fused = fused in (True, "rowsparse")
     U, I, d, K = c["U"], c["I"], c["d"], c["K"]
     model = lg.LightGCN(U, I, d, K)
     with torch.no_grad():
@@ -285,9 +287,9 @@ def run_case(c, dev, fused):
     return loss, u_f, i_f, model.users_emb.weight.grad, model.items_emb.weight.grad
 
 
-@pytest.mark.parametrize("fused", [False, True, "rowsparse"])
+@pytest.mark.parametrize("fused", [False, True, "rowsparse", "rowsparse-autograd"])
 def test_lightgcn_against_reference_golden(cuda_dev, golden, fused, monkeypatch):
-    if fused == "rowsparse":      # first backward layer through lgb_spmm_rowsparse whatever the table / batch sizes
+    if fused in ("rowsparse", "rowsparse-autograd"):      # first backward layer through lgb_spmm_rowsparse whatever the table / batch sizes
         monkeypatch.setattr(lg.lightgcn, "ROWSPARSE_MAX_SHARE", 0)
     for c in golden["lightgcn"]:
         loss, u_f, i_f, gu, gi = run_case(c, cuda_dev, fused)
@@ -313,6 +315,46 @@ def test_lightgcn_against_oracle(cuda_dev, wiring, K, d):
         loss, u_f, i_f, gu, gi = run_case(c, cuda_dev, fused)
         close(u_f, o_uf); close(i_f, o_if); close(loss, o_loss)
         close(gu, o_gu, atol=1e-9); close(gi, o_gi, atol=1e-9)
+
+
+@pytest.mark.parametrize("wiring", ["R", "S"])
+@pytest.mark.parametrize("d", [64, 32])
+def test_lightgcn_small_batch_rowsparse_backward(cuda_dev, wiring, d, monkeypatch):
+    """A batch that is small against the table (the reference's B = 128 on 1.48 M nodes, here 48 on 4 200): the first backward
+    layer runs as lgb_spmm_rowsparse on its own accord -- from the batch indices in fused_step, from the non-zero rows
+    lgb_scale_rows_nonzero finds in the autograd path -- and the gradients still equal the oracle's."""
+    U, I, E, B, K, lam = 3000, 1200, 40000, 48, 3, 1e-4
+    gen = torch.Generator().manual_seed(d)
+    users = (torch.rand(E, generator=gen) ** 2 * U).long().clamp(max=U - 1)
+    items = (torch.rand(E, generator=gen) ** 3 * I).long().clamp(max=I - 1)          # a few heavy items -> sliced rows
+    row, col, n = (lo.wiring_reference if wiring == "R" else lo.wiring_symmetric)(users, items, U, I)
+    Wu, Wi = torch.randn(U, d, generator=gen) * 0.1, torch.randn(I, d, generator=gen) * 0.1
+    pick = torch.randint(0, E, (B,), generator=gen)
+    c = dict(U=U, I=I, d=d, K=K, row=row, col=col, Wu=Wu, Wi=Wi, lam=lam,
+             u=users[pick], p=items[pick], n=torch.randint(0, I, (B,), generator=gen))
+    rowptr, cc, _ = lo.csr_from_coo(row, col, n, n)
+    o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(Wu, Wi, rowptr, cc, K, c["u"], c["p"], c["n"], lam)
+    monkeypatch.setattr(lg.csr, "DEFAULT_CHUNK", 128)
+    calls = []
+    real = DeviceCSR.spmm
+    monkeypatch.setattr(DeviceCSR, "spmm", lambda self, *a, **k: (calls.append(k.get("x_rows") is not None), real(self, *a, **k))[1])
+    for fused in (False, True):
+        del calls[:]
+        loss, u_f, i_f, gu, gi = run_case(c, cuda_dev, fused)
+        assert calls == [False] * K + [True] + [False] * (K - 1)                       # exactly the first backward layer
+        close(u_f, o_uf); close(i_f, o_if); close(loss, o_loss)
+        close(gu, o_gu, atol=1e-9); close(gi, o_gi, atol=1e-9)
+    # the autograd path found exactly the batch rows
+    model = lg.LightGCN(U, I, d, K).to(cuda_dev)
+    adj = lg.SparseTensor(row=row, col=col, sparse_sizes=(U + I, U + I)).to(cuda_dev)
+    u, p, nn_ = c["u"].to(cuda_dev), c["p"].to(cuda_dev), c["n"].to(cuda_dev)
+    u_f, u_0, i_f, i_0 = model(adj)
+    lg.bpr_loss(u_f[u], u_0[u], i_f[p], i_0[p], i_f[nn_], i_0[nn_], lam).backward()
+    want = torch.zeros(model._bitmap.numel() * 32, dtype=torch.bool)
+    want[c["u"]] = True; want[c["p"] + U] = True; want[c["n"] + U] = True
+    words = model._bitmap.cpu().to(torch.int64) & 0xFFFFFFFF
+    got = ((words[:, None] >> torch.arange(32)[None, :]) & 1).bool().view(-1)
+    assert torch.equal(got, want) and int(model._rows_count) == int(want.sum()) and model._rows_state["sparse"]
 
 
 def test_bpr_against_reference_golden(cuda_dev, golden):
