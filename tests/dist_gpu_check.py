@@ -25,6 +25,8 @@ def main():
         eng = ShardedLightGCN(pb["U"], pb["I"], pb["d"], K, pb["users"], pb["items"], dev,
                               init_tables=(pb["Wu"].to(dev), pb["Wi"].to(dev)),
                               schedule=mode[0], exchange=mode[1], max_batch=512)
+        if os.environ.get("DIST_CHECK_ROWSPARSE") == "1":      # first backward layer as lgb_spmm_rowsparse whatever the sizes
+            eng.rowsparse_ratio = 0
         step = eng.capture(512, pb["lam"]) if "graph" in mode[2:] else (lambda u, p, n: eng.fused_step(u, p, n, pb["lam"]))
         for _ in range(3):                    # repeated: every buffer, signal slot and stream dependency is re-used
             loss = step(pb["u"].to(dev), pb["p"].to(dev), pb["n"].to(dev))
@@ -36,7 +38,7 @@ def main():
         torch.testing.assert_close(eng.E_f[eng.Ug:].cpu(), o_if, **tol)
         torch.testing.assert_close(eng.grad[: eng.Ug].cpu(), o_gu[eng.lo:eng.hi], rtol=1e-5, atol=1e-9)
         torch.testing.assert_close(eng.grad[eng.Ug:].cpu(), o_gi, rtol=1e-5, atol=1e-9)
-    print(f"DIST_OK rank={dist.get_rank()} mode={','.join(mode)} exchange={eng.ops.kind} multicast={getattr(eng.ops, 'multicast', False)} "
+    print(f"DIST_OK rank={dist.get_rank()} mode={','.join(mode)} rowsparse={os.environ.get('DIST_CHECK_ROWSPARSE', '0')} exchange={eng.ops.kind} multicast={getattr(eng.ops, 'multicast', False)} "
           f"users=[{eng.lo},{eng.hi}) edges={eng.local_edges}", flush=True)
     dist.destroy_process_group()
 
