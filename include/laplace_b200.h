@@ -132,6 +132,7 @@ typedef struct lgb_csr {
    * every row -- hence the result, bit for bit -- do not depend on it.  The host plan sorts the slices by their first column
    * ("column sweep"): slices of different long rows that gather the same operand rows run next to each other and find them in L2. */
   const int32_t* task_exec;  /* [n_tasks] */
+  const int32_t* task_seg;   /* [n_tasks] segment of the stage-2 tree plan that slice t belongs to (LGB_SPMM_FUSED_STAGE2), or NULL */
 } lgb_csr;
 
 /* ---------------------------------------------------------------------------------------------
@@ -155,6 +156,13 @@ typedef struct lgb_csr {
  * ------------------------------------------------------------------------------------------- */
 #define LGB_SPMM_MEAN 1
 #define LGB_SPMM_TREE_WS 2     /* partial_ws is sized and zeroed for the stage-2 tree (see above) */
+/* With LGB_SPMM_FUSED_STAGE2 (and LGB_SPMM_TREE_WS, a plan that carries task_seg, and a scratch of n_seg more ZERO ints behind
+ * the tree's: n_tasks*d + 64 + n_seg*d + n_long + n_seg) the sub-warp kernels run the tree INSIDE the main launch: the warp that
+ * stores the last partial row of a segment (a ticket per segment) adds the segment, the warp that finishes the last segment of
+ * a row adds the level-2 rows and runs the epilogue.  Same sums in the same fixed order as the separate stage-2 kernel (who does
+ * them depends on timing, what they compute does not); one launch less per call, and the reductions overlap with the short rows
+ * that follow the slices in the grid.  Kernel families without the fused path ignore the flag and launch stage 2 as before. */
+#define LGB_SPMM_FUSED_STAGE2 4
 /* bits 4..11 of flags pick a kernel variant for A/B measurements (all of them for d in 33..64; 0, 1 and 16 for d <= 32):
  * 0 = tuned default (sub-warp rows: one lane group per short row, 64 resident warps per SM), 1 = first version (warp per
  * row, unroll 8), 2/3 = software-pipelined persistent warps, 4..6, 12 = warp per row at other unroll / occupancy points,

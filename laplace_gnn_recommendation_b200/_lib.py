@@ -28,7 +28,7 @@ class LgbCsr(C.Structure):
         ("long_rows", c_vp), ("long_ptr", c_vp), ("task_row", c_vp), ("task_start", c_vp), ("task_end", c_vp),
         ("colidx_hot", c_vp), ("hot_cols", c_vp), ("n_hot", c_i32), ("_pad2", c_i32),
         ("seg_row", c_vp), ("seg_t0", c_vp), ("seg_t1", c_vp), ("row_seg0", c_vp), ("n_seg", c_i64),
-        ("task_exec", c_vp),
+        ("task_exec", c_vp), ("task_seg", c_vp),
     ]
 
 

@@ -24,7 +24,9 @@ DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
 # execute long-row slices in column-sweep order by default (DeviceCSR.use_sweep_order; autotune decides per graph when it runs)
 DEFAULT_SWEEP = os.environ.get("LGB_SPMM_SWEEP", "0") == "1"
 STAGE2_SEG = 32                                                   # partial rows per warp of the stage-2 tree
-STAGE2_TREE = os.environ.get("LGB_SPMM_STAGE2", "tree") != "flat"  # flat = one CTA per long row (the round-1 stage 2), for A/B
+STAGE2_MODE = os.environ.get("LGB_SPMM_STAGE2", "tree")           # flat = one CTA per long row (the round-1 stage 2) | tree | fused
+STAGE2_TREE = STAGE2_MODE != "flat"
+STAGE2_FUSED = STAGE2_MODE == "fused"                              # the tree inside the main launch (LGB_SPMM_FUSED_STAGE2)
 
 
 # candidates of DeviceCSR.autotune for d <= 64: the default sub-warp kernel, its CTA-wide-slice and chain-shortening forms,
@@ -92,7 +94,7 @@ class DeviceCSR:
         self.n_tasks = 0
         self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = None
         self.n_seg = 0
-        self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = None
+        self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = self.task_seg = None
         self.sweep = DEFAULT_SWEEP                         # execute the long-row slices in column-sweep order: use_sweep_order()
         self.task_exec: Optional[torch.Tensor] = None
         self.perm: Optional[torch.Tensor] = None      # COO -> CSR permutation (int64) when built from COO
@@ -202,6 +204,8 @@ class DeviceCSR:
         self.seg_row, self.seg_t0 = seg_row.to(i32), first.to(i32)
         self.seg_t1 = torch.minimum(first + STAGE2_SEG, lp[seg_row + 1]).to(i32)
         self.row_seg0 = row_seg0.to(i32)
+        # segment of every slice (fused stage 2): the segments tile the slices in order
+        self.task_seg = torch.repeat_interleave(torch.arange(self.n_seg, device=self.device), (self.seg_t1 - self.seg_t0).long()).to(i32)
 
     def use_degree_order(self, on: bool = True) -> "DeviceCSR":
         """Process ordinary rows in descending degree-bucket order (better intra-CTA balance on skewed graphs)."""
@@ -303,7 +307,7 @@ class DeviceCSR:
             self.chunk = int(chunk)
             self.n_long = self.n_tasks = self.n_seg = 0
             self.long_rows = self.long_ptr = self.task_row = self.task_start = self.task_end = self.task_exec = None
-            self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = None
+            self.seg_row = self.seg_t0 = self.seg_t1 = self.row_seg0 = self.task_seg = None
             if self.chunk > 0:
                 self._build_plan()
             self._struct = None
@@ -400,6 +404,7 @@ class DeviceCSR:
             s.seg_row, s.seg_t0, s.seg_t1, s.row_seg0 = ptr(self.seg_row), ptr(self.seg_t0), ptr(self.seg_t1), ptr(self.row_seg0)
             s.n_seg = int(self.n_seg)
             s.task_exec = ptr(self.task_exec)
+            s.task_seg = ptr(self.task_seg)
             self._struct = s
         return self._struct
 
@@ -413,7 +418,8 @@ class DeviceCSR:
         if buf is None:
             # behind the partial sums: 64 floats for the work counters of the hot-column kernels (variants 30 / 31), the level-2
             # rows and the tickets of the stage-2 tree; all of it starts at zero and every launch leaves counters / tickets zero
-            buf = torch.zeros(self.n_tasks * d + 64 + self.n_seg * d + self.n_long + 64, dtype=torch.float32, device=self.device)
+            # ... and the segment tickets of the fused stage 2
+            buf = torch.zeros(self.n_tasks * d + 64 + self.n_seg * d + self.n_long + self.n_seg + 64, dtype=torch.float32, device=self.device)
             self._partials[key] = buf
         return buf
 
@@ -442,7 +448,7 @@ class DeviceCSR:
             variant = SPMM_VARIANT if self.variant is None else self.variant
         if variant in (30, 31) and self.n_hot == 0 and os.environ.get("LGB_SPMM_HOT"):
             self.set_hot(int(os.environ["LGB_SPMM_HOT"]))      # a variant pinned from the environment brings its plan along
-        flags = (1 if mean else 0) | (2 if (STAGE2_TREE and self.n_seg) else 0) | (variant << 4)
+        flags = (1 if mean else 0) | (2 if (STAGE2_TREE and self.n_seg) else 0) | (4 if (STAGE2_FUSED and self.n_seg) else 0) | (variant << 4)
         with torch.cuda.device(self.device):
             if y_tail is not None:
                 # split epilogue: rows >= split_row write raw sums to y_tail (see lgb_spmm_split)

@@ -59,7 +59,13 @@ struct SpmmParams {
   const int32_t* task_exec;   // [n_tasks] execution order of the slices (NULL = plan order); partial rows stay indexed by slice id
   const uint32_t* filter;     // row-sparse operand (lgb_spmm_rowsparse): bit c set <=> row c of X may be non-zero; NULL = dense X
   const uint32_t* resid_filter;   // same for the rows of resid (NULL = dense): a row that is not flagged is not read
+  const int32_t* task_seg;    // fused stage 2 (LGB_SPMM_FUSED_STAGE2): segment of slice t; NULL = stage 2 is a launch of its own
+  int* seg_tickets;           // [n_seg], zero between launches
+  const int32_t* task_seg_plan;   // host side only: the plan's task_seg when the call allows the fused stage 2 (the sub-warp
+                                  // launcher copies it into task_seg; other kernel families leave task_seg NULL)
 };
+
+__device__ __forceinline__ void slice_done(const SpmmParams& p, int64_t t, int lane);
 
 // bit test of the row-sparse operand's bitmap (n_cols bits, L1-resident: 185 KB for the H&M-shaped table)
 __device__ __forceinline__ bool filter_hit(const uint32_t* __restrict__ filter, int c) {
@@ -498,6 +504,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
           st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)t * d4 + f, sum);
         }
       }
+      if (wi == 0 && p.task_seg) slice_done(p, t, lane);     // fused stage 2: the warp that stored the partial row
       return;
     }
     w = p.n_tasks + ((int64_t)blockIdx.x - p.n_tasks) * SPMM_WARPS + (threadIdx.x >> 5);
@@ -519,6 +526,7 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(con
         if (f < d4) st_f4(reinterpret_cast<float4*>(p.partial) + (size_t)t * d4 + f, acc[q]);
       }
     }
+    if (p.task_seg) slice_done(p, t, lane);
     return;
   }
   const int64_t first = (w - p.n_tasks) * NG;
@@ -681,8 +689,10 @@ static int launch_subwarp(const SpmmParams& p, cudaStream_t stream) {
 }
 
 template <int G, int UNROLL, int MINB, bool WIDE, int D4C, bool PF, int VPL, bool W256, bool FILTER>
-static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
+static int launch_subwarp_impl(const SpmmParams& p_in, cudaStream_t stream) {
   constexpr int NG = 32 / G;
+  SpmmParams p = p_in;
+  p.task_seg = p_in.task_seg_plan;                   // this family runs the fused stage 2 when the call allows it
   const int64_t row_warps = (p.n_rows + NG - 1) / NG;
   const int64_t warps = p.n_tasks + row_warps;
   if (warps > 0) {
@@ -691,6 +701,7 @@ static int launch_subwarp_impl(const SpmmParams& p, cudaStream_t stream) {
     spmm_subwarp_kernel<G, UNROLL, MINB, WIDE, D4C, PF, VPL, W256, FILTER><<<(unsigned)blocks, SPMM_WARPS * 32, 0, stream>>>(p);
     LGB_LAUNCH_CHECK();
   }
+  if (p.task_seg) return LGB_OK;                     // stage 2 ran inside the launch (slice_done)
   { const int rc2 = launch_stage2<G, VPL>(p, stream); if (rc2) return rc2; }
   return LGB_OK;
 }
@@ -958,6 +969,76 @@ __global__ void __launch_bounds__(128) spmm_long_reduce_tree_kernel(const SpmmPa
       tot = f4_add(tot, pick_col(v, lane));
     }
     if (lane < TREE_CB && c0 + lane < d4) epilogue_col(p, r, deg, c0 + lane, tot);
+  }
+  if (lane == 0) p.tickets[L] = 0;
+}
+
+// Fused stage 2 (LGB_SPMM_FUSED_STAGE2): called by the ONE warp that has just stored partial row t.  The last slice of a
+// segment to arrive adds the segment's partial rows, the last segment of a row adds the level-2 rows and runs the epilogue --
+// the tree kernel above, executed by whoever finishes last.  Four float4 columns per pass (16 registers of payload: this code
+// shares the 32-register budget of the gather kernel it is linked into, and it is off the hot path -- one call in 32 does work).
+constexpr int FUSE_CB = 4;
+
+__device__ __forceinline__ void fuse_sum32(const float4* __restrict__ rows, int t0, int t1, int d4, int c0, int lane, float4 (&v)[FUSE_CB]) {
+  const bool have = t0 + lane < t1;
+  const float4* src = rows + (size_t)(t0 + lane) * d4 + c0;
+#pragma unroll
+  for (int f = 0; f < FUSE_CB; ++f) v[f] = (have && c0 + f < d4) ? ld_cg_f4(src + f) : f4_zero();   // written by other SMs: L2
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int f = 0; f < FUSE_CB; ++f) v[f] = f4_add(v[f], f4_shfl_xor(v[f], off));
+}
+
+__device__ __forceinline__ float4 fuse_pick(const float4 (&v)[FUSE_CB], int lane) {
+  float4 m = v[0];
+#pragma unroll
+  for (int f = 1; f < FUSE_CB; ++f)
+    if ((lane & (FUSE_CB - 1)) == f) m = v[f];
+  return m;
+}
+
+__device__ __forceinline__ void slice_done(const SpmmParams& p, int64_t t, int lane) {
+  __threadfence();                                   // partial row t is visible device-wide before the ticket is taken
+  const int seg = p.task_seg[t];
+  const int t0 = p.seg_t0[seg], t1 = p.seg_t1[seg];
+  int ticket = 0;
+  if (lane == 0) ticket = atomicAdd(p.seg_tickets + seg, 1);
+  ticket = __shfl_sync(FULL_MASK, ticket, 0);
+  if (ticket != t1 - t0 - 1) return;
+  __threadfence();                                   // every other slice of the segment has published its partial row
+  if (lane == 0) p.seg_tickets[seg] = 0;             // nobody takes this ticket again in this launch
+  const int L = p.seg_row[seg];
+  const int s0 = p.row_seg0[L], nseg = p.row_seg0[L + 1] - s0;
+  const int r = p.long_rows[L];
+  const int deg = p.rowptr[r + 1] - p.rowptr[r];
+  const int d4 = p.d4;
+  const float4* part = reinterpret_cast<const float4*>(p.partial);
+  float4* part2 = reinterpret_cast<float4*>(p.part2);
+  float4 v[FUSE_CB];
+  if (nseg == 1) {
+    for (int c0 = 0; c0 < d4; c0 += FUSE_CB) {
+      fuse_sum32(part, t0, t1, d4, c0, lane, v);
+      if (lane < FUSE_CB && c0 + lane < d4) epilogue_col(p, r, deg, c0 + lane, fuse_pick(v, lane));
+    }
+    return;
+  }
+  for (int c0 = 0; c0 < d4; c0 += FUSE_CB) {
+    fuse_sum32(part, t0, t1, d4, c0, lane, v);
+    if (lane < FUSE_CB && c0 + lane < d4) st_f4(part2 + (size_t)seg * d4 + c0 + lane, fuse_pick(v, lane));
+  }
+  __threadfence();
+  if (lane == 0) ticket = atomicAdd(p.tickets + L, 1);
+  ticket = __shfl_sync(FULL_MASK, ticket, 0);
+  if (ticket != nseg - 1) return;
+  __threadfence();
+  for (int c0 = 0; c0 < d4; c0 += FUSE_CB) {
+    float4 tot = f4_zero();
+    for (int b = s0; b < s0 + nseg; b += 32) {       // fixed order: segment blocks ascending, butterfly inside a block
+      fuse_sum32(part2, b, min(b + 32, s0 + nseg), d4, c0, lane, v);
+      tot = f4_add(tot, fuse_pick(v, lane));
+    }
+    if (lane < FUSE_CB && c0 + lane < d4) epilogue_col(p, r, deg, c0 + lane, tot);
   }
   if (lane == 0) p.tickets[L] = 0;
 }
@@ -1454,6 +1535,11 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   p.tickets = p.part2 ? reinterpret_cast<int*>(p.part2 + (size_t)p.n_seg * d) : nullptr;
   p.task_exec = p.n_tasks > 0 ? g->task_exec : nullptr;
   p.filter = nullptr; p.resid_filter = nullptr;
+  // fused stage 2: only the sub-warp family runs it; the tickets of the segments sit behind the tree's row tickets
+  p.task_seg = nullptr; p.seg_tickets = nullptr;
+  const bool want_fused2 = (flags & LGB_SPMM_FUSED_STAGE2) && p.n_seg > 0 && p.tickets && g->task_seg;
+  p.task_seg_plan = want_fused2 ? g->task_seg : nullptr;
+  p.seg_tickets = want_fused2 ? p.tickets + p.n_long : nullptr;
   if (p.n_tasks > 0) {
     LGB_REQUIRE(partial_ws && g->task_row && g->task_start && g->task_end && g->long_rows && g->long_ptr, LGB_EINVAL,
                 "lgb_spmm: plan has %lld tasks but plan arrays (task_row/start/end, long_rows/ptr) / partial workspace missing",

@@ -41,7 +41,7 @@ def test_ctypes_table_matches_header(lib):
 
 def test_struct_layouts():
     from laplace_gnn_recommendation_b200._lib import LgbBprArgs, LgbCsr
-    assert C.sizeof(LgbCsr) == 3 * 8 + 4 * 8 + 8 + 2 * 8 + 5 * 8 + 2 * 8 + 8 + 4 * 8 + 8 + 8  # mirrors struct lgb_csr (ABI 2: + hot-column plan, ABI 3: + stage-2 segments, ABI 4: + task_exec)
+    assert C.sizeof(LgbCsr) == 3 * 8 + 4 * 8 + 8 + 2 * 8 + 5 * 8 + 2 * 8 + 8 + 4 * 8 + 8 + 2 * 8  # mirrors struct lgb_csr (ABI 2: + hot-column plan, ABI 3: + stage-2 segments, ABI 4: + task_exec, task_seg)
     assert C.sizeof(LgbBprArgs) == 9 * 8 + 8 + 8 + 4 * 4 + 2 * 8 + 8 + 6 * 8 + 2 * 8            # mirrors struct lgb_bpr_args
 
 

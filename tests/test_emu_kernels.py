@@ -38,6 +38,13 @@ test_spmm_256bit_gathers_d128_vs_oracle = TZ.test_spmm_256bit_gathers_d128_vs_or
 test_spmm_fused_epilogue_and_degree_order = TL.test_spmm_fused_epilogue_and_degree_order
 test_spmm_sweep_order_bit_identical = TL.test_spmm_sweep_order_bit_identical
 test_spmm_rowsparse_matches_dense = TL.test_spmm_rowsparse_matches_dense
+
+
+@pytest.mark.parametrize("variant,d", [(0, 64), (23, 64), (16, 48)])
+def test_spmm_fused_stage2_bit_identical(cuda_dev, variant, d, monkeypatch):
+    TL.test_spmm_fused_stage2_bit_identical(cuda_dev, variant, d, monkeypatch)       # (the GPU tier runs every combination)
+
+
 test_lightgcn_small_batch_rowsparse_backward = TL.test_lightgcn_small_batch_rowsparse_backward
 test_lightgcn_against_reference_golden = TL.test_lightgcn_against_reference_golden
 test_lightgcn_against_oracle = TL.test_lightgcn_against_oracle

@@ -141,6 +141,40 @@ def test_spmm_sweep_order_bit_identical(cuda_dev, variant):
     assert g.task_exec is None and torch.equal(g.spmm(X, variant=variant), y0)
 
 
+@pytest.mark.parametrize("variant,d", [(0, 64), (16, 64), (20, 64), (23, 64), (0, 32), (16, 48), (12, 64)])
+def test_spmm_fused_stage2_bit_identical(cuda_dev, variant, d, monkeypatch):
+    """LGB_SPMM_FUSED_STAGE2: the stage-2 tree run inside the main launch (by whichever warp stores the last partial row of a
+    segment / finishes the last segment of a row) gives the bits of the separate tree kernel, launch after launch (tickets
+    reset themselves); kernel families without the fused path (variant 12) ignore the flag."""
+    n, nnz = 200, 50000
+    row, col = random_graph(31, n, n, nnz, skew=True)
+    g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n, n, chunk=8)        # row 0: ~13 000 entries -> > 32 segments
+    _, val = g.gcn_norm()
+    g = g.with_values(val).use_sweep_order(True)
+    assert g.n_seg > 40 and int((g.row_seg0[1:] - g.row_seg0[:-1]).max()) > 32 and g.task_seg.numel() == g.n_tasks
+    gen = torch.Generator().manual_seed(3)
+    X, R, A = (torch.randn(n, d, generator=gen).to(cuda_dev) for _ in range(3))
+    monkeypatch.setattr(lg.csr, "STAGE2_FUSED", False)
+    y_tree = g.spmm(X, resid=R, variant=variant)
+    acc_tree = torch.empty(n, d, device=cuda_dev)
+    g.spmm(X, want_y=False, acc_in=A, acc_out=acc_tree, acc_div=4.0, variant=variant)
+    monkeypatch.setattr(lg.csr, "STAGE2_FUSED", True)
+    for _ in range(3):
+        assert torch.equal(g.spmm(X, resid=R, variant=variant), y_tree)
+    acc = torch.empty(n, d, device=cuda_dev)
+    g.spmm(X, want_y=False, acc_in=A, acc_out=acc, acc_div=4.0, variant=variant)
+    assert torch.equal(acc, acc_tree)
+    ws = g._partial_ws(d)
+    assert not bool(ws[g.n_tasks * d + 64 + g.n_seg * d:].any())                       # every ticket back at zero
+    bm = lg.rows_bitmap(n, ((torch.arange(0, n, 7, device=cuda_dev), 0),), cuda_dev)
+    Xs = torch.zeros(n, d, device=cuda_dev); Xs[::7] = X[::7]
+    if d % 4 == 0 and d <= 64:
+        monkeypatch.setattr(lg.csr, "STAGE2_FUSED", False)
+        want = g.spmm(Xs, resid=Xs, x_rows=bm, resid_rows=bm)
+        monkeypatch.setattr(lg.csr, "STAGE2_FUSED", True)
+        assert torch.equal(g.spmm(Xs, resid=Xs, x_rows=bm, resid_rows=bm), want)
+
+
 @pytest.mark.parametrize("d", [64, 32, 48, 20, 128, 6])
 def test_spmm_rowsparse_matches_dense(cuda_dev, d):
     """lgb_spmm_rowsparse (operand zero outside the rows of a bitmap: entries that multiply a zero row are never gathered)
