@@ -24,7 +24,10 @@ DEFAULT_CHUNK = int(os.environ.get("LGB_SPMM_CHUNK", "1024"))
 # execute long-row slices in column-sweep order by default (DeviceCSR.use_sweep_order; autotune decides per graph when it runs)
 DEFAULT_SWEEP = os.environ.get("LGB_SPMM_SWEEP", "0") == "1"
 STAGE2_SEG = 32                                                   # partial rows per warp of the stage-2 tree
-STAGE2_MODE = os.environ.get("LGB_SPMM_STAGE2", "tree")           # flat = one CTA per long row (the round-1 stage 2) | tree | fused
+# stage 2 (sum of the partial rows of a sliced row): flat = one CTA per long row (round 1) | tree = one warp per 32 partial rows,
+# a launch of its own | fused = the tree inside the main launch (default: -2 % epoch time at N = 1, -8 % per SpMM pair on a 1/8
+# shard, profiles/README.md r2r; kernel families without the fused path fall back to the tree)
+STAGE2_MODE = os.environ.get("LGB_SPMM_STAGE2", "fused")
 STAGE2_TREE = STAGE2_MODE != "flat"
 STAGE2_FUSED = STAGE2_MODE == "fused"                              # the tree inside the main launch (LGB_SPMM_FUSED_STAGE2)
 
@@ -38,6 +41,8 @@ AUTOTUNE_CANDIDATES = (0, 16, 18, 19, 12, 13, 20, 22, 23, 25)
 # than the sub-warp kernel on both halves of the H&M graph (the L1 already keeps the hottest rows; persistent 1024-thread CTAs
 # lose the block scheduler's fine-grained balancing): kept as variants, tried by autotune only with LGB_SPMM_TRY_HOT=1 / hot=
 HOT_CANDIDATES = ((30, 256), (31, 512), (31, 768))
+# variants served by the sub-warp kernel family at d <= 64 (the family that carries the fused stage 2); launch accounting only
+FUSED_STAGE2_VARIANTS = frozenset((0, 13, 14, 15, 16, 18, 19, 20, 21, 22, 23, 24, 25))
 
 
 def _time_ms(fn, reps: int, device) -> float:
@@ -470,5 +475,6 @@ class DeviceCSR:
             else:
                 check(lib.lgb_spmm(C.byref(self.struct), ptr(X), d, ptr(Y), ptr(resid), ptr(acc_in), ptr(acc_out),
                                    float(acc_div), flags, ptr(self._partial_ws(d)), stream()), "spmm")
-        _lib.count_launch(2 if self.n_long else 1)
+        fused = STAGE2_FUSED and self.n_seg and variant in FUSED_STAGE2_VARIANTS and d % 4 == 0 and d <= 64
+        _lib.count_launch(2 if (self.n_long and not fused) else 1)
         return Y
