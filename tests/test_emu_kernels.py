@@ -37,10 +37,15 @@ test_spmm_64bit_index_family_vs_oracle = TZ.test_spmm_64bit_index_family_vs_orac
 test_spmm_256bit_gathers_d128_vs_oracle = TZ.test_spmm_256bit_gathers_d128_vs_oracle
 test_spmm_fused_epilogue_and_degree_order = TL.test_spmm_fused_epilogue_and_degree_order
 test_spmm_sweep_order_bit_identical = TL.test_spmm_sweep_order_bit_identical
-test_spmm_rowsparse_matches_dense = TL.test_spmm_rowsparse_matches_dense
 
 
-@pytest.mark.parametrize("variant,d", [(0, 64), (23, 64), (16, 48)])
+@pytest.mark.parametrize("d", [64, 32, 48, 20])                 # the three filtered kernel shapes (256-bit, d/4 <= 8, d/4 <= 16)
+def test_spmm_rowsparse_matches_dense(cuda_dev, d):
+    TL.test_spmm_rowsparse_matches_dense(cuda_dev, d)          # (the GPU tier also runs the dense fallbacks: d = 128, d = 6)
+
+
+
+@pytest.mark.parametrize("variant,d", [(0, 64), (23, 64)])
 def test_spmm_fused_stage2_bit_identical(cuda_dev, variant, d, monkeypatch):
     TL.test_spmm_fused_stage2_bit_identical(cuda_dev, variant, d, monkeypatch)       # (the GPU tier runs every combination)
 
