@@ -452,20 +452,20 @@ __global__ void __launch_bounds__(SPMM_WARPS * 32) spmm_pipe_kernel(const SpmmPa
 // group, when all of them are short (<= SUBW_MAX non-zeros); otherwise it walks them one by one with the whole warp
 // (the spmm_rows_kernel path).  No cross-group reduction in sub-warp mode; per-row summation order is plain ascending.
 //
-// WIDE (variant 16, measurement pending): a slice of a long row is shared by the SPMM_WARPS warps of ONE CTA (warp i takes
+// WIDE (variant 16; measured in round 2 -- every plan the autotune picks on the H&M graph uses it): a slice of a long row is shared by the SPMM_WARPS warps of ONE CTA (warp i takes
 // the 32-entry batches i, i+4, ...; the four sums are added in warp order through shared memory).  Scaling measurements
 // (profiles/README.md r1c) fit  t_launch = 0.09 ms + nnz / 34 G/s : the constant is the dependent-iteration chain of one
 // chunk-sized slice at gather-unroll 2, which bounds the launch from below once the graph is sharded 4-8 ways.  Sharing
 // the slice cuts that chain by SPMM_WARPS without more registers, more partial rows or more long rows.
 constexpr int SUBW_MAX = 64;
 
-// PF (variant 18, measurement pending): shortens the dependent chain of a short row by two memory round trips -- the
+// PF (variant 18; measured in round 2: within 2 % of the plain form, never the winner on the H&M graph): shortens the dependent chain of a short row by two memory round trips -- the
 // epilogue operands (acc_in / resid rows, streamed from DRAM) are requested into L2 as soon as the row id is known, and the
 // second batch of (col,val) pairs of rows with more than G entries is loaded before the first batch is consumed.
-// VPL > 1 (variants 20/21, measurement pending): a lane holds VPL float4 of the row, so a row needs only G = d/(4*VPL) lanes
+// VPL > 1 (variants 20/21; measured in round 2: the winner on item-row views, profiles/README.md r2a): a lane holds VPL float4 of the row, so a row needs only G = d/(4*VPL) lanes
 // and a warp runs 32/G row chains at once (d = 64: G = 8, VPL = 2 -> four rows per warp, half the shuffles and address
 // arithmetic per non-zero).
-// W256 (variants 23-25, d = 64 only, measurement pending): the short-row path fetches a lane's two float4 with ONE 256-bit
+// W256 (variants 23-25, d = 64 only; measured in round 2: variant 23 is the plan that ships at N = 1, r2d / r2n): the short-row path fetches a lane's two float4 with ONE 256-bit
 // load (sm_100's LDG.E.256) -- a 256-byte row = one load instruction of 8 lanes, four rows per warp-level load.
 template <int G, int UNROLL, int MINB, bool WIDE = false, int D4C = 0, bool PF = false, int VPL = 1, bool W256 = false, bool FILTER = false>
 __global__ void __launch_bounds__(SPMM_WARPS * 32, MINB) spmm_subwarp_kernel(const SpmmParams p) {
@@ -1616,7 +1616,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
       case 13: return launch_subwarp<16, 4, 12>(p, stream);
       case 14: return launch_subwarp<16, 4, 10>(p, stream);
       case 15: return launch_subwarp<16, 8, 8>(p, stream);
-      case 16: return launch_subwarp<16, 2, 16, true>(p, stream);   // sub-warp rows + one CTA per slice (measurement pending)
+      case 16: return launch_subwarp<16, 2, 16, true>(p, stream);   // sub-warp rows + one CTA per slice
       case 18: return launch_subwarp<16, 2, 16, false, true>(p, stream);   // sub-warp rows + chain-shortening prefetches
       case 19: return launch_subwarp<16, 2, 16, true, true>(p, stream);    // 16 + 18
       case 20: return launch_subwarp<8, 1, 16, true, false, 2>(p, stream);  // four rows per warp (8 lanes x 2 float4), unroll 1
@@ -1631,7 +1631,7 @@ static int spmm_impl(const lgb_csr* g, const float* X, int32_t d, float* Y, cons
   }
   if (d4 <= 32) {
     if (variant == 1) return launch_vec<32, 1, 8>(p, 1, stream);
-    // 26: d = 128 with 256-bit gathers -- 16 lanes x 32 bytes per row, two rows per warp-level load (measurement pending)
+    // 26: d = 128 with 256-bit gathers -- 16 lanes x 32 bytes per row, two rows per warp-level load (r2a sweep: d = 128 picks 26 / 27 on some shards)
     if (variant == 26 && d4 == 32) return launch_vec<16, 2, 1, 16, uint32_t, 32, true>(p, 1, stream);
     if (variant == 27 && d4 == 32) return launch_vec<16, 2, 2, 10, uint32_t, 32, true>(p, 1, stream);
     return launch_vec<32, 1, 2, 16>(p, 1, stream);
