@@ -490,7 +490,9 @@ class ShardedLightGCN:
         for name, g in (("users", self.g_users), ("items", self.g_items)):
             # the item rows gather from the local user shard (H&M shape: 351 MB / world, beyond the L2 up to 4 ranks): also try
             # their long-row slices in column-sweep order (csr.py use_sweep_order); the user rows gather from the L2-resident item block
-            g.autotune(self.d, fused_epilogue=False, chunks=chunks, sweeps=(False, True) if name == "items" else (False,))
+            # degree-bucket row order: 18 % on the user rows at N = 1 (profiles/README.md r2u), tried on both views
+            g.autotune(self.d, fused_epilogue=False, chunks=chunks, sweeps=(False, True) if name == "items" else (False,),
+                       degree_orders=(False, True))
             out[name] = dict(g.autotune_report.get("chosen", {"variant": g.variant}), ms=g.autotune_report["ms"],
                              rejected=g.autotune_report["rejected"])
         return out

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--chunks", default="1024,256")
     ap.add_argument("--degree", default="powerlaw")
     ap.add_argument("--d", type=int, default=64)
+    ap.add_argument("--degree-orders", default="0", help="comma list of 0/1: ordinary rows in natural / degree-bucket order")
     a = ap.parse_args()
     dev = _common.device()
     U, I, E = WORKLOADS["hm"]
@@ -62,7 +63,10 @@ def main():
                 return v
             gu, gi = view(gu0), view(gi0)
             print(f"  chunk {chunk}: users view long={gu.n_long} tasks={gu.n_tasks} | items view long={gi.n_long} tasks={gi.n_tasks}")
-            for v in [int(x) for x in a.variants.split(",")]:
+            for v, order in [(int(x), bool(int(o))) for o in a.degree_orders.split(",") for x in a.variants.split(",")]:
+                gu.use_degree_order(order); gi.use_degree_order(order)
+                if len(a.degree_orders.split(",")) > 1:
+                    print(f"    degree order {int(order)}:", end="")
                 t_i = timeit(lambda: gi.spmm(Xu, Y=Yi, variant=v))
                 t_u = timeit(lambda: gu.spmm(Xi, Y=Yu, resid=R, variant=v))
                 t_b = timeit(lambda: both(gu, gi, v)) if not _common.DRYRUN else float("nan")

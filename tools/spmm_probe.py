@@ -14,6 +14,29 @@ from bench import WORKLOADS, make_graph, spmm_bytes  # noqa: E402
 from laplace_gnn_recommendation_b200.dist import CudaOps  # noqa: E402
 
 
+def locality_order(h, kind):
+    """Row order = descending degree bucket (like lgb_degree_order), inside a bucket sorted by a column key of the row."""
+    rp = h.rowptr.long()
+    deg = rp[1:] - rp[:-1]
+    n = deg.numel()
+    lo, hi = int(rp[0]), int(rp[-1])
+    cols = h.colidx[lo:hi].long()
+    bucket = torch.where(deg <= 1, deg, 1 + torch.ceil(torch.log2(deg.clamp(min=2).double())).long())
+    if kind == "firstcol":
+        key = torch.where(deg > 0, h.colidx[(rp[:-1]).clamp(max=max(hi - 1, 0))].long(), torch.full_like(deg, h.n_cols))
+    else:
+        coldeg = torch.bincount(cols, minlength=h.n_cols)
+        rows_of_e = torch.repeat_interleave(torch.arange(n, device=rp.device), deg)
+        vals = coldeg[cols]
+        m = torch.zeros(n, dtype=vals.dtype, device=rp.device).scatter_reduce_(0, rows_of_e, vals, "amax", include_self=True)
+        idx = torch.nonzero(vals == m[rows_of_e]).view(-1)
+        key = torch.full((n,), h.n_cols, dtype=torch.long, device=rp.device)
+        key[rows_of_e[idx]] = cols[idx]
+    o1 = torch.argsort(key, stable=True)
+    o2 = torch.argsort(-bucket[o1], stable=True)
+    return o1[o2].to(torch.int32).contiguous()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--degree", default="powerlaw")
@@ -22,6 +45,8 @@ def main():
     ap.add_argument("--workload", default="hm")
     ap.add_argument("--chunks", default="", help="slice sizes of the long-row plan to walk (default: the library default)")
     ap.add_argument("--rowsparse", type=int, default=0, help="B > 0: also time lgb_spmm_rowsparse on an operand that is zero outside the 3B rows of a BPR batch")
+    ap.add_argument("--row-orders", default="", help="comma list of none|degree|firstcol|hotcol: processing order of the ordinary rows "
+                    "(firstcol / hotcol: degree buckets, and inside a bucket rows sorted by their first / their most-referenced column)")
     ap.add_argument("--sweep", default="0", help="comma list of 0/1: long-row slices in plan order / column-sweep order")
     a = ap.parse_args()
     dev = _common.device()
@@ -51,6 +76,26 @@ def main():
         deg = (g.rowptr[1:] - g.rowptr[:-1]).long()
         print(f"rowsparse: {torch.unique(rows).numel()} operand rows flagged; entries that hit them: {int(deg[torch.unique(rows)].sum())} of {g.nnz}")
     chunks = [int(x) for x in a.chunks.split(",")] if a.chunks else [g.chunk]
+    if a.row_orders:
+        chunk, v = chunks[0], int(a.variants.split(",")[0])
+        for h in (g, gu, gi):
+            h._set_chunk(chunk)
+            h.use_sweep_order(bool(int(a.sweep.split(",")[-1])))
+        for kind in a.row_orders.split(","):
+            for h in (g, gu, gi):
+                if kind == "none":
+                    h.use_degree_order(False)
+                elif kind == "degree":
+                    h.use_degree_order(False); h.use_degree_order(True)
+                else:
+                    h.row_order = locality_order(h, kind); h._struct = None
+            ref = g.spmm(X, variant=0) if kind == a.row_orders.split(",")[0] else ref
+            err = float((g.spmm(X, variant=v) - ref).abs().max())
+            t_plain = timeit(lambda: g.spmm(X, Y=Y, variant=v))
+            t_u = timeit(lambda: gu.spmm(X, Y=Y[:U], variant=v))
+            t_i = timeit(lambda: gi.spmm(X, Y=Y[U:], variant=v))
+            print(f"row order {kind:9s} chunk {chunk} variant {v}: plain {t_plain:.3f} ms | user rows {t_u:.3f} ms | item rows {t_i:.3f} ms | max diff vs first {err:.2e}", flush=True)
+        return
     for chunk in chunks:
         for sweep in [bool(int(x)) for x in a.sweep.split(",")]:
             for h in (g, gu, gi):
