@@ -248,11 +248,19 @@ static int groups_per_block(int d) {
   return BPR_THREADS / G;
 }
 
+// The vector kernels move rows with 128-bit loads / reductions: every table must start on a 16-byte boundary (rows then do,
+// d % 4 == 0); anything else takes the scalar kernel instead of a misaligned-address fault.
+static bool bpr_needs_scalar(const lgb_bpr_args& a) {
+  const uintptr_t ptrs = (uintptr_t)a.uf | (uintptr_t)a.u0 | (uintptr_t)a.pf | (uintptr_t)a.p0 | (uintptr_t)a.nf | (uintptr_t)a.n0 |
+                         (uintptr_t)a.duf | (uintptr_t)a.du0 | (uintptr_t)a.dpf | (uintptr_t)a.dp0 | (uintptr_t)a.dnf | (uintptr_t)a.dn0;
+  return a.d % 4 != 0 || (ptrs & 15) != 0;
+}
+
 template <bool INDEXED>
-static int launch_bpr(const BprParams& p, cudaStream_t stream) {
+static int launch_bpr(const BprParams& p, bool scalar, cudaStream_t stream) {
   const unsigned nb = (unsigned)p.nblocks;
   const int d4 = p.d4;
-  if (p.a.d % 4 != 0) bpr_scalar_kernel<INDEXED><<<nb, BPR_THREADS, 0, stream>>>(p);
+  if (scalar) bpr_scalar_kernel<INDEXED><<<nb, BPR_THREADS, 0, stream>>>(p);
   else if (d4 <= 8) bpr_kernel<8, 1, INDEXED><<<nb, BPR_THREADS, 0, stream>>>(p);
   else if (d4 <= 16) bpr_kernel<16, 1, INDEXED><<<nb, BPR_THREADS, 0, stream>>>(p);
   else if (d4 <= 32) bpr_kernel<32, 1, INDEXED><<<nb, BPR_THREADS, 0, stream>>>(p);
@@ -287,10 +295,11 @@ int lgb_bpr(const lgb_bpr_args* a, void* stream_) {
   BprParams p;
   p.a = *a;
   p.d4 = a->d / 4;
-  const int gpb = groups_per_block(a->d);
+  const bool scalar = bpr_needs_scalar(*a);
+  const int gpb = scalar ? BPR_THREADS / 32 : groups_per_block(a->d);
   p.nblocks = (a->B + gpb - 1) / gpb;
   LGB_REQUIRE(p.nblocks < (1ll << 31), LGB_ERANGE, "lgb_bpr: grid too large");
-  int rc = n_idx ? launch_bpr<true>(p, stream) : launch_bpr<false>(p, stream);
+  int rc = n_idx ? launch_bpr<true>(p, scalar, stream) : launch_bpr<false>(p, scalar, stream);
   if (rc) return rc;
   if (a->loss) {
     bpr_finalize_kernel<<<1, 1024, 0, stream>>>(a->ws, p.nblocks, a->B_norm > 0 ? a->B_norm : a->B, a->lambda, a->loss);

@@ -126,6 +126,11 @@ edge_mlp2_fwd_kernel(const float* __restrict__ pu, const float* __restrict__ pi,
   if (lane == 0) out[e] = acc + (b2 ? b2[0] : 0.f);
 }
 
+// the kernels above take the 128-bit path whenever the widths are multiples of four: the tables must then be 16-byte aligned
+static inline bool edge_aligned(int wa, int wb, const void* a, const void* b, const void* c, const void* d2) {
+  return ((wa | wb) & 3) != 0 || ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d2) & 15) == 0);
+}
+
 static inline unsigned edge_blocks(int64_t L) { return (unsigned)((L + DEC_WARPS - 1) / DEC_WARPS); }
 
 }  // namespace lgb
@@ -139,6 +144,7 @@ int lgb_edge_concat_fwd(const float* zu, const float* zi, const int64_t* row, co
   LGB_REQUIRE(L >= 0 && du > 0 && di > 0 && (L == 0 || (zu && zi && row && col && out)), LGB_EINVAL,
               "lgb_edge_concat_fwd: bad argument");
   if (L == 0) return LGB_OK;
+  LGB_REQUIRE(edge_aligned(du, di, zu, zi, out, nullptr), LGB_EINVAL, "lgb_edge_concat_fwd: zu / zi / out must be 16-byte aligned when du, di %% 4 == 0");
   edge_concat_fwd_kernel<<<edge_blocks(L), DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(zu, zi, row, col, L, du, di, out);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
@@ -149,6 +155,7 @@ int lgb_edge_concat_bwd(const float* gout, const int64_t* row, const int64_t* co
   LGB_REQUIRE(L >= 0 && du > 0 && di > 0 && (L == 0 || (gout && row && col)), LGB_EINVAL,
               "lgb_edge_concat_bwd: bad argument");
   if (L == 0 || (!dzu && !dzi)) return LGB_OK;
+  LGB_REQUIRE(edge_aligned(du, di, gout, dzu, dzi, nullptr), LGB_EINVAL, "lgb_edge_concat_bwd: gout / dzu / dzi must be 16-byte aligned when du, di %% 4 == 0");
   edge_concat_bwd_kernel<<<edge_blocks(L), DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(gout, row, col, L, du, di, dzu, dzi);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
@@ -158,6 +165,7 @@ int lgb_edge_dot_fwd(const float* zu, const float* zi, const int64_t* row, const
                      float* out, void* stream) {
   LGB_REQUIRE(L >= 0 && d > 0 && (L == 0 || (zu && zi && row && col && out)), LGB_EINVAL, "lgb_edge_dot_fwd: bad argument");
   if (L == 0) return LGB_OK;
+  LGB_REQUIRE(edge_aligned(d, d, zu, zi, nullptr, nullptr), LGB_EINVAL, "lgb_edge_dot_fwd: zu / zi must be 16-byte aligned when d %% 4 == 0");
   edge_dot_fwd_kernel<<<edge_blocks(L), DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(zu, zi, row, col, L, d, out);
   LGB_LAUNCH_CHECK();
   return LGB_OK;
@@ -167,6 +175,7 @@ int lgb_edge_dot_bwd(const float* zu, const float* zi, const int64_t* row, const
                      int64_t L, int32_t d, float* dzu, float* dzi, void* stream) {
   LGB_REQUIRE(L >= 0 && d > 0 && (L == 0 || (zu && zi && row && col && gout)), LGB_EINVAL, "lgb_edge_dot_bwd: bad argument");
   if (L == 0 || (!dzu && !dzi)) return LGB_OK;
+  LGB_REQUIRE(edge_aligned(d, d, zu, zi, dzu, dzi), LGB_EINVAL, "lgb_edge_dot_bwd: zu / zi / dzu / dzi must be 16-byte aligned when d %% 4 == 0");
   edge_dot_bwd_kernel<<<edge_blocks(L), DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(zu, zi, row, col, gout, L, d, dzu, dzi);
   LGB_LAUNCH_CHECK();
   return LGB_OK;

@@ -383,3 +383,4 @@ test_device_sampler_distribution_and_validity = TZ.test_device_sampler_distribut
 test_acceptance_ranking_model_learns = TZ.test_acceptance_ranking_model_learns
 test_reverse_edge_type_shares_the_transposed_csr = TZ.test_reverse_edge_type_shares_the_transposed_csr
 test_topk_tiled_scoring_is_bit_identical = TZ.test_topk_tiled_scoring_is_bit_identical
+test_bpr_misaligned_tables_take_the_scalar_kernel = TZ.test_bpr_misaligned_tables_take_the_scalar_kernel

@@ -409,3 +409,31 @@ def test_device_sampler_distribution_and_validity(cuda_dev):
     assert len(seen_edges) > 0.7 * len(pos)                # 5120 uniform draws over <= 900 distinct edges
     u, p, n = lg.sample_mini_batch_device(64, ei.to(cuda_dev))
     assert all((a, b) in pos and (a, c) not in pos for a, b, c in zip(u.tolist(), p.tolist(), n.tolist()))
+
+
+def test_bpr_misaligned_tables_take_the_scalar_kernel(cuda_dev):
+    """Tables that do not start on a 16-byte boundary (a view at an odd float offset of a larger buffer) must not reach the
+    128-bit kernels: same loss and gradients as the aligned call."""
+    from oracle import lightgcn_oracle as lo
+    U, I, d, B, lam = 40, 30, 8, 50, 1e-3
+    gen = torch.Generator().manual_seed(9)
+    N = U + I
+    base = torch.randn(2 * N * d + 4, generator=gen).to(cuda_dev)
+    Ef = base[1:1 + N * d].view(N, d)                      # starts 4 bytes into the allocation
+    E0 = base[N * d + 3:N * d + 3 + N * d].view(N, d)
+    assert Ef.data_ptr() % 16 != 0 and E0.data_ptr() % 16 != 0
+    u = torch.randint(0, U, (B,), generator=gen).to(cuda_dev)
+    p = torch.randint(0, I, (B,), generator=gen).to(cuda_dev)
+    n = torch.randint(0, I, (B,), generator=gen).to(cuda_dev)
+    loss = torch.empty((), device=cuda_dev)
+    g = torch.zeros(N, d, device=cuda_dev)
+    lg.bpr_indexed(Ef, E0, U, u, p, n, lam, loss=loss, dE_f=g)
+    Efa, E0a = Ef.clone(), E0.clone()
+    loss_a = torch.empty((), device=cuda_dev)
+    ga = torch.zeros(N, d, device=cuda_dev)
+    lg.bpr_indexed(Efa, E0a, U, u, p, n, lam, loss=loss_a, dE_f=ga)
+    torch.testing.assert_close(loss, loss_a, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(g, ga, rtol=1e-5, atol=1e-8)
+    want = lo.bpr_loss(Efa.cpu()[u.cpu()], E0a.cpu()[u.cpu()], Efa.cpu()[U + p.cpu()], E0a.cpu()[U + p.cpu()],
+                       Efa.cpu()[U + n.cpu()], E0a.cpu()[U + n.cpu()], lam)
+    torch.testing.assert_close(loss.cpu(), want, rtol=1e-5, atol=1e-7)
