@@ -368,7 +368,6 @@ def test_lightgcn_small_batch_rowsparse_backward(cuda_dev, wiring, d, monkeypatc
              u=users[pick], p=items[pick], n=torch.randint(0, I, (B,), generator=gen))
     rowptr, cc, _ = lo.csr_from_coo(row, col, n, n)
     o_loss, o_gu, o_gi, o_uf, o_if = lo.train_iteration(Wu, Wi, rowptr, cc, K, c["u"], c["p"], c["n"], lam)
-    monkeypatch.setattr(lg.csr, "DEFAULT_CHUNK", 128)
     calls = []
     real = DeviceCSR.spmm
     monkeypatch.setattr(DeviceCSR, "spmm", lambda self, *a, **k: (calls.append(k.get("x_rows") is not None), real(self, *a, **k))[1])
