@@ -587,6 +587,14 @@ def run_ours(args):
                 "dram_frac": (traffic / 1e9) / (avg_ms * 1e-3) / peak if (traffic and avg_ms) else None,
                 "traffic_source": cap["source"] if cap else "no ncu capture of this exact configuration (workload, degree, d, n_gpus, plan)",
                 "l2_hit_pct": cap.get("lts_hit_pct") if cap else None, "l1_hit_pct": cap.get("l1_hit_pct") if cap else None,
+                # what bounds the launch once the rows come from L2: bytes that cross L2 -> SM (ncu l1tex__m_xbar2l1tex_read_bytes of
+                # the same plan) / live launch time; ncu rates it against 2 sectors / clk / L2 slice, B300_MICROARCH.md measures
+                # ~6 300 B / clk (~12.4 TB/s at 1.965 GHz) as what the L2 -> SM path sustains
+                "l2_to_sm": ({"bytes_per_launch": cap["l2_to_sm_bytes_per_call"],
+                              "GBps": cap["l2_to_sm_bytes_per_call"] / 1e9 / (avg_ms * 1e-3),
+                              "frac_of_sustained_12400_GBps": cap["l2_to_sm_bytes_per_call"] / 1e9 / (avg_ms * 1e-3) / 12400.0,
+                              "ncu_pct_of_l2_read_peak": cap.get("l2_read_pct_of_ncu_peak")}
+                             if (cap and cap.get("l2_to_sm_bytes_per_call") and avg_ms) else None),
                 "compulsory_floor_bytes_per_launch": floor,
                 "traffic_over_floor": traffic / floor if (traffic and floor) else None,
                 "plan": plan,
