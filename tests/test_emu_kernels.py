@@ -51,6 +51,7 @@ def test_spmm_fused_stage2_bit_identical(cuda_dev, variant, d, monkeypatch):
 
 
 test_lightgcn_small_batch_rowsparse_backward = TL.test_lightgcn_small_batch_rowsparse_backward
+test_spmm_rowsparse_random_shapes = TL.test_spmm_rowsparse_random_shapes
 test_lightgcn_against_reference_golden = TL.test_lightgcn_against_reference_golden
 test_lightgcn_against_oracle = TL.test_lightgcn_against_oracle
 test_bpr_against_reference_golden = TL.test_bpr_against_reference_golden

@@ -216,6 +216,38 @@ def test_spmm_rowsparse_matches_dense(cuda_dev, d):
         g.spmm(Xd, x_rows=bm[:2])                                                  # bitmap shorter than the operand
 
 
+def test_spmm_rowsparse_random_shapes(cuda_dev):
+    """Seeded sweep over small random shapes for lgb_spmm_rowsparse: bitmap sizes that are not multiples of 32, empty rows,
+    duplicate entries, no plan / tiny slices (many segments), every hit density from none to all, both slice orders, resid
+    with and without its own bitmap -- always the dense kernel's answer."""
+    gen = torch.Generator().manual_seed(2024)
+    for case in range(24):
+        n_rows = int(torch.randint(1, 90, (1,), generator=gen))
+        n_cols = int(torch.randint(1, 130, (1,), generator=gen))
+        nnz = int(torch.randint(0, 1500, (1,), generator=gen))
+        d = [4, 8, 20, 32, 48, 64][case % 6]
+        chunk = [0, 4, 16, 64][(case // 6) % 4]
+        row = (torch.rand(nnz, generator=gen) ** 3 * n_rows).long().clamp(max=n_rows - 1)
+        col = torch.randint(0, n_cols, (nnz,), generator=gen)
+        g = DeviceCSR.from_coo(row.to(cuda_dev), col.to(cuda_dev), n_rows, n_cols, chunk=chunk)
+        g = g.with_values(torch.rand(nnz, generator=gen).to(cuda_dev) + 0.5)
+        g.use_sweep_order(case % 2 == 0)
+        density = [0.0, 0.05, 0.5, 1.0][case % 4]
+        flagged = torch.rand(n_cols, generator=gen) < density
+        X = torch.randn(n_cols, d, generator=gen) * flagged[:, None]
+        ids = torch.nonzero(flagged).view(-1)
+        bm = lg.rows_bitmap(n_cols, ((ids.to(cuda_dev), 0),), cuda_dev)
+        r_flag = torch.rand(n_rows, generator=gen) < 0.3
+        R = torch.randn(n_rows, d, generator=gen) * r_flag[:, None]
+        rbm = lg.rows_bitmap(n_rows, ((torch.nonzero(r_flag).view(-1).to(cuda_dev), 0),), cuda_dev)
+        Xd, Rd = X.to(cuda_dev), R.to(cuda_dev)
+        what = f"case {case}: {n_rows}x{n_cols} nnz={nnz} d={d} chunk={chunk} density={density}"
+        want = g.spmm(Xd, resid=Rd)
+        torch.testing.assert_close(g.spmm(Xd, resid=Rd, x_rows=bm), want, rtol=1e-5, atol=1e-6, msg=what)
+        torch.testing.assert_close(g.spmm(Xd, resid=Rd, x_rows=bm, resid_rows=rbm), want, rtol=1e-5, atol=1e-6, msg=what)
+        torch.testing.assert_close(g.spmm(Xd, x_rows=bm, mean=True), g.spmm(Xd, mean=True), rtol=1e-5, atol=1e-6, msg=what)
+
+
 def test_spmm_fused_epilogue_and_degree_order(cuda_dev):
     n, nnz, d = 500, 20000, 64
     row, col = random_graph(5, n, n, nnz, skew=True)
