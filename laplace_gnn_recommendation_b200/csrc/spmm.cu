@@ -957,6 +957,7 @@ __global__ void __launch_bounds__(128) spmm_long_reduce_tree_kernel(const SpmmPa
     if (lane < TREE_CB && c0 + lane < d4) st_f4(part2 + (size_t)seg * d4 + c0 + lane, pick_col(v, lane));
   }
   __threadfence();
+  __syncwarp();                                      // EVERY lane's stores are fenced before lane 0 takes the ticket
   int ticket = 0;
   if (lane == 0) ticket = atomicAdd(p.tickets + L, 1);
   ticket = __shfl_sync(FULL_MASK, ticket, 0);
@@ -999,7 +1000,8 @@ __device__ __forceinline__ float4 fuse_pick(const float4 (&v)[FUSE_CB], int lane
 }
 
 __device__ __forceinline__ void slice_done(const SpmmParams& p, int64_t t, int lane) {
-  __threadfence();                                   // partial row t is visible device-wide before the ticket is taken
+  __threadfence();                                   // partial row t is visible device-wide before the ticket is taken ...
+  __syncwarp();                                      // ... by lane 0, on behalf of EVERY lane that stored a piece of it
   const int seg = p.task_seg[t];
   const int t0 = p.seg_t0[seg], t1 = p.seg_t1[seg];
   int ticket = 0;
@@ -1028,6 +1030,7 @@ __device__ __forceinline__ void slice_done(const SpmmParams& p, int64_t t, int l
     if (lane < FUSE_CB && c0 + lane < d4) st_f4(part2 + (size_t)seg * d4 + c0 + lane, fuse_pick(v, lane));
   }
   __threadfence();
+  __syncwarp();
   if (lane == 0) ticket = atomicAdd(p.tickets + L, 1);
   ticket = __shfl_sync(FULL_MASK, ticket, 0);
   if (ticket != nseg - 1) return;
