@@ -607,7 +607,17 @@ class ShardedLightGCN:
         complete item-row residual (identical on every rank).  rows_u / rows_i: optional bitmaps (ops.rows_bitmap) of the rows
         of ru / ri that may be non-zero."""
         if self.K == 0:
-            self.grad_users.copy_(ru); self.grad_items.copy_(ri)
+            # no propagation: the item-row gradient is the BPR scatter itself.  Every rank computed it, but with atomics, whose
+            # order (hence the last bit of a row that received three or more contributions) is not the same everywhere: all
+            # ranks adopt rank 0's bits through the exchange (x + 0 + ... + 0), like the K >= 1 path does for its residual
+            self.grad_users.copy_(ru)
+            yi = self._yi[0]
+            if self.rank == 0:
+                yi.copy_(ri)
+            else:
+                self.ops.zero(yi)
+            self.ops.exchange_async(yi, channel=0).wait()
+            self.grad_items.copy_(yi)
             return self.grad_users, self.grad_items
         self._propagate(ru, ri, resid_u=ru, resid_i=ri, last_u=self.grad_users, rows_u=rows_u, rows_i=rows_i)
         return self.grad_users, self.grad_items
